@@ -1,0 +1,149 @@
+"""
+Synthetic scenario batches (ego start pose x dynamic-obstacle set) for the batched planning tick.
+
+The reference has no scenario generator -- its only fixtures are the static dummy object of
+/root/reference/graph_ltpl/testing_tools/src/objectlist_dummy.py:175-176 and the start pose of
+/root/reference/main_min_example.py:63-67.  The batches here follow SURVEY.md section 8(d) (configs 2 / 4 / 5):
+ego placed on the race line at a uniformly drawn arc length, 1..n dynamic objects 30..280 m ahead with a uniformly
+drawn lateral offset inside the track, object dicts in exactly the format ``Graph_LTPL.calc_paths`` consumes
+(/root/reference/graph_ltpl/data_objects/ObjectListInterface.py:75-141).
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from .lattice import import_globtraj_csv
+
+DEFAULT_SEED = 20260924
+OBJ_FIELDS = ("X", "Y", "theta", "v", "length")
+
+
+@dataclass
+class ScenarioBatch:
+    """SoA scenario batch.  obj[:, k, :] = (X, Y, theta, v, length); entries k >= n_obj[b] are ignored."""
+    pos: np.ndarray        # (B, 2) float64
+    heading: np.ndarray    # (B,)   float64
+    vel: np.ndarray        # (B,)   float64
+    n_obj: np.ndarray      # (B,)   int32
+    obj: np.ndarray        # (B, K, 5) float64
+
+    @property
+    def size(self) -> int:
+        return int(self.pos.shape[0])
+
+    def object_list(self, b: int) -> list:
+        """object dicts of scenario b in the reference's format (OLI:96-141)."""
+        out = []
+        for k in range(int(self.n_obj[b])):
+            x, y, th, v, ln = (float(a) for a in self.obj[b, k])
+            out.append({'id': k + 1, 'type': 'physical', 'X': x, 'Y': y, 'theta': th, 'v': v, 'length': ln,
+                        'width': 2.5})
+        return out
+
+    def subset(self, idx) -> "ScenarioBatch":
+        idx = np.asarray(idx)
+        return ScenarioBatch(self.pos[idx].copy(), self.heading[idx].copy(), self.vel[idx].copy(),
+                             self.n_obj[idx].copy(), self.obj[idx].copy())
+
+    def shard(self, rank: int, world: int) -> "ScenarioBatch":
+        """scenario i goes to rank i % world."""
+        return self.subset(np.arange(rank, self.size, world))
+
+    @staticmethod
+    def from_object_lists(pos, heading, vel, object_lists, k_max=None) -> "ScenarioBatch":
+        b = len(object_lists)
+        n_obj = np.array([len(o) if o is not None else 0 for o in object_lists], dtype=np.int32)
+        k = int(max(1, n_obj.max() if b else 1)) if k_max is None else int(k_max)
+        obj = np.zeros((b, k, 5))
+        for i, ol in enumerate(object_lists):
+            for j, o in enumerate(ol or []):
+                if 'prediction' in o:
+                    raise NotImplementedError("batched scenarios use the reference's built-in 0.2 s constant-velocity "
+                                              "prediction (OLI:121-127); explicit 'prediction' arrays are not batched")
+                obj[i, j] = [o['X'], o['Y'], o['theta'], o['v'], o['length']]
+        return ScenarioBatch(np.asarray(pos, dtype=np.float64).reshape(b, 2),
+                             np.asarray(heading, dtype=np.float64).reshape(b),
+                             np.asarray(vel, dtype=np.float64).reshape(b), n_obj, obj)
+
+
+class Track(object):
+    """Full-resolution track / race line arrays of a 12-column global trajectory CSV."""
+
+    def __init__(self, globtraj_input_path: str):
+        t = import_globtraj_csv(globtraj_input_path)
+        self.refline = t["refline"]
+        self.normvec = t["normvec"]
+        self.w_right = t["width_right"]
+        self.w_left = t["width_left"]
+        self.alpha = t["alpha"]
+        self.s = t["s_rl"][:-1]
+        self.length = float(t["s_rl"][-1])
+        self.psi = t["psi_rl"]
+        self.vel = t["vel_rl"]
+        self.raceline = self.refline + self.normvec * self.alpha[:, None]
+
+    def _seg(self, s):
+        s = np.mod(s, self.length)
+        i = np.clip(np.searchsorted(self.s, s, side="right") - 1, 0, self.s.size - 1)
+        j = (i + 1) % self.s.size
+        s_next = np.where(j == 0, self.length, self.s[j])
+        f = (s - self.s[i]) / (s_next - self.s[i])
+        return i, j, f
+
+    def raceline_pose(self, s):
+        """(x, y), heading, race line velocity at arc length s (linear interpolation between race line points)."""
+        i, j, f = self._seg(s)
+        xy = self.raceline[i] * (1.0 - f)[:, None] + self.raceline[j] * f[:, None]
+        dpsi = np.mod(self.psi[j] - self.psi[i] + np.pi, 2 * np.pi) - np.pi
+        psi = np.mod(self.psi[i] + f * dpsi + np.pi, 2 * np.pi) - np.pi
+        vel = self.vel[i] * (1.0 - f) + self.vel[j] * f
+        return xy, psi, vel
+
+    def frame(self, s):
+        """reference-line point, normal vector and track widths at (the race line point preceding) arc length s."""
+        i, _, _ = self._seg(s)
+        return self.refline[i], self.normvec[i], self.w_left[i], self.w_right[i], self.psi[i], self.vel[i]
+
+
+def make_scenarios(track: Track, batch: int, seed: int = DEFAULT_SEED, n_obj_min: int = 1, n_obj_max: int = 3,
+                   k_max: int = None, obj_margin: float = 1.4, ahead=(30.0, 280.0)) -> ScenarioBatch:
+    """SURVEY 8(d) config 2 (n_obj 1..3) / config 4 (n_obj_min = n_obj_max = 5)."""
+    rng = np.random.default_rng(seed)
+    s_e = rng.uniform(0.0, track.length, size=batch)
+    pos, heading, v_rl = track.raceline_pose(s_e)
+    vel = rng.uniform(5.0, np.maximum(0.9 * v_rl, 5.0))
+    n_obj = rng.integers(n_obj_min, n_obj_max + 1, size=batch).astype(np.int32)
+    k = int(n_obj_max if k_max is None else k_max)
+    obj = np.zeros((batch, k, 5))
+    ds = rng.uniform(ahead[0], ahead[1], size=(batch, k))
+    u = rng.uniform(0.0, 1.0, size=(batch, k))
+    uv = rng.uniform(0.0, 1.0, size=(batch, k))
+    for j in range(k):
+        ref, nv, wl, wr, psi, vrl = track.frame(s_e + ds[:, j])
+        lo = -(wl - obj_margin)
+        hi = (wr - obj_margin)
+        d = lo + u[:, j] * (hi - lo)
+        obj[:, j, 0:2] = ref + nv * d[:, None]
+        obj[:, j, 2] = psi
+        obj[:, j, 3] = uv[:, j] * 0.5 * vrl
+        obj[:, j, 4] = 5.0
+    mask = np.arange(k)[None, :] >= n_obj[:, None]
+    obj[mask] = 0.0
+    return ScenarioBatch(pos=pos, heading=heading, vel=vel, n_obj=n_obj, obj=obj)
+
+
+def make_velocity_microbench(n_paths: int, n_points: int, seed: int = DEFAULT_SEED) -> dict:
+    """smooth random curvature profiles for the stand-alone forward/backward solver."""
+    rng = np.random.default_rng(seed)
+    el = 2.5 + rng.uniform(-0.1, 0.1, size=(n_paths, n_points)).astype(np.float64)
+    s = np.cumsum(el, axis=1) - el
+    amp = rng.uniform(0.0, 0.04 / 3.0, size=(n_paths, 3, 1))
+    wl = rng.uniform(60.0, 600.0, size=(n_paths, 3, 1))
+    ph = rng.uniform(0.0, 2 * np.pi, size=(n_paths, 3, 1))
+    kappa = np.sum(amp * np.sin(2 * np.pi * s[:, None, :] / wl + ph), axis=1)
+    return dict(kappa=kappa, el=el, v_start=rng.uniform(0.0, 40.0, size=n_paths),
+                v_end=rng.uniform(0.0, 40.0, size=n_paths), v_max=60.0, gg=(5.0, 5.0), drag_coeff=0.85, m_veh=1000.0,
+                dyn_model_exp=1.0)

@@ -1,0 +1,247 @@
+"""
+TEST INFRASTRUCTURE -- golden-vector generator.
+
+Runs the UNMODIFIED reference Python (/root/reference/graph_ltpl, commit 18763ef9) in THIS container and stores its
+inputs/outputs as small fixtures under tests/golden/.  The reference cannot be imported as is:
+  * `igraph` and `trajectory_planning_helpers` are absent  -> oracle/shims/{igraph,trajectory_planning_helpers} (restated)
+  * `zmq` absent (objectlist_dummy.py:2)                    -> oracle/shims/zmq (empty)
+  * NumPy-2 removals `np.object` (main_offline_callback.py:160) and `np.Inf` (MOPG:96) -> aliased below
+Everything else (Graph_LTPL, OnlineTrajectoryHandler, main_online_path_gen, gen_local_node_template, GraphBase,
+ObjectListInterface, VpForwardBackward, calc_vel_profile_follow, the whole offline pipeline ...) is the reference's own
+code, executed verbatim.  /root/reference does not travel to the GPU box, hence the committed fixtures.
+
+Usage (from the repo root):   python -m oracle.gen_golden [--quick]
+"""
+
+import argparse
+import configparser
+import os
+import sys
+import time
+
+os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+GOLDEN = os.path.join(REPO, 'tests', 'golden')
+ACTIONS = ("straight", "follow", "left", "right")
+
+
+def load_reference():
+    """import the reference package on top of the shims; returns the `graph_ltpl` module."""
+    if not os.path.isdir(REF):
+        raise RuntimeError("/root/reference is not available on this box")
+    for p in (REPO, os.path.join(REPO, 'oracle', 'shims'), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    if not hasattr(np, 'object'):
+        np.object = object
+    if not hasattr(np, 'Inf'):
+        np.Inf = np.inf
+    import graph_ltpl  # noqa
+    import graph_ltpl.Graph_LTPL as gl
+    gl.FORCE_RECALC = False
+    return graph_ltpl
+
+
+def write_offline_ini(path, overrides):
+    cfg = configparser.ConfigParser()
+    cfg.read(os.path.join(REF, 'params', 'ltpl_config_offline.ini'))
+    for key, val in (overrides or {}).items():
+        for sec in cfg.sections():
+            if key in cfg[sec]:
+                cfg[sec][key] = str(val)
+    with open(path, 'w') as fh:
+        cfg.write(fh)
+
+
+def make_ltpl(graph_ltpl, tag, overrides=None):
+    ini = '/tmp/golden_offline_%s.ini' % tag
+    write_offline_ini(ini, overrides)
+    path_dict = {'globtraj_input_path': REF + "/inputs/traj_ltpl_cl/traj_ltpl_cl_monteblanco.csv",
+                 'graph_store_path': "/tmp/golden_graph_%s.pckl" % tag,
+                 'ltpl_offline_param_path': ini,
+                 'ltpl_online_param_path': REF + "/params/ltpl_config_online.ini"}
+    ltpl = graph_ltpl.Graph_LTPL.Graph_LTPL(path_dict=path_dict, visual_mode=False, log_to_file=False)
+    t0 = time.time()
+    ltpl.graph_init()
+    print("[%s] reference graph_init: %.1f s" % (tag, time.time() - t0))
+    return ltpl, path_dict
+
+
+def ax_max_machines_table():
+    tab = np.loadtxt(REF + "/inputs/veh_dyn_info/ax_max_machines.csv", comments='#', delimiter=',')
+    return np.vstack((tab, [100.0, tab[-1, 1]]))
+
+
+def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False):
+    """one stateless planning tick through the reference's public API (main_min_example.py:69-104 flow)."""
+    name = '_Graph_LTPL__nmbr_export_points'
+    keep = getattr(ltpl, name)
+    if full:
+        setattr(ltpl, name, 10 ** 6)
+    try:
+        out_of_track = ltpl.set_startpos(pos_est=np.array(pos), heading_est=float(heading), vel_est=float(vel))
+        rec = {'out_of_track': bool(out_of_track)}
+        if out_of_track:
+            return rec
+        oth = ltpl._Graph_LTPL__oth
+        path_dict = ltpl.calc_paths(prev_action_id="straight", object_list=object_list)
+        rec['paths'] = {k: [np.array(a) for a in v] for k, v in path_dict.items()}
+        rec['nodes'] = {k: [list(map(list, n)) for n in v]
+                        for k, v in oth._OnlineTrajectoryHandler__last_action_set_nodes.items()}
+        rec['node_idx'] = {k: [np.array(n) for n in v]
+                           for k, v in oth._OnlineTrajectoryHandler__last_action_set_node_idx.items()}
+        rec['coeff'] = {k: [np.array(n) for n in v]
+                        for k, v in oth._OnlineTrajectoryHandler__last_action_set_coeff.items()}
+        rec['red_len'] = {k: list(v) for k, v in oth._OnlineTrajectoryHandler__last_action_set_red_len.items()}
+        rec['closest_obj_index'] = oth._OnlineTrajectoryHandler__closest_obj_index
+        rec['start_node'] = list(oth._OnlineTrajectoryHandler__start_node)
+        traj, ids, _ = ltpl.calc_vel_profile(pos_est=np.array(pos), vel_est=float(vel), **vel_kwargs)
+        rec['traj'] = {k: [np.array(a) for a in v] for k, v in traj.items()}
+        rec['ids'] = dict(ids)
+        return rec
+    finally:
+        setattr(ltpl, name, keep)
+
+
+def pack_ticks(recs, pmax=None):
+    """ragged per-scenario records -> padded arrays."""
+    n = len(recs)
+    hmax = 1
+    for r in recs:
+        for k in r.get('paths', {}):
+            pmax = max(pmax or 0, r['paths'][k][0].shape[0])
+            hmax = max(hmax, len(r['nodes'][k][0]))
+    out = dict(
+        out_of_track=np.array([r['out_of_track'] for r in recs]),
+        path=np.zeros((n, 4, pmax, 5)), path_len=np.zeros((n, 4), dtype=np.int32),
+        nodes=np.full((n, 4, hmax, 2), -1, dtype=np.int32), nodes_len=np.zeros((n, 4), dtype=np.int32),
+        node_idx=np.full((n, 4, hmax), -1, dtype=np.int32),
+        coeff=np.zeros((n, 4, hmax, 8)), coeff_len=np.zeros((n, 4), dtype=np.int32),
+        red_len=np.zeros((n, 4), dtype=np.int8),
+        traj=np.zeros((n, 4, pmax, 7)), traj_len=np.zeros((n, 4), dtype=np.int32),
+        traj_id=np.full((n, 4), -1, dtype=np.int32),
+        closest_obj_index=np.full(n, -1, dtype=np.int32), start_node=np.full((n, 2), -1, dtype=np.int32))
+    for i, r in enumerate(recs):
+        if r['out_of_track']:
+            continue
+        out['closest_obj_index'][i] = -1 if r['closest_obj_index'] is None else r['closest_obj_index']
+        out['start_node'][i] = r['start_node']
+        for a, act in enumerate(ACTIONS):
+            if act in r['paths'] and len(r['paths'][act]) and np.size(r['paths'][act][0]):
+                p = r['paths'][act][0]
+                out['path'][i, a, :p.shape[0]] = p
+                out['path_len'][i, a] = p.shape[0]
+                nd = [[-1 if v is None else int(v) for v in pair] for pair in r['nodes'][act][0]]
+                out['nodes'][i, a, :len(nd)] = nd
+                out['nodes_len'][i, a] = len(nd)
+                ni = r['node_idx'][act][0]
+                out['node_idx'][i, a, :len(ni)] = ni
+                c = r['coeff'][act][0]
+                out['coeff'][i, a, :c.shape[0]] = c
+                out['coeff_len'][i, a] = c.shape[0]
+                out['red_len'][i, a] = int(bool(r['red_len'][act][0]))
+            if act in r['traj'] and len(r['traj'][act]):
+                t = r['traj'][act][0]
+                out['traj'][i, a, :t.shape[0]] = t
+                out['traj_len'][i, a] = t.shape[0]
+                out['traj_id'][i, a] = r['ids'][act]
+    return out
+
+
+def lattice_fixture(graph_ltpl, ltpl, n_edge_samples=300, seed=7):
+    """compact description of the reference-built GraphBase (validates the product's lattice builder)."""
+    from graphbasedlocaltrajectoryplanner_b200.lattice import Lattice
+    gb = ltpl._Graph_LTPL__graph_base
+    lat = Lattice.from_graph_base(gb)
+    rng = np.random.default_rng(seed)
+    pick = np.sort(rng.choice(lat.num_edges, size=min(n_edge_samples, lat.num_edges), replace=False))
+    samp = []
+    for e in pick:
+        a0, a1 = lat.samp_off[e], lat.samp_off[e + 1]
+        samp.append(np.column_stack((lat.samp_x[a0:a1], lat.samp_y[a0:a1], lat.samp_psi[a0:a1],
+                                     lat.samp_kappa[a0:a1], lat.samp_el[a0:a1])))
+    fx = dict(num_layers=lat.num_layers, closed=lat.closed, node_off=lat.node_off, raceline_index=lat.raceline_index,
+              s_raceline=lat.s_raceline, vel_raceline=lat.vel_raceline,
+              node_xy_psi=np.column_stack((lat.node_x, lat.node_y, lat.node_psi)),
+              edge_layer_off=lat.edge_layer_off, edge_src=lat.edge_src.astype(np.int16),
+              edge_dst=lat.edge_dst.astype(np.int16), edge_cost=lat.edge_cost, edge_len=lat.edge_len,
+              samp_off=lat.samp_off, pick=pick.astype(np.int32), pick_samples=np.concatenate(samp, axis=0),
+              checksums=np.array([lat.samp_x.sum(), lat.samp_y.sum(), lat.samp_psi.sum(), lat.samp_kappa.sum(),
+                                  lat.samp_el.sum(), np.abs(lat.samp_kappa).sum()]))
+    return fx, lat
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--quick', action='store_true', help='default lattice only')
+    ap.add_argument('--n-default', type=int, default=96)
+    ap.add_argument('--n-other', type=int, default=32)
+    args = ap.parse_args()
+
+    graph_ltpl = load_reference()
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios, DEFAULT_SEED
+    os.makedirs(GOLDEN, exist_ok=True)
+    track = Track(REF + "/inputs/traj_ltpl_cl/traj_ltpl_cl_monteblanco.csv")
+    vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
+                      safety_d=30.0, incl_emerg_traj=False)
+
+    configs = [("default", {}, args.n_default, 0, 3)]
+    if not args.quick:
+        configs.append(("l216", {"lat_resolution": 1.0, "lon_straight_step": 12.0}, args.n_other, 1, 3))
+        configs.append(("l430", {"lon_curve_step": 6.0, "lon_straight_step": 6.0, "lat_resolution": 0.5},
+                        args.n_other, 5, 5))
+
+    for tag, overrides, n, omin, omax in configs:
+        ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
+        fx, lat = lattice_fixture(graph_ltpl, ltpl)
+        np.savez_compressed(os.path.join(GOLDEN, 'lattice_%s.npz' % tag), **fx)
+        print("[%s] lattice: %s" % (tag, lat.summary()))
+
+        sc = make_scenarios(track, n, seed=DEFAULT_SEED + len(tag), n_obj_min=omin, n_obj_max=omax)
+        recs, recs_full = [], []
+        t0 = time.time()
+        for b in range(sc.size):
+            ol = sc.object_list(b)
+            recs.append(run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], ol, vel_kwargs, full=False))
+            recs_full.append(run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], ol, vel_kwargs, full=True))
+        print("[%s] %d reference ticks (x2) in %.1f s" % (tag, sc.size, time.time() - t0))
+        full = pack_ticks(recs_full)
+        cut = pack_ticks(recs, pmax=full['path'].shape[2])
+        assert np.array_equal(cut['traj_len'], np.minimum(full['traj_len'], 115))
+        payload = {('full_' + k): v for k, v in full.items()}
+        payload['cut_traj_len'] = cut['traj_len']
+        payload.update(sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj, sc_obj=sc.obj,
+                       ax_max_machines=vel_kwargs['ax_max_machines'],
+                       overrides=np.array(repr(sorted(overrides.items()))))
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_%s.npz' % tag), **payload)
+        acts = {a: int((full['path_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)}
+        print("[%s] action paths: %s; trajectories: %s; reduced: %d" %
+              (tag, acts, {a: int((full['traj_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)},
+               int(full['red_len'].sum())))
+
+        if tag == "default":
+            # main_min_example.py start pose + the static dummy object of objectlist_dummy.py:175
+            refline = graph_ltpl.imp_global_traj.src.import_globtraj_csv.import_globtraj_csv(
+                import_path=path_dict['globtraj_input_path'])[0]
+            pos = refline[0, :]
+            heading = float(np.arctan2(np.diff(refline[0:2, 1]), np.diff(refline[0:2, 0]))[0] - np.pi / 2)
+            obj = {'id': 1, 'type': 'physical', 'X': 127, 'Y': 82, 'theta': 0.0, 'length': 5.0, 'width': 2.5,
+                   'v': 0.0}
+            api_default = dict()  # calc_vel_profile API defaults (LTPL:344-352)
+            r1 = [run_tick(ltpl, pos, heading, 0.0, [obj], api_default, full=True)]
+            # variant: ego ~180 m before the static object so that follow / left / right are exercised
+            p2, h2, _ = track.raceline_pose(np.array([1300.0]))
+            r2 = [run_tick(ltpl, p2[0], h2[0], 20.0, [obj], api_default, full=True)]
+            pk = pack_ticks(r1 + r2)
+            pk.update(sc_pos=np.vstack((pos, p2[0])), sc_heading=np.array([heading, h2[0]]),
+                      sc_vel=np.array([0.0, 20.0]), obj=np.array([127.0, 82.0, 0.0, 0.0, 5.0]))
+            np.savez_compressed(os.path.join(GOLDEN, 'config1_min_example.npz'), **pk)
+            print("[config1] actions:", {a: pk['path_len'][:, i].tolist() for i, a in enumerate(ACTIONS)})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,86 @@
+"""Shared helpers of the parity tests: lattice construction per golden tag, golden loading, record comparison."""
+import ast
+import functools
+import os
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(REPO, "tests", "golden")
+TRACK_CSV = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco.csv")
+OFFLINE_INI = os.path.join(REPO, "params", "ltpl_config_offline.ini")
+ONLINE_INI = os.path.join(REPO, "params", "ltpl_config_online.ini")
+ACTIONS = ("straight", "follow", "left", "right")
+
+# tolerances of BASELINE.json north_star: node sequences bit-exact; coordinates / velocity 1e-4 relative
+# (absolute floors for quantities that pass through zero: heading [rad], curvature [1/m], acceleration [m/s^2]).
+RTOL = 1e-4
+ATOL = dict(s=1e-3, x=1e-3, y=1e-3, psi=1e-4, kappa=2e-6, el=1e-4, vx=2e-3, ax=5e-3)
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+@functools.lru_cache(maxsize=None)
+def lattice_for(tag):
+    from graphbasedlocaltrajectoryplanner_b200.lattice import build_lattice
+    ov = dict(ast.literal_eval(str(golden("ticks_%s.npz" % tag)["overrides"])))
+    return build_lattice(TRACK_CSV, OFFLINE_INI, overrides=ov)
+
+
+def object_list(g, b):
+    out = []
+    for k in range(int(g["sc_n_obj"][b])):
+        x, y, th, v, ln = (float(a) for a in g["sc_obj"][b, k])
+        out.append({'id': k + 1, 'type': 'physical', 'X': x, 'Y': y, 'theta': th, 'v': v, 'length': ln, 'width': 2.5})
+    return out
+
+
+def assert_close(name, got, want, cols, ctx=""):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, "%s %s: shape %s vs %s" % (ctx, name, got.shape, want.shape)
+    for c, key in enumerate(cols):
+        d = np.abs(got[:, c] - want[:, c])
+        if key == "psi":   # headings are compared modulo 2 pi
+            d = np.abs(np.mod(got[:, c] - want[:, c] + np.pi, 2 * np.pi) - np.pi)
+        lim = ATOL[key] + RTOL * np.abs(want[:, c])
+        bad = np.nonzero(d > lim)[0]
+        assert bad.size == 0, "%s %s col %s: %d/%d rows off, worst |d|=%.3e at row %d (want %.6e got %.6e)" % (
+            ctx, name, key, bad.size, d.size, d.max(), int(np.argmax(d)), want[int(np.argmax(d)), c],
+            got[int(np.argmax(d)), c])
+
+
+def compare_record(rec, g, b, prefix="full_", ctx=""):
+    """compare one tick record (dict of dicts like oracle.tick()) against row b of a golden ticks file."""
+    ctx = "%s scenario %d" % (ctx, b)
+    assert bool(rec["out_of_track"]) == bool(g[prefix + "out_of_track"][b]), ctx
+    if rec["out_of_track"]:
+        return
+    assert list(rec["start_node"]) == g[prefix + "start_node"][b].tolist(), ctx + " start node"
+    coi = -1 if rec["closest_obj_index"] is None else int(rec["closest_obj_index"])
+    assert coi == int(g[prefix + "closest_obj_index"][b]), ctx + " closest_obj_index"
+    for a, act in enumerate(ACTIONS):
+        n_want = int(g[prefix + "path_len"][b, a])
+        has = act in rec["paths"] and len(rec["paths"][act]) > 0
+        assert has == (n_want > 0), "%s: action %s present=%s, golden len %d" % (ctx, act, has, n_want)
+        if has:
+            nodes = [[-1 if v is None else int(v) for v in pair] for pair in rec["nodes"][act][0]]
+            want_nodes = g[prefix + "nodes"][b, a, :int(g[prefix + "nodes_len"][b, a])].tolist()
+            assert nodes == want_nodes, "%s: node sequence of %s differs\n got  %s\n want %s" % (ctx, act, nodes,
+                                                                                                 want_nodes)
+            ni = np.asarray(rec["node_idx"][act][0]).tolist()
+            assert ni == g[prefix + "node_idx"][b, a, :len(ni)].tolist(), ctx + " node_idx " + act
+            assert bool(rec["red_len"][act][0]) == bool(g[prefix + "red_len"][b, a]), ctx + " red_len " + act
+            assert_close("path[%s]" % act, rec["paths"][act][0], g[prefix + "path"][b, a, :n_want],
+                         ("x", "y", "psi", "kappa", "el"), ctx)
+        t_want = int(g[prefix + "traj_len"][b, a])
+        t_has = act in rec["traj_full"] and len(rec["traj_full"][act]) > 0
+        assert t_has == (t_want > 0), "%s: trajectory %s present=%s, golden len %d" % (ctx, act, t_has, t_want)
+        if t_has:
+            # the id base (+10 per calc_vel_profile call, OTH:669) is instance state; the action code is id % 10
+            assert int(rec["ids"][act]) % 10 == int(g[prefix + "traj_id"][b, a]) % 10, ctx + " traj id " + act
+            assert_close("traj[%s]" % act, rec["traj_full"][act][0], g[prefix + "traj"][b, a, :t_want],
+                         ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+            assert rec["traj"][act][0].shape[0] == int(g["cut_traj_len"][b, a]) if "cut_traj_len" in g.files else True

@@ -1,0 +1,37 @@
+"""Pins the oracle (oracle/ltpl_oracle.py, oracle/tph_port.py) against golden vectors produced by executing the
+reference's own Python files in the build container (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+TAGS = ("default", "l216", "l430")
+
+
+def _run(tag, idx=None):
+    from oracle.ltpl_oracle import OracleLTPL
+    g = H.golden("ticks_%s.npz" % tag)
+    orc = OracleLTPL(H.lattice_for(tag))
+    vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    n = g["sc_pos"].shape[0]
+    for b in (range(n) if idx is None else idx):
+        rec = orc.tick(g["sc_pos"][b], g["sc_heading"][b], g["sc_vel"][b], H.object_list(g, b), vk)
+        H.compare_record(rec, g, b, ctx=tag)
+
+
+@pytest.mark.parametrize("tag", TAGS)
+def test_oracle_matches_reference_ticks(tag):
+    _run(tag)
+
+
+def test_oracle_config1_min_example():
+    """main_min_example.py start pose + static dummy object; API-default velocity arguments."""
+    from oracle.ltpl_oracle import OracleLTPL
+    g = H.golden("config1_min_example.npz")
+    orc = OracleLTPL(H.lattice_for("default"))
+    x, y, th, v, ln = (float(a) for a in g["obj"])
+    obj = [{'id': 1, 'type': 'physical', 'X': x, 'Y': y, 'theta': th, 'length': ln, 'width': 2.5, 'v': v}]
+    for b in range(2):
+        rec = orc.tick(g["sc_pos"][b], g["sc_heading"][b], g["sc_vel"][b], obj, {})
+        H.compare_record(rec, g, b, prefix="", ctx="config1")
+    assert int(g["path_len"][0, 0]) > 0 and int(g["path_len"][1, 1]) > 0   # straight / follow exercised
