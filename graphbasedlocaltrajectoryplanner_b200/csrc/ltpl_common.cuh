@@ -1,0 +1,225 @@
+// ltpl_common.cuh -- device-side lattice view + numerics helpers shared by all kernels (sm_100a).
+//
+// Numerics contract (DESIGN.md "Numerics"): every DECISION of the reference path (nearest-index argmins, collision
+// tests, interval tests on s-coordinates, DP relax / argmin) is taken in IEEE float64 with the same operation order as
+// NumPy executes it (this translation unit is compiled with -fmad=false, and the helpers below additionally use
+// explicit round-to-nearest intrinsics so that a later relaxation of the flag cannot change decisions).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "ltpl_b200.h"
+
+#define LTPL_FULL 0xffffffffu
+#define LTPL_PI 3.141592653589793
+#define LTPL_INF CUDART_INF
+
+// resolved device pointers of the lattice blob
+struct LatDev {
+    int L, Nn, E, S, n_glob, closed, plan_mode, max_nodes, max_window_edges;
+    double lat_offset, lat_res, step, vel_decrease_lat, veh_width, veh_length, virt_cost, min_plan_horizon;
+    const int* node_off;
+    const int* rl_idx;
+    const double* s_rl;
+    const double* vel_rl;
+    const double2* refline;
+    const double2* raceline;
+    const double2* bound1;
+    const double2* bound2;
+    const double2* center;
+    const double2* node_xy;
+    const double* node_psi;
+    const int* node_layer;
+    const int2* in_off;
+    const int* edge_layer_off;
+    const int* edge_src;
+    const int* edge_dst;
+    const double* edge_cost;
+    const double* edge_len;
+    const double* edge_psi1;
+    const int* samp_off;
+    const double2* samp_xy;
+    const double* samp_el;
+    const int* samp_edge;
+    const double* glob_rl;  // [n_glob - 1][6]
+};
+
+struct LtplLattice {
+    LtplLatticeHeader h;
+    LatDev d;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// float64 helpers with NumPy operation order
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double sq_rn(double a) { return __dmul_rn(a, a); }
+
+// np.power(ax - bx, 2) + np.power(ay - by, 2)
+__device__ __forceinline__ double dist2_rn(double ax, double ay, double bx, double by) {
+    return __dadd_rn(sq_rn(__dsub_rn(ax, bx)), sq_rn(__dsub_rn(ay, by)));
+}
+
+// get_s_coord.py:102-121
+__device__ __forceinline__ double angle3pt(double ax, double ay, double bx, double by, double cx, double cy) {
+    double ang = atan2(cy - by, cx - bx) - atan2(ay - by, ax - bx);
+    if (ang > LTPL_PI)
+        ang -= 2 * LTPL_PI;
+    else if (ang <= -LTPL_PI)
+        ang += 2 * LTPL_PI;
+    return ang;
+}
+
+// tph.normalize_psi
+__device__ __forceinline__ double normalize_psi(double psi) {
+    double a = fmod(fabs(psi), 2 * LTPL_PI);
+    double out = (psi > 0.0) ? a : ((psi < 0.0) ? -a : 0.0);
+    if (out >= LTPL_PI)
+        out -= 2 * LTPL_PI;
+    else if (out < -LTPL_PI)
+        out += 2 * LTPL_PI;
+    return out;
+}
+
+struct ArgMinD {
+    double v;
+    int i;
+};
+
+// first-minimum argmin over the warp (ties -> lower index), every lane gets the result
+__device__ __forceinline__ ArgMinD warp_argmin(double v, int i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(LTPL_FULL, v, o);
+        int oi = __shfl_xor_sync(LTPL_FULL, i, o);
+        if (ov < v || (ov == v && oi < i)) {
+            v = ov;
+            i = oi;
+        }
+    }
+    ArgMinD r;
+    r.v = v;
+    r.i = i;
+    return r;
+}
+
+// np.argmin of squared distances between pos and n points (closest_path_index.py:24-30, GIE:41-42, GB:341-345)
+__device__ __forceinline__ ArgMinD warp_closest_point(const double2* __restrict__ pts, int n, double px, double py,
+                                                      int lane) {
+    double bv = LTPL_INF;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < n; i += 32) {
+        double2 p = pts[i];
+        double d = dist2_rn(p.x, p.y, px, py);
+        if (d < bv) {
+            bv = d;
+            bi = i;
+        }
+    }
+    return warp_argmin(bv, bi);
+}
+
+// get_s_coord.py:8-99 on a CLOSED polyline with explicit s_array (s_array[0] <= 0.05, i.e. no leading-zero insertion).
+// Warp-collective; returns the s coordinate; idx_out = closest_indexes (pair)
+__device__ __forceinline__ double s_coord_closed(const double2* __restrict__ pts, const double* __restrict__ s_arr, int n,
+                                                 double px, double py, int lane, int* i0_out, int* i1_out) {
+    ArgMinD m = warp_closest_point(pts, n, px, py, lane);
+    int nb = m.i;
+    int idx1 = nb - 1;  // python negative index -> last element
+    int idx2 = nb + 1;
+    if (idx2 > n - 1) idx2 = 0;
+    int a1 = (idx1 < 0) ? idx1 + n : idx1;
+    double2 pn = pts[nb], p1 = pts[a1], p2 = pts[idx2];
+    double ang1 = fabs(angle3pt(pn.x, pn.y, px, py, p1.x, p1.y));
+    double ang2 = fabs(angle3pt(pn.x, pn.y, px, py, p2.x, p2.y));
+    double2 a, b;
+    double sbase;
+    if (ang1 > ang2) {
+        a = p1;
+        b = pn;
+        sbase = s_arr[a1];
+    } else {
+        a = pn;
+        b = p2;
+        sbase = s_arr[nb];
+    }
+    double bax = b.x - a.x, bay = b.y - a.y;
+    double t = __ddiv_rn(__dadd_rn(__dmul_rn(px - a.x, bax), __dmul_rn(py - a.y, bay)), __dadd_rn(sq_rn(bax), sq_rn(bay)));
+    double sx = __dadd_rn(a.x, __dmul_rn(t, bax));
+    double sy = __dadd_rn(a.y, __dmul_rn(t, bay));
+    double ds = sqrt(__dadd_rn(sq_rn(a.x - sx), sq_rn(a.y - sy)));
+    if (i0_out) {
+        if (ang1 >= ang2) {
+            *i0_out = idx1;
+            *i1_out = nb;
+        } else {
+            *i0_out = nb;
+            *i1_out = idx2;
+        }
+    }
+    return __dadd_rn(sbase, ds);
+}
+
+// check_inside_bounds.py:26-59 (warp-collective)
+__device__ __forceinline__ bool inside_bounds(const LatDev& lt, double px, double py, int lane) {
+    int i0, i1;
+    {
+        // get_s_coord(centerline, pos, only_index=True, closed=True)[1]
+        ArgMinD m = warp_closest_point(lt.center, lt.L, px, py, lane);
+        int nb = m.i, n = lt.L;
+        int idx1 = nb - 1, idx2 = nb + 1;
+        if (idx2 > n - 1) idx2 = 0;
+        int a1 = (idx1 < 0) ? idx1 + n : idx1;
+        double2 pn = lt.center[nb], p1 = lt.center[a1], p2 = lt.center[idx2];
+        double ang1 = fabs(angle3pt(pn.x, pn.y, px, py, p1.x, p1.y));
+        double ang2 = fabs(angle3pt(pn.x, pn.y, px, py, p2.x, p2.y));
+        if (ang1 >= ang2) {
+            i0 = a1;
+            i1 = nb;
+        } else {
+            i0 = nb;
+            i1 = idx2;
+        }
+    }
+    // np.linspace(a, b) with 50 points: y[k] = k * ((b - a) / 49) + a, y[49] = b
+    double2 c0 = lt.center[i0], c1 = lt.center[i1];
+    double stx = __ddiv_rn(c1.x - c0.x, 49.0), sty = __ddiv_rn(c1.y - c0.y, 49.0);
+    double bv = LTPL_INF;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < 50; k += 32) {
+        double cx = (k == 49) ? c1.x : __dadd_rn(__dmul_rn((double)k, stx), c0.x);
+        double cy = (k == 49) ? c1.y : __dadd_rn(__dmul_rn((double)k, sty), c0.y);
+        double d = dist2_rn(cx, cy, px, py);
+        if (d < bv) {
+            bv = d;
+            bi = k;
+        }
+    }
+    ArgMinD m = warp_argmin(bv, bi);
+    int k = m.i;
+    double2 u0 = lt.bound1[i0], u1 = lt.bound1[i1], w0 = lt.bound2[i0], w1 = lt.bound2[i1];
+    double b1x = (k == 49) ? u1.x : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(u1.x - u0.x, 49.0)), u0.x);
+    double b1y = (k == 49) ? u1.y : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(u1.y - u0.y, 49.0)), u0.y);
+    double b2x = (k == 49) ? w1.x : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(w1.x - w0.x, 49.0)), w0.x);
+    double b2y = (k == 49) ? w1.y : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(w1.y - w0.y, 49.0)), w0.y);
+    double d_track_2 = dist2_rn(b1x, b1y, b2x, b2y);
+    double d_b1_2 = dist2_rn(b1x, b1y, px, py);
+    double d_b2_2 = dist2_rn(b2x, b2y, px, py);
+    return !(d_b1_2 > d_track_2 || d_b2_2 > d_track_2);
+}
+
+// planning-range membership of a layer (GB:704-709)
+__device__ __forceinline__ bool layer_in_range(int x, int start, int end) {
+    return (start < end) ? (x >= start && x <= end) : (x >= start || x <= end);
+}
+
+// np.interp(v, xp, fp) for increasing xp (clamped at both ends)
+__device__ __forceinline__ double interp_table(double v, const double* __restrict__ xp, const double* __restrict__ fp,
+                                               int n) {
+    if (v <= xp[0]) return fp[0];
+    if (v >= xp[n - 1]) return fp[n - 1];
+    int j = 0;
+    while (j < n - 2 && v >= xp[j + 1]) ++j;
+    double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+    return slope * (v - xp[j]) + fp[j];
+}

@@ -1,0 +1,213 @@
+/*
+ * ltpl_b200.h -- C-ABI of the B200-native batched online planning path of Graph_LTPL.
+ *
+ * The reference (TUMFTM/GraphBasedLocalTrajectoryPlanner @ 18763ef9) has no FFI / plugin seam; its boundary for this
+ * path is the Python API  Graph_LTPL.set_startpos / calc_paths / calc_vel_profile  (graph_ltpl/Graph_LTPL.py:262-296,
+ * 300-340, 344-408), one level down  OnlineTrajectoryHandler.set_initial_pose / calc_paths / calc_vel_profile
+ * (graph_ltpl/online_graph/src/OnlineTrajectoryHandler.py:181-270, 289-516, 603-1040)  and  main_online_path_gen
+ * (graph_ltpl/online_graph/src/main_online_path_gen.py:11-21).  Each entry point below names the reference interface
+ * it replaces.  The binding a maintainer adds on the reference side is a ctypes stub.
+ *
+ * Conventions
+ *   - plain C, no torch types: every buffer is a raw DEVICE pointer owned by the caller (PyTorch tensors are used only
+ *     as allocators on the Python side); the library never allocates on the hot path.
+ *   - every call is asynchronous on the given CUDA stream (cudaStream_t passed as void*).
+ *   - return value: 0 = ok, < 0 = error (message via ltpl_last_error()).
+ *   - per (scenario, action slot) results carry a status bit field (LTPL_ST_*); infeasible actions are flagged, never
+ *     silently dropped, mirroring "omitted from the dict" in the reference (MOPG:246-248, OTH:1007-1025).
+ *   - batched ticks are STATELESS: first tick after set_startpos (the reference's multi-tick memory is wall-clock
+ *     dependent, OTH:353-378).
+ */
+#ifndef LTPL_B200_H
+#define LTPL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LTPL_ABI_VERSION 3
+
+/* action ids (OTH:14-17 ACTION_ID_MAP) */
+#define LTPL_ACT_NONE (-1)
+#define LTPL_ACT_STRAIGHT 0
+#define LTPL_ACT_FOLLOW 1
+#define LTPL_ACT_LEFT 2
+#define LTPL_ACT_RIGHT 3
+
+/* action slots per scenario: slot 0 = straight | follow (mutually exclusive, MOPG:124-174), 1 = left, 2 = right */
+#define LTPL_NSLOT 3
+
+/* status bits per (scenario, slot) */
+#define LTPL_ST_FOUND            (1 << 0)  /* a path exists for this slot (MOPG:246-257)                               */
+#define LTPL_ST_REDUCED_HORIZON  (1 << 1)  /* goal layer was moved towards the vehicle (MOPG:203-243)                  */
+#define LTPL_ST_TIE_AMBIGUOUS    (1 << 2)  /* exact cost tie met in the search: igraph's pick is heap-order dependent  */
+#define LTPL_ST_START_BLOCKED    (1 << 3)  /* start node removed by the action's node filter (GB:882-885)              */
+#define LTPL_ST_TRAJ_VALID       (1 << 4)  /* trajectory kept in the action set after calc_vel_profile (OTH:945-948)   */
+#define LTPL_ST_VEL_BOUND_VIOL   (1 << 5)  /* |vx[0] - vel_plan| >= v_max_offset or follow-mode bound broken (OTH:907)  */
+#define LTPL_ST_TOO_CLOSE        (1 << 6)  /* follow mode: inside the safety distance (OTH:821-822)                    */
+#define LTPL_ST_CONST_ONLY       (1 << 7)  /* "track blocked": constant segment only (OTH:475-506)                     */
+#define LTPL_ST_RENAMED_STRAIGHT (1 << 8)  /* follow renamed to straight after horizon reduction (MOPG:233-238)        */
+
+/* per scenario flags */
+#define LTPL_SC_OUT_OF_TRACK     (1 << 0)  /* OTH:214-219                                                             */
+#define LTPL_SC_HEADING_MISMATCH (1 << 1)  /* OTH:234-240                                                             */
+#define LTPL_SC_CAPACITY         (1 << 2)  /* a fixed-capacity buffer (P0_MAX / P_MAX / H_MAX) would overflow          */
+#define LTPL_SC_BRAKE_PREFIX     (1 << 3)  /* vel_plan > vel_max + 0.1: the reference path raises here (OTH:747-754,   */
+                                           /* 830/919 column_stack length mismatch); reported instead of planned       */
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* lattice blob: ONE contiguous device buffer (so it can be NCCL-broadcast as bytes) + this host-side header.          */
+/* All `off_*` are byte offsets into the blob, 256-byte aligned.  Layout documented in DESIGN.md "HBM layout".         */
+/* Replaces the pickled GraphBase (GraphBase.py:93-135) as the input of the online path.                               */
+/* ------------------------------------------------------------------------------------------------------------------ */
+typedef struct LtplLatticeHeader {
+    int32_t abi_version;
+    int32_t num_layers, num_nodes, num_edges, num_samples, n_glob_rl;
+    int32_t closed;              /* GB:116                                            */
+    int32_t plan_horizon_mode;   /* 0 = 'distance', 1 = 'layers' (GLNT:104-136)       */
+    int32_t max_nodes_per_layer; /* <= 64                                             */
+    int32_t max_window_edges;    /* max #edges inside any planning window (+1 layer)  */
+    int32_t pad0, pad1;
+    double lat_offset, lat_resolution, sampled_resolution, vel_decrease_lat, veh_width, veh_length;
+    double virt_goal_node_cost, min_plan_horizon;
+    /* per layer [L] */
+    uint64_t off_node_off;       /* int32 [L+1]                                       */
+    uint64_t off_raceline_index; /* int32 [L]                                         */
+    uint64_t off_s_raceline;     /* f64 [L]                                           */
+    uint64_t off_vel_raceline;   /* f64 [L]                                           */
+    uint64_t off_refline;        /* f64x2 [L]                                         */
+    uint64_t off_raceline;       /* f64x2 [L]                                         */
+    uint64_t off_bound1;         /* f64x2 [L]  refline + normvec * w_right (OTH:208)  */
+    uint64_t off_bound2;         /* f64x2 [L]  refline - normvec * w_left  (OTH:210)  */
+    uint64_t off_centerline;     /* f64x2 [L]  (bound1 + bound2) / 2                  */
+    /* per node [Nn] */
+    uint64_t off_node_xy;        /* f64x2 [Nn]                                        */
+    uint64_t off_node_psi;       /* f64 [Nn]                                          */
+    uint64_t off_node_layer;     /* int32 [Nn]                                        */
+    uint64_t off_in_off;         /* int32x2 [Nn] (first in-edge, #in-edges)           */
+    /* per edge [E], CSC order (start_layer, dst, src) */
+    uint64_t off_edge_layer_off; /* int32 [L+1]                                       */
+    uint64_t off_edge_src;       /* int32 [E]                                         */
+    uint64_t off_edge_dst;       /* int32 [E]                                         */
+    uint64_t off_edge_cost;      /* f64 [E]                                           */
+    uint64_t off_edge_len;       /* f64 [E]                                           */
+    uint64_t off_edge_psi1;      /* f64 [E] heading of the last sample                */
+    uint64_t off_samp_off;       /* int32 [E+1]                                       */
+    /* per sample [S] */
+    uint64_t off_samp_xy;        /* f64x2 [S]                                         */
+    uint64_t off_samp_el;        /* f64 [S]                                           */
+    uint64_t off_samp_edge;      /* int32 [S] owning edge                             */
+    /* global race line, rows (s, x, y, kappa, vel, el) with el = diff(s) (CVPF:166)  */
+    uint64_t off_glob_rl;        /* f64 [n_glob_rl - 1][6]                            */
+    uint64_t blob_bytes;
+} LtplLatticeHeader;
+
+typedef struct LtplLattice LtplLattice; /* opaque handle: header copy + resolved device pointers */
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* parameters: online ini (OTH:99-122, LTPL:168-173) + per-call arguments of calc_vel_profile (LTPL:344-352)           */
+/* ------------------------------------------------------------------------------------------------------------------ */
+#define LTPL_MAX_AXM 32
+typedef struct LtplParams {
+    double max_heading_offset;   /* GENERAL.max_heading_offset                        */
+    double v_max_offset;         /* ACTIONSET.v_max_offset                            */
+    double follow_c_p, follow_k_d, follow_k_p, follow_tan_w;
+    int32_t follow_control_type; /* 0 = PD, 1 = PDtan (CVPF:65-71)                    */
+    int32_t nmbr_export_points;  /* EXPORT.nmbr_export_points                         */
+    double dyn_model_exp, drag_coeff, m_veh; /* graph_init arguments (LTPL:189-192)   */
+    double vel_max, gg_scale, gg_ax, gg_ay, safety_d;
+    int32_t n_axm;               /* rows of ax_max_machines (<= LTPL_MAX_AXM)         */
+    int32_t traj_base_id;        /* OTH:669 (+10 per calc_vel_profile call)           */
+    double axm_v[LTPL_MAX_AXM];
+    double axm_a[LTPL_MAX_AXM];
+} LtplParams;
+
+/* capacities chosen by the host from the lattice (see lattice_blob.py: capacities()) */
+typedef struct LtplDims {
+    int32_t batch;     /* B scenarios                                                  */
+    int32_t k_obj;     /* K object slots per scenario                                  */
+    int32_t p0_max;    /* points of the constant segment (pose -> start node)          */
+    int32_t p_max;     /* points of a full path (constant segment + new plan), % 4 == 0 */
+    int32_t h_max;     /* nodes of a node sequence incl. the leading [None, None] entry */
+    int32_t n_export;  /* rows of an exported trajectory (nmbr_export_points)          */
+    int32_t pad0, pad1;
+} LtplDims;
+
+/* Caller-owned device buffers.  q = slot * B + b indexes a path ("action major").                                      */
+typedef struct LtplBuffers {
+    /* scenario inputs (Graph_LTPL.set_startpos / calc_paths arguments)                                                 */
+    const double* pos;        /* [B][2]                                                                                  */
+    const double* heading;    /* [B]                                                                                     */
+    const double* vel;        /* [B]  start velocity == vel_est of the first tick                                        */
+    const int32_t* n_obj;     /* [B]                                                                                     */
+    const double* obj;        /* [B][K][5] X, Y, theta, v, length (OLI:96-141)                                           */
+    /* set_startpos results (OTH:262-268 iterative memory of the forced 'straight' action)                               */
+    int32_t* sc_flags;        /* [B] LTPL_SC_*                                                                           */
+    int32_t* start_node;      /* [B][2] (layer, node)                                                                    */
+    int32_t* const_len;       /* [B] points of the constant segment                                                      */
+    double* const_seg;        /* [5][B][p0_max] planes x, y, psi, kappa, el                                              */
+    double* const_coeff;      /* [B][8] spline coefficients x(4) | y(4) (OTH:265)                                        */
+    /* calc_paths results                                                                                                */
+    int32_t* action_id;       /* [NSLOT][B] LTPL_ACT_*                                                                   */
+    int32_t* status;          /* [NSLOT][B] LTPL_ST_*                                                                    */
+    int32_t* n_nodes;         /* [NSLOT][B] nodes in the sequence incl. the leading (-1, -1)                             */
+    int32_t* nodes;           /* [NSLOT][B][h_max][2]                                                                    */
+    int32_t* node_idx;        /* [NSLOT][B][h_max] index of every node in the path arrays (MOPG:295)                     */
+    int32_t* edge_seq;        /* [NSLOT][B][h_max] lattice edge ids of the new plan (scratch for path assembly)          */
+    int32_t* closest_obj;     /* [B] closest_obj_index or -1 (GLNT:191-203, MOPG:113-115)                                */
+    int32_t* path_len;        /* [NSLOT][B]                                                                              */
+    double* path;             /* [5][NSLOT*B][p_max] planes x, y, psi, kappa, el  (path_dict of calc_paths)              */
+    double* coeff;            /* [NSLOT*B][h_max][8] (MOPG:305-309 spline_coeff_mat, stitched OTH:470-472)               */
+    /* calc_vel_profile results                                                                                          */
+    double* vel_scratch;      /* [3][NSLOT*B][p_max] brake / follow / complete profiles (CVPF:152,263,297)               */
+    double* s_vx_ax;          /* [3][NSLOT*B][p_max] planes s, vx, ax                                                    */
+    float* traj;              /* [NSLOT][B][n_export][7] s, x, y, psi, kappa, vx, ax (OTH:941, LTPL:401-406)             */
+    int32_t* traj_len;        /* [NSLOT][B]                                                                              */
+    int32_t* traj_id;         /* [NSLOT][B] traj_base_id + action id (OTH:696-697)                                       */
+} LtplBuffers;
+
+/* stand-alone forward/backward ggv velocity profile over dense path arrays (BASELINE.json config 5).                   */
+/* Replaces VpForwardBackward.calc_vel_profile -> tph.calc_vel_profile(closed=False) (VpForwardBackward.py:194-227).    */
+typedef struct LtplVelBatch {
+    int32_t n_paths, n_points; /* every path has n_points curvature values and n_points - 1 used element lengths         */
+    const double* kappa;       /* [n_paths][n_points]                                                                    */
+    const double* el;          /* [n_paths][n_points] (last column ignored)                                              */
+    const double* v_start;     /* [n_paths]                                                                              */
+    const double* v_end;       /* [n_paths]                                                                              */
+    double* vx;                /* [n_paths][n_points]                                                                    */
+    double* ax;                /* [n_paths][n_points] (last column 0)                                                    */
+} LtplVelBatch;
+
+int ltpl_version(void);
+const char* ltpl_last_error(void);
+int ltpl_sizeof(int which); /* 0 header, 1 params, 2 dims, 3 buffers, 4 velbatch: ABI self check for the ctypes mirror */
+
+/* lattice handle over a caller-owned device blob -- replaces unpickling GraphBase (main_offline_callback.py:60-66)      */
+int ltpl_lattice_create(const LtplLatticeHeader* header, const void* dev_blob, LtplLattice** out);
+int ltpl_lattice_destroy(LtplLattice* lat);
+
+/* Graph_LTPL.set_startpos (LTPL:262-296 -> OTH.set_initial_pose OTH:181-270), batched                                   */
+int ltpl_set_startpos_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims, const LtplBuffers* buf,
+                            void* stream);
+/* Graph_LTPL.calc_paths (LTPL:300-340 -> OLI:75-153, OTH:289-516, MOPG:11-334, GLNT:13-222, GIE:5-63, GB:567-646,       */
+/* GB:854-929), batched, first tick after set_startpos                                                                   */
+int ltpl_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims, const LtplBuffers* buf,
+                          void* stream);
+/* Graph_LTPL.calc_vel_profile (LTPL:344-408 -> OTH:518-601, 603-1040, VPFB, CVPF), batched                              */
+int ltpl_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims,
+                                const LtplBuffers* buf, void* stream);
+/* calc_paths + calc_vel_profile back to back (one planning tick)                                                        */
+int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims, const LtplBuffers* buf,
+                    void* stream);
+/* tph.calc_vel_profile(closed=False, loc_gg mode) over dense arrays                                                     */
+int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* stream);
+
+/* number of kernel launches issued by this library since load (bench.py "gpu_launches")                                 */
+uint64_t ltpl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LTPL_B200_H */
