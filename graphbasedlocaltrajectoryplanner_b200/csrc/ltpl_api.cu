@@ -1,0 +1,204 @@
+// ltpl_api.cu -- C-ABI of libltpl_b200.so (include/ltpl_b200.h).  Host side only resolves pointers and launches
+// kernels on the caller's stream; no allocation, no synchronisation on the hot path.
+//
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#define LTPL_WARPS_PER_CTA_EXPORT 8
+#include "ltpl_path.cuh"
+#include "ltpl_plan.cuh"
+#include "ltpl_vel.cuh"
+
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(const char* what) {
+    g_err = what;
+    return -1;
+}
+
+static int check_launch(const char* name) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        g_err = std::string(name) + ": " + cudaGetErrorString(e);
+        (void)cudaGetLastError();
+        return -2;
+    }
+    return 0;
+}
+
+extern "C" {
+
+int ltpl_version(void) { return LTPL_ABI_VERSION; }
+
+const char* ltpl_last_error(void) { return g_err.c_str(); }
+
+uint64_t ltpl_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int ltpl_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(LtplLatticeHeader);
+        case 1: return (int)sizeof(LtplParams);
+        case 2: return (int)sizeof(LtplDims);
+        case 3: return (int)sizeof(LtplBuffers);
+        case 4: return (int)sizeof(LtplVelBatch);
+        default: return -1;
+    }
+}
+
+int ltpl_lattice_create(const LtplLatticeHeader* h, const void* dev_blob, LtplLattice** out) {
+    if (!h || !dev_blob || !out) return fail("ltpl_lattice_create: null argument");
+    if (h->abi_version != LTPL_ABI_VERSION) return fail("ltpl_lattice_create: ABI version mismatch");
+    if (h->max_nodes_per_layer > 64 || h->max_nodes_per_layer < 1)
+        return fail("ltpl_lattice_create: max_nodes_per_layer must be in [1, 64]");
+    if (h->num_layers < 4) return fail("ltpl_lattice_create: lattice needs at least 4 layers");
+    LtplLattice* lat = new (std::nothrow) LtplLattice;
+    if (!lat) return fail("ltpl_lattice_create: out of host memory");
+    lat->h = *h;
+    const unsigned char* p = static_cast<const unsigned char*>(dev_blob);
+    LatDev& d = lat->d;
+    d.L = h->num_layers;
+    d.Nn = h->num_nodes;
+    d.E = h->num_edges;
+    d.S = h->num_samples;
+    d.n_glob = h->n_glob_rl;
+    d.closed = h->closed;
+    d.plan_mode = h->plan_horizon_mode;
+    d.max_nodes = h->max_nodes_per_layer;
+    d.max_window_edges = h->max_window_edges;
+    d.lat_offset = h->lat_offset;
+    d.lat_res = h->lat_resolution;
+    d.step = h->sampled_resolution;
+    d.vel_decrease_lat = h->vel_decrease_lat;
+    d.veh_width = h->veh_width;
+    d.veh_length = h->veh_length;
+    d.virt_cost = h->virt_goal_node_cost;
+    d.min_plan_horizon = h->min_plan_horizon;
+#define LTPL_PTR(field, type, off) d.field = reinterpret_cast<const type*>(p + h->off)
+    LTPL_PTR(node_off, int, off_node_off);
+    LTPL_PTR(rl_idx, int, off_raceline_index);
+    LTPL_PTR(s_rl, double, off_s_raceline);
+    LTPL_PTR(vel_rl, double, off_vel_raceline);
+    LTPL_PTR(refline, double2, off_refline);
+    LTPL_PTR(raceline, double2, off_raceline);
+    LTPL_PTR(bound1, double2, off_bound1);
+    LTPL_PTR(bound2, double2, off_bound2);
+    LTPL_PTR(center, double2, off_centerline);
+    LTPL_PTR(node_xy, double2, off_node_xy);
+    LTPL_PTR(node_psi, double, off_node_psi);
+    LTPL_PTR(node_layer, int, off_node_layer);
+    LTPL_PTR(in_off, int2, off_in_off);
+    LTPL_PTR(edge_layer_off, int, off_edge_layer_off);
+    LTPL_PTR(edge_src, int, off_edge_src);
+    LTPL_PTR(edge_dst, int, off_edge_dst);
+    LTPL_PTR(edge_cost, double, off_edge_cost);
+    LTPL_PTR(edge_len, double, off_edge_len);
+    LTPL_PTR(edge_psi1, double, off_edge_psi1);
+    LTPL_PTR(samp_off, int, off_samp_off);
+    LTPL_PTR(samp_xy, double2, off_samp_xy);
+    LTPL_PTR(samp_el, double, off_samp_el);
+    LTPL_PTR(samp_edge, int, off_samp_edge);
+    LTPL_PTR(glob_rl, double, off_glob_rl);
+#undef LTPL_PTR
+    *out = lat;
+    return 0;
+}
+
+int ltpl_lattice_destroy(LtplLattice* lat) {
+    delete lat;
+    return 0;
+}
+
+static int check_common(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf) {
+    if (!lat || !prm || !dm || !bf) return fail("null argument");
+    if (dm->batch <= 0) return fail("dims.batch must be > 0");
+    if (dm->k_obj < 1 || dm->k_obj > LTPL_KMAX) return fail("dims.k_obj must be in [1, 16]");
+    if (dm->p_max % 4 != 0 || dm->p_max < dm->p0_max) return fail("dims.p_max must be a multiple of 4 and >= p0_max");
+    if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");
+    if (prm->axm_v[prm->n_axm - 1] < prm->vel_max)  // tph.calc_vel_profile input check
+        return fail("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!");
+    return 0;
+}
+
+int ltpl_set_startpos_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                            void* stream) {
+    if (int r = check_common(lat, prm, dm, bf)) return r;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    k_startpos<<<grid, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
+    return check_launch("k_startpos");
+}
+
+static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                        cudaStream_t st) {
+    const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
+    const int hl = dm->h_max;
+    const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
+    const size_t smem_plan = plan_smem_bytes_per_warp(maxn, hl, mask_words) * LTPL_WARPS_PER_CTA;
+    const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
+    if (smem_plan > 200 * 1024 || smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
+    static thread_local size_t attr_plan = 0, attr_path = 0;
+    if (smem_plan > 48 * 1024 && smem_plan > attr_plan) {
+        if (cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(k_plan) failed");
+        attr_plan = smem_plan;
+    }
+    if (smem_path > 48 * 1024 && smem_path > attr_path) {
+        if (cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
+            return fail("cudaFuncSetAttribute(k_path) failed");
+        attr_path = smem_path;
+    }
+    const int grid_plan = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    k_plan<<<grid_plan, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    if (int r = check_launch("k_plan")) return r;
+    const int nq = LTPL_NSLOT * dm->batch;
+    const int grid_path = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    k_path<<<grid_path, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
+    return check_launch("k_path");
+}
+
+static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                      cudaStream_t st) {
+    const int nq = LTPL_NSLOT * dm->batch;
+    k_vel<<<(nq + 127) / 128, 128, 0, st>>>(lat->d, *prm, *dm, *bf);
+    if (int r = check_launch("k_vel")) return r;
+    k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
+        *dm, *bf);
+    return check_launch("k_export");
+}
+
+int ltpl_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                          void* stream) {
+    if (int r = check_common(lat, prm, dm, bf)) return r;
+    return launch_paths(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
+}
+
+int ltpl_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,
+                                const LtplBuffers* bf, void* stream) {
+    if (int r = check_common(lat, prm, dm, bf)) return r;
+    return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
+}
+
+int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                    void* stream) {
+    if (int r = check_common(lat, prm, dm, bf)) return r;
+    if (int r = launch_paths(lat, prm, dm, bf, static_cast<cudaStream_t>(stream))) return r;
+    return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
+}
+
+int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* stream) {
+    if (!prm || !vb) return fail("null argument");
+    if (vb->n_paths <= 0 || vb->n_points < 2) return fail("velprofile: need n_paths > 0 and n_points >= 2");
+    if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");
+    if (prm->axm_v[prm->n_axm - 1] < prm->vel_max)
+        return fail("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!");
+    k_velprofile_dense<<<(vb->n_paths + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
+    return check_launch("k_velprofile_dense");
+}
+
+}  // extern "C"

@@ -1,0 +1,197 @@
+// ltpl_path.cuh -- k_path: edge -> path assembly (MOPG:259-297), C2 spline refit (tph.calc_splines as a tridiagonal
+// system in the knot tangents, MOPG:305-309), re-evaluation x, y, psi, kappa at the per-edge sample counts
+// (tph.interp_splines(stepnum_fixed) + calc_head_curv_an, MOPG:312-322) and stitching with the constant segment
+// (OTH:433-472).  One WARP per (action slot, scenario).
+#pragma once
+#include "ltpl_plan.cuh"
+
+__host__ __device__ inline size_t path_smem_bytes_per_warp(int h_max) {
+    // doubles: px, py, el, mx, my, cp, dx, dy  (h_max each) ; ints: nidx, eid, nsamp (h_max each)
+    size_t s = sizeof(double) * 8 * (size_t)h_max + sizeof(int) * 3 * (size_t)h_max;
+    return (s + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
+k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int B = dm.batch;
+    const int q = blockIdx.x * LTPL_WARPS_PER_CTA + wib;
+    if (q >= LTPL_NSLOT * B) return;
+    const int b = q % B;
+    const int st = bf.status[q];
+    if (!(st & LTPL_ST_FOUND)) return;
+    const int H = dm.h_max;
+    unsigned char* base = smem_raw + path_smem_bytes_per_warp(H) * wib;
+    double* kx = reinterpret_cast<double*>(base);
+    double* ky = kx + H;
+    double* kel = ky + H;
+    double* mx = kel + H;
+    double* my = mx + H;
+    double* cp = my + H;
+    double* dxp = cp + H;
+    double* dyp = dxp + H;
+    int* nidx = reinterpret_cast<int*>(dyp + H);
+    int* eid = nidx + H;
+    int* nsamp = eid + H;
+
+    const int p0 = bf.const_len[b];
+    const size_t cplane = (size_t)B * dm.p0_max;
+    const double* cs = bf.const_seg + (size_t)b * dm.p0_max;
+    const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
+    double* pp = bf.path + (size_t)q * dm.p_max;
+    int* node_idx = bf.node_idx + (size_t)q * H;
+    double* coeff = bf.coeff + (size_t)q * H * 8;
+
+    const int n_nodes = bf.n_nodes[q];  // incl. the leading (-1, -1)
+    const int nseg = n_nodes - 2;       // segments of the new plan
+
+    if (st & LTPL_ST_CONST_ONLY) {  // OTH:481-506: constant segment incl. its last point
+        for (int k = lane; k < p0; k += 32)
+            for (int c = 0; c < 5; ++c) pp[c * pplane + k] = cs[c * cplane + k];
+        if (lane == 0) {
+            node_idx[0] = 0;
+            node_idx[1] = p0 - 1;
+            for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
+            bf.path_len[q] = p0;
+        }
+        return;
+    }
+
+    // ---- segment bookkeeping (MOPG:268-297) ----
+    const int* es = bf.edge_seq + (size_t)q * H;
+    for (int i = lane; i < nseg; i += 32) {
+        const int e = es[i];
+        eid[i] = e;
+        nsamp[i] = lt.samp_off[e + 1] - lt.samp_off[e];
+        kel[i] = lt.edge_len[e];
+        const double2 p = lt.samp_xy[lt.samp_off[e]];
+        kx[i] = p.x;
+        ky[i] = p.y;
+        if (i == nseg - 1) {
+            const double2 pl = lt.samp_xy[lt.samp_off[e + 1] - 1];
+            kx[nseg] = pl.x;
+            ky[nseg] = pl.y;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {  // exclusive prefix sum of (n_i - 1): index of every node in the fused sample array
+        int acc = 0;
+        for (int i = 0; i < nseg; ++i) {
+            nidx[i] = acc;
+            acc += nsamp[i] - 1;
+        }
+        nidx[nseg] = acc;  // last node sits on the last sample
+    }
+    __syncwarp();
+    const int p_new = nidx[nseg] + 1;
+    const int loc = p0 - 1;  // closest_path_index(start node) on the constant segment == its last point (OTH:398-404)
+    const int p_tot = loc + p_new;
+    if (p_tot > dm.p_max) {
+        if (lane == 0) {
+            bf.status[q] = st & ~LTPL_ST_FOUND;
+            bf.action_id[q] = LTPL_ACT_NONE;
+            atomicOr(&bf.sc_flags[b], LTPL_SC_CAPACITY);
+        }
+        return;
+    }
+
+    // ---- C2 spline through the nodes: tridiagonal system in the knot tangents m_k (== tph.calc_splines) ----
+    const double psi_s = cs[2 * cplane + p0 - 1];           // MOPG:300-301: heading at the end of the constant segment
+    const double psi_e = lt.edge_psi1[eid[nseg - 1]];       // MOPG:307: psi of the last sample
+    if (lane < 2) {
+        const double* kp = (lane == 0) ? kx : ky;
+        double* m = (lane == 0) ? mx : my;
+        double* dp = (lane == 0) ? dxp : dyp;
+        m[0] = (lane == 0) ? cos(psi_s + LTPL_PI / 2) : sin(psi_s + LTPL_PI / 2);
+        m[nseg] = (lane == 0) ? cos(psi_e + LTPL_PI / 2) : sin(psi_e + LTPL_PI / 2);
+        if (nseg > 1) {
+            // rows k = 1 .. nseg-1:  (2/el[k-1]) m[k-1] + 4 (1/el[k-1] + 1/el[k]) m[k] + (2/el[k]) m[k+1] = r[k]
+            // forward sweep (both lanes keep their own c' copy: lane 0 -> cp, lane 1 recomputes into registers)
+            double cprev = 0.0, dprev = 0.0;
+            for (int k = 1; k < nseg; ++k) {
+                const double e0 = kel[k - 1], e1 = kel[k];
+                const double lo = 2.0 / e0, di = 4.0 * (1.0 / e0 + 1.0 / e1), up = 2.0 / e1;
+                double r = 6.0 * ((kp[k] - kp[k - 1]) / (e0 * e0) + (kp[k + 1] - kp[k]) / (e1 * e1));
+                if (k == 1) r -= lo * m[0];
+                if (k == nseg - 1) r -= up * m[nseg];
+                const double den = (k == 1) ? di : (di - lo * cprev);
+                const double cc = (k == nseg - 1) ? 0.0 : up / den;
+                const double dd = (k == 1) ? r / den : (r - lo * dprev) / den;
+                if (lane == 0) cp[k] = cc;
+                dp[k] = dd;
+                cprev = cc;
+                dprev = dd;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < 2 && nseg > 1) {
+        double* m = (lane == 0) ? mx : my;
+        const double* dp = (lane == 0) ? dxp : dyp;
+        m[nseg - 1] = dp[nseg - 1];
+        for (int k = nseg - 2; k >= 1; --k) m[k] = dp[k] - cp[k] * m[k + 1];
+    }
+    __syncwarp();
+
+    // ---- stitched bookkeeping (OTH:458-472) ----
+    for (int i = lane; i <= nseg; i += 32) node_idx[1 + i] = nidx[i] + loc;
+    if (lane == 0) {
+        node_idx[0] = 0;
+        for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
+        bf.path_len[q] = p_tot;
+    }
+    for (int i = lane; i < nseg; i += 32) {
+        const double e0 = kel[i];
+        const double dx = kx[i + 1] - kx[i], dy = ky[i + 1] - ky[i];
+        const double a1x = e0 * mx[i], e1x = e0 * mx[i + 1];
+        const double a1y = e0 * my[i], e1y = e0 * my[i + 1];
+        double* c = coeff + (size_t)(1 + i) * 8;
+        c[0] = kx[i]; c[1] = a1x; c[2] = 3 * dx - 2 * a1x - e1x; c[3] = -2 * dx + a1x + e1x;
+        c[4] = ky[i]; c[5] = a1y; c[6] = 3 * dy - 2 * a1y - e1y; c[7] = -2 * dy + a1y + e1y;
+    }
+    // constant part (OTH:442-444): everything but the last point of the constant segment
+    for (int k = lane; k < loc; k += 32)
+        for (int c = 0; c < 5; ++c) pp[c * pplane + k] = cs[c * cplane + k];
+    __syncwarp();
+
+    // ---- re-evaluation at the per-edge sample counts (MOPG:312-322); el column keeps the offline chords (q2) ----
+    for (int p = lane; p < p_new; p += 32) {
+        int lo_i = 0, hi_i = nseg - 1;  // largest i with nidx[i] <= p (the very last point belongs to the last segment)
+        while (lo_i < hi_i) {
+            const int mid = (lo_i + hi_i + 1) >> 1;
+            if (nidx[mid] <= p)
+                lo_i = mid;
+            else
+                hi_i = mid - 1;
+        }
+        const int i = lo_i;
+        const int k = p - nidx[i];
+        const int n_i = nsamp[i];
+        const double e0 = kel[i];
+        const double dx = kx[i + 1] - kx[i], dy = ky[i + 1] - ky[i];
+        const double a0x = kx[i], a1x = e0 * mx[i], e1x = e0 * mx[i + 1];
+        const double a0y = ky[i], a1y = e0 * my[i], e1y = e0 * my[i + 1];
+        const double a2x = 3 * dx - 2 * a1x - e1x, a3x = -2 * dx + a1x + e1x;
+        const double a2y = 3 * dy - 2 * a1y - e1y, a3y = -2 * dy + a1y + e1y;
+        double t, x, y;
+        if (p == p_new - 1) {  // incl_last_point: coordinates = sum of the coefficients, t = 1
+            t = 1.0;
+            x = ((a0x + a1x) + a2x) + a3x;
+            y = ((a0y + a1y) + a2y) + a3y;
+        } else {
+            t = k * (1.0 / (double)(n_i - 1));  // np.linspace(0, 1, n_i)[k]
+            x = cubic_rn(a0x, a1x, a2x, a3x, t);
+            y = cubic_rn(a0y, a1y, a2y, a3y, t);
+        }
+        double psi, kap;
+        head_curv(a1x, a2x, a3x, a1y, a2y, a3y, t, &psi, &kap);
+        const int o = loc + p;
+        pp[0 * pplane + o] = x;
+        pp[1 * pplane + o] = y;
+        pp[2 * pplane + o] = psi;
+        pp[3 * pplane + o] = kap;
+        pp[4 * pplane + o] = lt.samp_el[lt.samp_off[eid[i]] + k];
+    }
+}

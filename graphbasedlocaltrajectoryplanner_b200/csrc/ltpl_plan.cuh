@@ -1,0 +1,576 @@
+// ltpl_plan.cuh -- k_startpos (set_initial_pose) and k_plan (object handling, edge blocking, action sets, layered DP).
+// One WARP per scenario; all decisions in float64 (see ltpl_common.cuh).
+#pragma once
+#include "ltpl_common.cuh"
+
+#define LTPL_KMAX 16          // object slots per scenario held in shared memory
+#define LTPL_WARPS_PER_CTA 4
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_startpos: Graph_LTPL.set_startpos -> OnlineTrajectoryHandler.set_initial_pose (OTH:181-270)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cubic_rn(double a0, double a1, double a2, double a3, double t) {
+    // a0 + a1 * t + a2 * pow(t, 2) + a3 * pow(t, 3), evaluated left to right (tph.interp_splines)
+    double t2 = __dmul_rn(t, t);
+    double t3 = __dmul_rn(t2, t);
+    return __dadd_rn(__dadd_rn(__dadd_rn(a0, __dmul_rn(a1, t)), __dmul_rn(a2, t2)), __dmul_rn(a3, t3));
+}
+
+__device__ __forceinline__ void head_curv(double ax1, double ax2, double ax3, double ay1, double ay2, double ay3,
+                                          double t, double* psi, double* kappa) {
+    // tph.calc_head_curv_an
+    double t2 = t * t;
+    double xd = ax1 + 2 * ax2 * t + 3 * ax3 * t2;
+    double yd = ay1 + 2 * ay2 * t + 3 * ay3 * t2;
+    double xdd = 2 * ax2 + 6 * ax3 * t;
+    double ydd = 2 * ay2 + 6 * ay3 * t;
+    *psi = normalize_psi(atan2(yd, xd) - LTPL_PI / 2);
+    double q = xd * xd + yd * yd;
+    *kappa = (xd * ydd - yd * xdd) / (q * sqrt(q));
+}
+
+__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
+k_startpos(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (b >= dm.batch) return;
+    const double px = bf.pos[2 * b], py = bf.pos[2 * b + 1], heading = bf.heading[b];
+    int flags = 0;
+    if (lane == 0) {
+        bf.start_node[2 * b] = -1;
+        bf.start_node[2 * b + 1] = -1;
+        bf.const_len[b] = 0;
+    }
+    if (!inside_bounds(lt, px, py, lane)) {  // OTH:214-219
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_OUT_OF_TRACK;
+        return;
+    }
+    ArgMinD m = warp_closest_point(lt.node_xy, lt.Nn, px, py, lane);  // GB:341-345
+    const int closest_layer = lt.node_layer[m.i];
+    const int goal_layer = (closest_layer + 2) % (lt.L - 1);  // OTH:226 (quirk q5)
+    const int goal_node = lt.rl_idx[goal_layer];
+    const int g = lt.node_off[goal_layer] + goal_node;
+    const double2 pe = lt.node_xy[g];
+    const double psi_e = lt.node_psi[g];
+    if (lane == 0) {
+        bf.start_node[2 * b] = goal_layer;
+        bf.start_node[2 * b + 1] = goal_node;
+    }
+    double hd = fabs(heading - psi_e);  // OTH:234-240
+    if (hd > LTPL_PI) hd = fabs(2 * LTPL_PI - hd);
+    if (hd > prm.max_heading_offset) {
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_HEADING_MISMATCH;
+        return;
+    }
+    // single-segment spline pose -> start node (tph.calc_splines N = 1, el = |P1 - P0|)
+    const double dx = pe.x - px, dy = pe.y - py;
+    const double el = sqrt(__dadd_rn(sq_rn(dx), sq_rn(dy)));
+    const double ax0 = px, ay0 = py;
+    const double ax1 = cos(heading + LTPL_PI / 2) * el, ay1 = sin(heading + LTPL_PI / 2) * el;
+    const double ex1 = cos(psi_e + LTPL_PI / 2) * el, ey1 = sin(psi_e + LTPL_PI / 2) * el;
+    const double ax2 = 3 * dx - 2 * ax1 - ex1, ay2 = 3 * dy - 2 * ay1 - ey1;
+    const double ax3 = -2 * dx + ax1 + ex1, ay3 = -2 * dy + ay1 + ey1;
+    // tph.calc_spline_lengths: 15-point polyline, summed like np.sum over 14 values
+    double seg = 0.0;
+    if (lane < 14) {
+        double t0 = (lane == 0) ? 0.0 : lane * (1.0 / 14.0);
+        double t1 = (lane == 13) ? 1.0 : (lane + 1) * (1.0 / 14.0);
+        double x0 = cubic_rn(ax0, ax1, ax2, ax3, t0), y0 = cubic_rn(ay0, ay1, ay2, ay3, t0);
+        double x1 = cubic_rn(ax0, ax1, ax2, ax3, t1), y1 = cubic_rn(ay0, ay1, ay2, ay3, t1);
+        seg = sqrt(__dadd_rn(sq_rn(x1 - x0), sq_rn(y1 - y0)));
+    }
+    double r[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) r[k] = __shfl_sync(LTPL_FULL, seg, k);
+    double len = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+#pragma unroll
+    for (int k = 8; k < 14; ++k) len += r[k];
+    const int p0 = (int)ceil(len / lt.step) + 1;  // tph.interp_splines(stepsize_approx)
+    if (p0 > dm.p0_max || p0 < 2) {
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_CAPACITY;
+        return;
+    }
+    const double dstep = len / (double)(p0 - 1);
+    const size_t plane = (size_t)dm.batch * dm.p0_max;
+    double* cs = bf.const_seg + (size_t)b * dm.p0_max;
+    for (int k = lane; k < p0; k += 32) {
+        double t, x, y, tn, xn, yn;
+        if (k < p0 - 1) {
+            t = (k * dstep) / len;
+            x = cubic_rn(ax0, ax1, ax2, ax3, t);
+            y = cubic_rn(ay0, ay1, ay2, ay3, t);
+        } else {
+            t = 1.0;
+            x = ((ax0 + ax1) + ax2) + ax3;
+            y = ((ay0 + ay1) + ay2) + ay3;
+        }
+        double elk = 0.0;
+        if (k < p0 - 1) {
+            if (k + 1 < p0 - 1) {
+                tn = ((k + 1) * dstep) / len;
+                xn = cubic_rn(ax0, ax1, ax2, ax3, tn);
+                yn = cubic_rn(ay0, ay1, ay2, ay3, tn);
+            } else {
+                xn = ((ax0 + ax1) + ax2) + ax3;
+                yn = ((ay0 + ay1) + ay2) + ay3;
+            }
+            elk = sqrt(__dadd_rn(sq_rn(xn - x), sq_rn(yn - y)));  // OTH:259
+        }
+        double psi, kap;
+        head_curv(ax1, ax2, ax3, ay1, ay2, ay3, t, &psi, &kap);
+        cs[0 * plane + k] = x;
+        cs[1 * plane + k] = y;
+        cs[2 * plane + k] = psi;
+        cs[3 * plane + k] = kap;
+        cs[4 * plane + k] = elk;
+    }
+    if (lane == 0) {
+        bf.sc_flags[b] = flags;
+        bf.const_len[b] = p0;
+        double* cc = bf.const_coeff + (size_t)b * 8;
+        cc[0] = ax0; cc[1] = ax1; cc[2] = ax2; cc[3] = ax3;
+        cc[4] = ay0; cc[5] = ay1; cc[6] = ay2; cc[7] = ay3;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// layered shortest-path DP (igraph Dijkstra semantics on the layered DAG: GB:818-821, 854-929)
+// ---------------------------------------------------------------------------------------------------------------------
+struct DpCtx {
+    double* dist;        // [2][maxn]
+    unsigned char* pred; // [hl][maxn]  k-th in-edge of the node, 255 = unreachable
+    int maxn;
+    int cur;             // which half of dist holds the last completed layer
+    int layer;           // lattice layer of the last completed step
+};
+
+// runs up to n_steps layer transitions; returns the number completed (last layer with a reachable node)
+__device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int start_layer, int start_node, int n_steps,
+                                      const unsigned* __restrict__ mask, int e_base, int rem_layer, int rem_lo,
+                                      int rem_hi, int* tie_out) {
+    const int maxn = c.maxn;
+    for (int j = lane; j < maxn; j += 32) c.dist[j] = LTPL_INF;
+    __syncwarp();
+    if (lane == 0) c.dist[start_node] = 0.0;
+    __syncwarp();
+    int cur = 0, tie = 0, reach = 0, layer = start_layer;
+    for (int li = 1; li <= n_steps; ++li) {
+        int nxt = layer + 1;
+        if (nxt >= lt.L) nxt = 0;
+        const int nbase = lt.node_off[nxt];
+        const int nl = lt.node_off[nxt + 1] - nbase;
+        const double* dcur = c.dist + cur * maxn;
+        double* dnxt = c.dist + (cur ^ 1) * maxn;
+        int any = 0;
+        for (int j = lane; j < maxn; j += 32) {
+            double best = LTPL_INF, best_ds = LTPL_INF;
+            int best_k = 255;
+            if (j < nl && !(nxt == rem_layer && j >= rem_lo && j < rem_hi)) {
+                const int2 io = lt.in_off[nbase + j];
+                for (int k = 0; k < io.y; ++k) {
+                    const int e = io.x + k;
+                    const double ds = dcur[lt.edge_src[e]];
+                    if (!(ds < LTPL_INF)) continue;
+                    if (mask) {
+                        int idx = e - e_base;
+                        if (idx < 0) idx += lt.E;
+                        if ((mask[idx >> 5] >> (idx & 31)) & 1u) continue;
+                    }
+                    const double alt = __dadd_rn(ds, lt.edge_cost[e]);
+                    if (alt < best || (alt == best && ds < best_ds)) {
+                        best = alt;
+                        best_ds = ds;
+                        best_k = k;
+                    } else if (alt == best && ds == best_ds) {
+                        tie = 1;
+                    }
+                }
+            }
+            dnxt[j] = best;
+            c.pred[li * maxn + j] = (unsigned char)best_k;
+            any |= (best_k != 255);
+        }
+        any = __any_sync(LTPL_FULL, any);
+        __syncwarp();
+        if (!any) break;
+        cur ^= 1;
+        reach = li;
+        layer = nxt;
+    }
+    c.cur = cur;
+    c.layer = layer;
+    if (__any_sync(LTPL_FULL, tie)) *tie_out = 1;
+    return reach;
+}
+
+// virtual goal node: argmin_j dist[j] + |raceline_index - j| * lat_resolution * w_virt_goal (GB:188)
+__device__ __forceinline__ int dp_goal(const LatDev& lt, int lane, const DpCtx& c, int* tie_out) {
+    const int layer = c.layer;
+    const int nl = lt.node_off[layer + 1] - lt.node_off[layer];
+    const int rl = lt.rl_idx[layer];
+    const double* d = c.dist + c.cur * c.maxn;
+    double best = LTPL_INF, best_ds = LTPL_INF;
+    int best_j = 0x7fffffff, tie = 0;
+    for (int j = lane; j < nl; j += 32) {
+        const double ds = d[j];
+        if (!(ds < LTPL_INF)) continue;
+        int dn = rl - j;
+        if (dn < 0) dn = -dn;
+        const double alt = __dadd_rn(ds, __dmul_rn(__dmul_rn((double)dn, lt.lat_res), lt.virt_cost));
+        if (alt < best || (alt == best && ds < best_ds)) {
+            best = alt;
+            best_ds = ds;
+            best_j = j;
+        } else if (alt == best && ds == best_ds) {
+            tie = 1;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double oa = __shfl_xor_sync(LTPL_FULL, best, o);
+        const double od = __shfl_xor_sync(LTPL_FULL, best_ds, o);
+        const int oj = __shfl_xor_sync(LTPL_FULL, best_j, o);
+        if (oa < LTPL_INF && oa == best && od == best_ds && oj != best_j) tie = 1;
+        if (oa < best || (oa == best && (od < best_ds || (od == best_ds && oj < best_j)))) {
+            best = oa;
+            best_ds = od;
+            best_j = oj;
+        }
+    }
+    if (__any_sync(LTPL_FULL, tie)) *tie_out = 1;
+    return best_j;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_plan: OLI.process_object_list + gen_local_node_template + main_online_path_gen (action sets + graph search)
+// ---------------------------------------------------------------------------------------------------------------------
+struct PlanSmem {  // per warp, followed by dist / mask / pred (sizes depend on the lattice)
+    double vx[LTPL_KMAX], vy[LTPL_KMAX], vr[LTPL_KMAX], vv[LTPL_KMAX], pxp[LTPL_KMAX], pyp[LTPL_KMAX];
+    int n_veh;
+    int pad;
+};
+
+__host__ __device__ inline size_t plan_smem_bytes_per_warp(int maxn, int hl, int mask_words) {
+    size_t s = sizeof(PlanSmem) + sizeof(double) * 2 * maxn + sizeof(unsigned) * mask_words + (size_t)hl * maxn;
+    return (s + 15) & ~(size_t)15;
+}
+
+// mark edges of layer pair a -> a+1 that hold a sample inside the inflated obstacle disc (GB:626-644)
+__device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, double ox, double oy, double ref,
+                                           unsigned* mask, int e_base) {
+    const int e0 = lt.edge_layer_off[a], e1 = lt.edge_layer_off[a + 1];
+    if (e1 <= e0) return;
+    const int s0 = lt.samp_off[e0], s1 = lt.samp_off[e1];
+    for (int s = s0 + lane; s < s1; s += 32) {
+        const double2 p = lt.samp_xy[s];
+        const double x = __dsub_rn(p.x, ox), y = __dsub_rn(p.y, oy);
+        const double d2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        if (d2 <= ref) {
+            int idx = lt.samp_edge[s] - e_base;
+            if (idx < 0) idx += lt.E;
+            atomicOr(&mask[idx >> 5], 1u << (idx & 31));
+        }
+    }
+}
+
+// get_intersec_edges (GIE:36-63) for one disc; returns obj_layer or -1 when outside the planning range
+__device__ __forceinline__ int intersect_disc(const LatDev& lt, int lane, double ox, double oy, double radius,
+                                              int p_start, int p_end, unsigned* mask, int e_base) {
+    const ArgMinD m = warp_closest_point(lt.refline, lt.L, ox, oy, lane);
+    const int o = m.i;
+    const int lo = 1;
+    const bool in_rng = (p_start - lo <= o && o <= p_end + lo) ||
+                        (p_start > p_end && (p_start - lo <= o || o <= p_end + lo));
+    if (!in_rng) return -1;
+    // obstacle_ref = (r + veh_width / 2)^2 + stepsize^2 / 4  (GB:626-629)
+    const double ref = __dadd_rn(sq_rn(__dadd_rn(radius, __ddiv_rn(lt.veh_width, 2.0))), __ddiv_rn(sq_rn(lt.step), 4.0));
+    // layer window {o-1, o, o+1} with the reference's wrap handling (GB:597-600: quirk q4 drops o+1 when o == L-1)
+    int s_l = o - lo, e_l = o + lo;
+    if (s_l < 0) s_l += lt.L;
+    if (e_l > lt.L) e_l -= lt.L;
+    const bool has_prev = true;               // o-1 (mod L) is always part of the window
+    const bool has_next = (e_l < lt.L);       // e_l == L  -> layer L does not exist
+    const int prev = s_l;
+    const int next = e_l;
+    if (has_prev && layer_in_range(prev, p_start, p_end) && layer_in_range(o, p_start, p_end) &&
+        ((prev + 1) % lt.L) == o)
+        block_pair(lt, lane, prev, ox, oy, ref, mask, e_base);
+    if (has_next && layer_in_range(o, p_start, p_end) && layer_in_range(next, p_start, p_end) &&
+        ((o + 1) % lt.L) == next)
+        block_pair(lt, lane, o, ox, oy, ref, mask, e_base);
+    return o;
+}
+
+__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
+k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf, const int maxn, const int hl,
+       const int mask_words) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + wib;
+    if (b >= dm.batch) return;
+    unsigned char* base = smem_raw + plan_smem_bytes_per_warp(maxn, hl, mask_words) * wib;
+    PlanSmem* ps = reinterpret_cast<PlanSmem*>(base);
+    double* dist = reinterpret_cast<double*>(base + sizeof(PlanSmem));
+    unsigned* mask = reinterpret_cast<unsigned*>(dist + 2 * maxn);
+    unsigned char* pred = reinterpret_cast<unsigned char*>(mask + mask_words);
+    const int B = dm.batch;
+
+    // defaults
+    if (lane < LTPL_NSLOT) {
+        bf.action_id[lane * B + b] = LTPL_ACT_NONE;
+        bf.status[lane * B + b] = 0;
+        bf.n_nodes[lane * B + b] = 0;
+        bf.path_len[lane * B + b] = 0;
+    }
+    if (lane == 0) {
+        bf.closest_obj[b] = -1;
+        bf.cobj[4 * b + 3] = 0.0;
+    }
+    if (bf.sc_flags[b] != 0) return;
+
+    const int start_layer = bf.start_node[2 * b], start_node = bf.start_node[2 * b + 1];
+    const int p0 = bf.const_len[b];
+    const size_t cplane = (size_t)B * dm.p0_max;
+    const double* cs = bf.const_seg + (size_t)b * dm.p0_max;
+
+    // ---- OLI.process_object_list (OLI:96-141): drop off-track objects, radius = length / 2, 0.2 s CV prediction ----
+    int n_veh = 0;
+    {
+        int n_in = bf.n_obj[b];
+        if (n_in > dm.k_obj) n_in = dm.k_obj;
+        for (int k = 0; k < n_in; ++k) {
+            const double* o = bf.obj + ((size_t)b * dm.k_obj + k) * 5;
+            const double ox = o[0], oy = o[1];
+            if (inside_bounds(lt, ox, oy, lane)) {
+                if (lane == 0) {
+                    const double th = o[2], v = o[3];
+                    ps->vx[n_veh] = ox;
+                    ps->vy[n_veh] = oy;
+                    ps->vr[n_veh] = o[4] / 2.0;
+                    ps->vv[n_veh] = v;
+                    ps->pxp[n_veh] = __dsub_rn(ox, __dmul_rn(__dmul_rn(sin(th), v), 0.2));
+                    ps->pyp[n_veh] = __dadd_rn(oy, __dmul_rn(__dmul_rn(cos(th), v), 0.2));
+                }
+                ++n_veh;
+            }
+        }
+    }
+    for (int i = lane; i < mask_words; i += 32) mask[i] = 0u;
+    __syncwarp();
+
+    // ---- planning range (GLNT:104-142) ----
+    int end_layer;
+    if (lt.plan_mode == 0) {
+        double des = __dadd_rn(lt.s_rl[start_layer], lt.min_plan_horizon);
+        const double s_last = lt.s_rl[lt.L - 1];
+        if (des > s_last) {
+            if (lt.closed)
+                des = __dsub_rn(des, s_last);
+            else
+                des = s_last;
+        }
+        // bisect.bisect_left(s_raceline, des): first index with s >= des
+        int cnt = 0;
+        for (int i = lane; i < lt.L; i += 32) cnt += (lt.s_rl[i] < des) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(LTPL_FULL, cnt, o);
+        end_layer = cnt;
+    } else {
+        const int hz = (int)lt.min_plan_horizon;
+        if (lt.closed)
+            end_layer = (start_layer + hz) % lt.L;
+        else
+            end_layer = max(start_layer + hz, lt.L - 1);  // quirk q7
+    }
+    int planning_dist = end_layer - start_layer;
+    if (planning_dist < 0) planning_dist = lt.L - start_layer + end_layer;
+    if (end_layer >= lt.L || planning_dist + 1 > hl || planning_dist + 2 > dm.h_max) {
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_CAPACITY;
+        return;
+    }
+    const int e_base = lt.edge_layer_off[start_layer];
+
+    // ---- obstacles -> blocked edges, closest object (GLNT:165-213) ----
+    int closest_dist = -1, closest_idx = -1, con_layer = -1, con_node = -1;
+    for (int v = 0; v < n_veh; ++v) {
+        const double ox = ps->vx[v], oy = ps->vy[v], rr = ps->vr[v];
+        int obj_layer = intersect_disc(lt, lane, ox, oy, rr, start_layer, end_layer, mask, e_base);
+        obj_layer = intersect_disc(lt, lane, ps->pxp[v], ps->pyp[v], rr, start_layer, end_layer, mask, e_base);  // q14
+        if (obj_layer >= 0) {
+            int ld = obj_layer - start_layer;
+            if (ld < 0) ld = lt.L - start_layer + obj_layer;
+            if (ld <= planning_dist && (closest_dist < 0 || ld < closest_dist)) {
+                closest_dist = ld;
+                closest_idx = v;
+                con_layer = obj_layer;
+            }
+        }
+    }
+    __syncwarp();
+    if (closest_dist >= 0) {  // GLNT:206-213
+        const int nb = lt.node_off[con_layer];
+        const ArgMinD m = warp_closest_point(lt.node_xy + nb, lt.node_off[con_layer + 1] - nb, ps->vx[closest_idx],
+                                             ps->vy[closest_idx], lane);
+        con_node = m.i;
+    }
+
+    // ---- objects in / beside the constant path segment (MOPG:76-122) ----
+    bool obj_in_const = false, obj_beside = false;
+    if (p0 >= 2) {
+        const double sx0 = cs[0], sy0 = cs[cplane];                        // pos_est is None on the first tick
+        const double sxe = cs[p0 - 1], sye = cs[cplane + p0 - 1];
+        const double s_start = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sx0, sy0, lane, nullptr, nullptr);
+        const double s_end = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sxe, sye, lane, nullptr, nullptr);
+        double smallest = LTPL_INF;
+        for (int v = 0; v < n_veh; ++v) {
+            const double ox = ps->vx[v], oy = ps->vy[v];
+            const double s_obj = s_coord_closed(lt.raceline, lt.s_rl, lt.L, ox, oy, lane, nullptr, nullptr);
+            if ((s_start <= s_obj && s_obj <= s_end) || (s_start > s_end && (s_obj > s_start || s_obj < s_end))) {
+                obj_beside = true;
+                double od;
+                if (s_obj < s_start)
+                    od = __dsub_rn(__dadd_rn(s_obj, lt.s_rl[lt.L - 1]), s_start);
+                else
+                    od = __dsub_rn(s_obj, s_start);
+                if (closest_idx < 0 || od < smallest) {  // quirk q15
+                    closest_idx = v;
+                    smallest = od;
+                }
+                const double oref = sq_rn(__dadd_rn(ps->vr[v], __ddiv_rn(lt.veh_width, 2.0)));
+                int hit = 0;
+                for (int k = lane; k < p0; k += 32) hit |= (dist2_rn(cs[k], cs[cplane + k], ox, oy) <= oref) ? 1 : 0;
+                if (__any_sync(LTPL_FULL, hit)) obj_in_const = true;
+            }
+        }
+    }
+    if (lane == 0) {
+        bf.closest_obj[b] = closest_idx;
+        if (closest_idx >= 0) {
+            bf.cobj[4 * b + 0] = ps->vx[closest_idx];
+            bf.cobj[4 * b + 1] = ps->vy[closest_idx];
+            bf.cobj[4 * b + 2] = ps->vv[closest_idx];
+            bf.cobj[4 * b + 3] = 1.0;
+        }
+    }
+
+    // ---- action sets (MOPG:124-174); filter: 0 planning_range, 1 default, 2 overtake_left, 3 overtake_right ----
+    int n_act, names[3], filt[3];
+    if (obj_in_const || obj_beside) {
+        n_act = 1;
+        names[0] = LTPL_ACT_FOLLOW;
+        filt[0] = 0;
+        if (!obj_in_const) {  // last_action_id is the forced "straight" on the first tick -> offer left and right
+            names[1] = LTPL_ACT_LEFT;  filt[1] = 1;
+            names[2] = LTPL_ACT_RIGHT; filt[2] = 1;
+            n_act = 3;
+        }
+    } else if (closest_idx >= 0 && con_node >= 0) {
+        n_act = 3;
+        names[0] = LTPL_ACT_FOLLOW; filt[0] = 0;
+        names[1] = LTPL_ACT_LEFT;   filt[1] = 2;
+        names[2] = LTPL_ACT_RIGHT;  filt[2] = 3;
+    } else {
+        n_act = 1;
+        names[0] = LTPL_ACT_STRAIGHT;
+        filt[0] = 1;
+    }
+
+    // ---- graph search per action (MOPG:188-257) ----
+    DpCtx c;
+    c.dist = dist;
+    c.pred = pred;
+    c.maxn = maxn;
+    const int goal_steps = planning_dist;
+    int mod_steps = goal_steps;
+    for (int a = 0; a < n_act; ++a) {
+        int name = names[a];
+        const int f = filt[a];
+        int rem_layer = -1, rem_lo = 0, rem_hi = 0;
+        if (f == 2) {  // remove nodes [n_obj, n_l) of the object's layer (MOPG:148-152)
+            rem_layer = con_layer;
+            rem_lo = con_node;
+            rem_hi = lt.node_off[con_layer + 1] - lt.node_off[con_layer];
+        } else if (f == 3) {  // remove nodes [0, n_obj) (MOPG:155-159)
+            rem_layer = con_layer;
+            rem_lo = 0;
+            rem_hi = con_node;
+        }
+        int st = 0, tie = 0, found = 0, reach = 0;
+        if (mod_steps > 0) {
+            const bool start_removed = (rem_layer == start_layer && start_node >= rem_lo && start_node < rem_hi);
+            if (start_removed) {
+                st |= LTPL_ST_START_BLOCKED;  // GB:882-885
+            } else {
+                reach = dp_run(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
+                               rem_layer, rem_lo, rem_hi, &tie);
+            }
+            if (name == LTPL_ACT_FOLLOW || name == LTPL_ACT_STRAIGHT) {
+                if (reach < mod_steps) mod_steps = reach;  // goal layer moves towards the vehicle (MOPG:203-220)
+                found = (reach >= 1);
+            } else {
+                found = (reach == mod_steps);
+            }
+        }
+        const int mod_goal = (start_layer + mod_steps) % lt.L;
+        const bool reduced = (mod_steps != goal_steps) || (!lt.closed && end_layer == lt.L - 1);
+        if (reduced) {
+            st |= LTPL_ST_REDUCED_HORIZON;
+            const bool in_mod = (con_layer >= 0) &&
+                                ((start_layer <= con_layer && con_layer <= mod_goal) ||
+                                 (start_layer > mod_goal && (con_layer >= start_layer || con_layer <= mod_goal)));
+            if (!obj_in_const && con_layer >= 0 && !in_mod) {
+                if (name == LTPL_ACT_FOLLOW || name == LTPL_ACT_STRAIGHT) {
+                    if (name == LTPL_ACT_FOLLOW) st |= LTPL_ST_RENAMED_STRAIGHT;
+                    name = LTPL_ACT_STRAIGHT;
+                } else {
+                    found = 0;
+                }
+            }
+        }
+        const int slot = (name == LTPL_ACT_LEFT) ? 1 : ((name == LTPL_ACT_RIGHT) ? 2 : 0);
+        const int q = slot * B + b;
+        if (found) {
+            const int gj = dp_goal(lt, lane, c, &tie);
+            if (tie) st |= LTPL_ST_TIE_AMBIGUOUS;
+            st |= LTPL_ST_FOUND;
+            if (lane == 0) {
+                int* nd = bf.nodes + (size_t)q * dm.h_max * 2;
+                int* es = bf.edge_seq + (size_t)q * dm.h_max;
+                nd[0] = -1;
+                nd[1] = -1;
+                int j = gj, layer = c.layer;
+                for (int li = reach; li >= 1; --li) {
+                    nd[2 * (li + 1)] = layer;
+                    nd[2 * (li + 1) + 1] = j;
+                    const int e = lt.in_off[lt.node_off[layer] + j].x + (int)pred[li * maxn + j];
+                    es[li - 1] = e;
+                    j = lt.edge_src[e];
+                    layer = (layer == 0) ? lt.L - 1 : layer - 1;
+                }
+                nd[2] = start_layer;
+                nd[3] = j;  // == start_node
+                bf.n_nodes[q] = reach + 2;
+                bf.action_id[q] = name;
+                bf.status[q] = st;
+            }
+        } else if (lane == 0 && bf.action_id[q] == LTPL_ACT_NONE) {
+            bf.status[q] = st;
+        }
+        __syncwarp();
+    }
+
+    // ---- "track blocked": no action at all -> constant segment only (OTH:475-506) ----
+    if (lane == 0) {
+        bool any = false;
+        for (int s = 0; s < LTPL_NSLOT; ++s) any |= (bf.action_id[s * B + b] != LTPL_ACT_NONE);
+        if (!any && p0 > 2) {
+            const int q = b;
+            int* nd = bf.nodes + (size_t)q * dm.h_max * 2;
+            nd[0] = -1; nd[1] = -1; nd[2] = start_layer; nd[3] = start_node;
+            bf.n_nodes[q] = 2;
+            bf.action_id[q] = LTPL_ACT_STRAIGHT;
+            bf.status[q] = LTPL_ST_FOUND | LTPL_ST_CONST_ONLY | LTPL_ST_REDUCED_HORIZON;
+        }
+    }
+}

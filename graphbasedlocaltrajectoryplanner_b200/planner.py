@@ -1,0 +1,279 @@
+"""
+BatchPlanner -- host side of the batched planning tick.  PyTorch is used ONLY as the owner of device buffers and
+streams (``tensor.data_ptr()`` / ``torch.cuda.current_stream().cuda_stream``); all compute happens in the hand-written
+sm_100a kernels behind the C-ABI (capi.py -> libltpl_b200.so).
+
+Mirrors, batched over B independent scenarios, the reference call sequence of one planning tick
+(/root/reference/main_min_example.py:69-104):
+
+    set_startpos (LTPL:262-296)  ->  calc_paths (LTPL:300-340)  ->  calc_vel_profile (LTPL:344-408)
+"""
+
+from __future__ import annotations
+
+import configparser
+import ctypes as C
+import json
+
+import numpy as np
+import torch
+
+from . import capi
+from .lattice import Lattice
+from .lattice_blob import pack_lattice
+from .scenarios import ScenarioBatch
+
+NSLOT = capi.NSLOT
+
+
+def read_online_config(path: str) -> dict:
+    """online ini keys the batched path needs (reference: OTH:99-122, LTPL:168-173)."""
+    cfg = configparser.ConfigParser()
+    if not cfg.read(path):
+        raise ValueError('Specified cost config file does not exist or is empty!')
+    ctype = cfg.get('FOLLOW', 'controller_type')
+    vp_type = cfg.get('VP', 'vp_type')
+    if vp_type != "fb":
+        raise ValueError('Only the forward-backward velocity planner (vp_type=fb) is available in the batched path!')
+    return dict(max_heading_offset=json.loads(cfg.get('GENERAL', 'max_heading_offset')),
+                nmbr_export_points=json.loads(cfg.get('EXPORT', 'nmbr_export_points')),
+                v_max_offset=cfg.getfloat('ACTIONSET', 'v_max_offset'),
+                max_solutions=cfg.getint('ACTIONSET', 'max_solutions'),
+                filt_window_width=cfg.getint('SMOOTHING', 'filt_window_width'),
+                w_last_edges=json.loads(cfg.get('COST', 'w_last_edges')),
+                controller_type=ctype,
+                control_params=json.loads(cfg.get('FOLLOW', 'control_params_' + ctype)),
+                delaycomp=cfg.getfloat('DELAY', 'delaycomp'))
+
+
+DEFAULT_ONLINE = dict(max_heading_offset=0.8, nmbr_export_points=115, v_max_offset=0.1, max_solutions=1,
+                      filt_window_width=1, w_last_edges=[0.0, 0.5, 0.8], controller_type="PD",
+                      control_params={"c_p": 1.25, "k_d": 0.025, "k_p": 0.2}, delaycomp=0.1)
+
+
+class BatchPlanner(object):
+    def __init__(self, lattice: Lattice = None, online: dict = None, device=None, veh_param_dyn_model_exp: float = 1.0,
+                 veh_param_dragcoeff: float = 0.85, veh_param_mass: float = 1000.0, packed: tuple = None,
+                 blob_tensor: torch.Tensor = None):
+        """``packed`` = (LatticeHeader, capacities) + ``blob_tensor`` (device uint8) when the blob arrived through a
+        collective instead of being uploaded from ``lattice`` (parallel.broadcast_lattice)."""
+        self.lib = capi.load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchPlanner needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:0")
+        torch.cuda.set_device(self.device)
+        self.online = dict(DEFAULT_ONLINE)
+        if online:
+            self.online.update(online)
+        if self.online["filt_window_width"] != 1:
+            raise NotImplementedError("velocity smoothing windows other than 1 (identity, shipped default) not batched")
+        self.veh = dict(dyn_model_exp=float(veh_param_dyn_model_exp), drag_coeff=float(veh_param_dragcoeff),
+                        m_veh=float(veh_param_mass))
+        if packed is None:
+            self.header, blob, self.cap = pack_lattice(lattice)
+            self.blob = torch.from_numpy(blob).to(self.device)
+        else:
+            self.header, self.cap = packed
+            self.blob = blob_tensor
+            if self.blob.device != self.device or self.blob.dtype != torch.uint8 \
+                    or self.blob.numel() != self.header.blob_bytes:
+                raise ValueError("blob tensor does not match the lattice header")
+        handle = C.c_void_p()
+        capi.check(self.lib, self.lib.ltpl_lattice_create(C.byref(self.header), C.c_void_p(self.blob.data_ptr()),
+                                                          C.byref(handle)), "ltpl_lattice_create")
+        self.handle = handle
+        self.dims = None
+        self.buf = None
+        self.t = {}
+        self.params = capi.Params()
+        self._tick_count = 0
+        self.set_vel_params()
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.ltpl_lattice_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # -- parameters ------------------------------------------------------------------------------------------------------
+    def set_vel_params(self, vel_max: float = 100.0, gg_scale: float = 1.0, local_gg=(5.0, 5.0),
+                       ax_max_machines=np.atleast_2d([100.0, 5.0]), safety_d: float = 30.0) -> None:
+        """per-call arguments of Graph_LTPL.calc_vel_profile (LTPL:344-352)."""
+        if type(local_gg) is not tuple or len(local_gg) != 2:   # OTH:651-653 (location dependent dicts: not batched)
+            raise ValueError("Provided local_gg does not satisfy requested format! Read parameter documentation.")
+        axm = np.atleast_2d(np.asarray(ax_max_machines, dtype=np.float64))
+        if axm.shape[1] != 2:
+            raise RuntimeError("ax_max_machines must consist of the two columns [vx, ax_max_machines]!")
+        if axm.shape[0] > capi.MAX_AXM:
+            raise ValueError("ax_max_machines has more than %d rows" % capi.MAX_AXM)
+        if axm[-1, 0] < vel_max:                               # tph.calc_vel_profile input check
+            raise RuntimeError("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!")
+        p = self.params
+        o = self.online
+        p.max_heading_offset = o["max_heading_offset"]
+        p.v_max_offset = o["v_max_offset"]
+        cp = o["control_params"]
+        p.follow_c_p, p.follow_k_d, p.follow_k_p = cp["c_p"], cp["k_d"], cp["k_p"]
+        p.follow_tan_w = cp.get("tan_w", 1.0)
+        if o["controller_type"] not in ("PD", "PDtan"):
+            raise ValueError('Unsupported control type "' + o["controller_type"] + '"!')
+        p.follow_control_type = 0 if o["controller_type"] == "PD" else 1
+        p.nmbr_export_points = int(o["nmbr_export_points"])
+        p.dyn_model_exp, p.drag_coeff, p.m_veh = self.veh["dyn_model_exp"], self.veh["drag_coeff"], self.veh["m_veh"]
+        p.vel_max, p.gg_scale, p.gg_ax, p.gg_ay, p.safety_d = vel_max, gg_scale, local_gg[0], local_gg[1], safety_d
+        p.n_axm = axm.shape[0]
+        for i in range(axm.shape[0]):
+            p.axm_v[i] = axm[i, 0]
+            p.axm_a[i] = axm[i, 1]
+
+    # -- buffers -----------------------------------------------------------------------------------------------------------
+    def allocate(self, batch: int, k_obj: int = 3) -> None:
+        if self.dims is not None and self.dims.batch == batch and self.dims.k_obj == max(1, k_obj):
+            return
+        k_obj = max(1, int(k_obj))
+        if k_obj > capi.KMAX:
+            raise ValueError("at most %d objects per scenario" % capi.KMAX)
+        d = capi.Dims()
+        d.batch, d.k_obj = int(batch), k_obj
+        d.p0_max, d.p_max, d.h_max = self.cap["p0_max"], self.cap["p_max"], self.cap["h_max"]
+        d.n_export = int(self.online["nmbr_export_points"])
+        B, K, P0, P, H, NE = d.batch, d.k_obj, d.p0_max, d.p_max, d.h_max, d.n_export
+        dev = self.device
+        f64, i32, f32 = torch.float64, torch.int32, torch.float32
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
+        t = dict(
+            pos=z((B, 2), f64), heading=z((B,), f64), vel=z((B,), f64), n_obj=z((B,), i32), obj=z((B, K, 5), f64),
+            sc_flags=z((B,), i32), start_node=z((B, 2), i32), const_len=z((B,), i32), const_seg=z((5, B, P0), f64),
+            const_coeff=z((B, 8), f64), action_id=z((NSLOT, B), i32), status=z((NSLOT, B), i32),
+            n_nodes=z((NSLOT, B), i32), nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
+            edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), path_len=z((NSLOT, B), i32),
+            path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), vel_scratch=z((3, NSLOT * B, P), f64),
+            s_vx_ax=z((3, NSLOT * B, P), f64), traj=z((NSLOT, B, NE, 7), f32), traj_len=z((NSLOT, B), i32),
+            traj_id=z((NSLOT, B), i32))
+        buf = capi.Buffers()
+        for name in capi.BUFFER_FIELDS:
+            setattr(buf, name, t[name].data_ptr())
+        self.t, self.buf, self.dims = t, buf, d
+        # pinned host staging for the per-tick host <-> device copies
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()   # noqa: E731
+        self.h_in = dict(pos=pin((B, 2), f64), heading=pin((B,), f64), vel=pin((B,), f64), n_obj=pin((B,), i32),
+                         obj=pin((B, K, 5), f64))
+        self.h_out = dict(traj=pin((NSLOT, B, NE, 7), f32), traj_len=pin((NSLOT, B), i32),
+                          traj_id=pin((NSLOT, B), i32), action_id=pin((NSLOT, B), i32), status=pin((NSLOT, B), i32),
+                          sc_flags=pin((B,), i32))
+
+    def device_bytes(self) -> int:
+        return int(sum(v.numel() * v.element_size() for v in self.t.values()) + self.blob.numel())
+
+    @property
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- scenario upload (host -> device) -------------------------------------------------------------------------------------
+    def h2d_bytes(self) -> int:
+        return int(sum(v.numel() * v.element_size() for v in self.h_in.values()))
+
+    def d2h_bytes(self) -> int:
+        return int(sum(v.numel() * v.element_size() for v in self.h_out.values()))
+
+    def stage_scenarios(self, sc: ScenarioBatch) -> None:
+        """copy a scenario batch into the pinned staging buffers (host-side preparation, not part of a tick)."""
+        if self.dims is None or sc.size != self.dims.batch or sc.obj.shape[1] > self.dims.k_obj:
+            self.allocate(sc.size, sc.obj.shape[1])
+        k = sc.obj.shape[1]
+        self.h_in["pos"].numpy()[...] = sc.pos
+        self.h_in["heading"].numpy()[...] = sc.heading
+        self.h_in["vel"].numpy()[...] = sc.vel
+        self.h_in["n_obj"].numpy()[...] = sc.n_obj
+        self.h_in["obj"].numpy()[...] = 0.0
+        self.h_in["obj"].numpy()[:, :k, :] = sc.obj
+
+    def upload(self) -> None:
+        for name, src in self.h_in.items():
+            self.t[name].copy_(src, non_blocking=True)
+
+    def download(self) -> dict:
+        for name, dst in self.h_out.items():
+            dst.copy_(self.t[name], non_blocking=True)
+        return self.h_out
+
+    # -- kernels ---------------------------------------------------------------------------------------------------------------
+    def _call(self, fn, what):
+        capi.check(self.lib, fn(self.handle, C.byref(self.params), C.byref(self.dims), C.byref(self.buf), self.stream),
+                   what)
+
+    def set_startpos(self) -> None:
+        self._call(self.lib.ltpl_set_startpos_batch, "ltpl_set_startpos_batch")
+
+    def calc_paths(self) -> None:
+        self._call(self.lib.ltpl_calc_paths_batch, "ltpl_calc_paths_batch")
+
+    def calc_vel_profile(self) -> None:
+        self._tick_count += 1
+        self.params.traj_base_id = 10 * self._tick_count   # OTH:669
+        self._call(self.lib.ltpl_calc_vel_profile_batch, "ltpl_calc_vel_profile_batch")
+
+    def tick(self) -> None:
+        """calc_paths + calc_vel_profile back to back."""
+        self._tick_count += 1
+        self.params.traj_base_id = 10 * self._tick_count
+        self._call(self.lib.ltpl_tick_batch, "ltpl_tick_batch")
+
+    def launch_count(self) -> int:
+        return int(self.lib.ltpl_launch_count())
+
+    # -- result access (device -> host, test / facade use) ----------------------------------------------------------------------
+    def fetch(self, *names) -> dict:
+        torch.cuda.synchronize(self.device)
+        return {n: self.t[n].cpu().numpy() for n in names}
+
+    def records(self, indices=None) -> list:
+        """per-scenario result dicts in the reference's vocabulary ({action: [ndarray]}), for parity tests and the
+        single-scenario facade.  Copies every result buffer to the host."""
+        f = self.fetch("sc_flags", "start_node", "action_id", "status", "n_nodes", "nodes", "node_idx", "closest_obj",
+                       "path_len", "path", "coeff", "s_vx_ax", "traj", "traj_len", "traj_id", "const_seg", "const_len")
+        B = self.dims.batch
+        out = []
+        for b in (range(B) if indices is None else indices):
+            rec = dict(flags=int(f["sc_flags"][b]))
+            rec["out_of_track"] = bool(rec["flags"] & (capi.SC_OUT_OF_TRACK | capi.SC_HEADING_MISMATCH))
+            if rec["flags"] & (capi.SC_CAPACITY | capi.SC_BRAKE_PREFIX):
+                rec["error"] = rec["flags"]
+            if rec["out_of_track"]:
+                out.append(rec)
+                continue
+            rec["start_node"] = f["start_node"][b].tolist()
+            co = int(f["closest_obj"][b])
+            rec["closest_obj_index"] = None if co < 0 else co
+            n0 = int(f["const_len"][b])
+            rec["const_path_seg"] = f["const_seg"][:, b, :n0].T.copy()
+            for key in ("paths", "nodes", "node_idx", "coeff", "red_len", "tie", "traj_full", "traj", "ids", "status"):
+                rec[key] = {}
+            for s in range(NSLOT):
+                a = int(f["action_id"][s, b])
+                if a == capi.ACT_NONE:
+                    continue
+                name = capi.ACTION_NAMES[a]
+                q = s * B + b
+                st = int(f["status"][s, b])
+                n = int(f["path_len"][s, b])
+                nn = int(f["n_nodes"][s, b])
+                rec["status"][name] = st
+                rec["paths"][name] = [f["path"][:, q, :n].T.copy()]
+                nodes = f["nodes"][s, b, :nn].tolist()
+                rec["nodes"][name] = [[[None, None] if p[0] < 0 else p for p in nodes]]
+                rec["node_idx"][name] = [f["node_idx"][s, b, :nn].copy()]
+                rec["coeff"][name] = [f["coeff"][q, :max(nn - 1, 1)].copy()]
+                rec["red_len"][name] = [bool(st & capi.ST_REDUCED_HORIZON)]
+                rec["tie"][name] = bool(st & capi.ST_TIE_AMBIGUOUS)
+                if st & capi.ST_TRAJ_VALID:
+                    full = np.column_stack((f["s_vx_ax"][0, q, :n], f["path"][0:4, q, :n].T, f["s_vx_ax"][1, q, :n],
+                                            f["s_vx_ax"][2, q, :n]))
+                    rec["traj_full"][name] = [full]
+                    tl = int(f["traj_len"][s, b])
+                    rec["traj"][name] = [f["traj"][s, b, :tl].astype(np.float64)]
+                    rec["ids"][name] = int(f["traj_id"][s, b])
+            out.append(rec)
+        return out

@@ -156,7 +156,8 @@ typedef struct LtplBuffers {
     int32_t* nodes;           /* [NSLOT][B][h_max][2]                                                                    */
     int32_t* node_idx;        /* [NSLOT][B][h_max] index of every node in the path arrays (MOPG:295)                     */
     int32_t* edge_seq;        /* [NSLOT][B][h_max] lattice edge ids of the new plan (scratch for path assembly)          */
-    int32_t* closest_obj;     /* [B] closest_obj_index or -1 (GLNT:191-203, MOPG:113-115)                                */
+    int32_t* closest_obj;     /* [B] closest_obj_index (into the on-track object list) or -1 (GLNT:191-203, MOPG:113)    */
+    double* cobj;             /* [B][4] x, y, v, valid of that object (OTH:770-771)                                      */
     int32_t* path_len;        /* [NSLOT][B]                                                                              */
     double* path;             /* [5][NSLOT*B][p_max] planes x, y, psi, kappa, el  (path_dict of calc_paths)              */
     double* coeff;            /* [NSLOT*B][h_max][8] (MOPG:305-309 spline_coeff_mat, stitched OTH:470-472)               */
