@@ -1,0 +1,203 @@
+"""
+``Graph_LTPL`` -- drop-in facade with the call surface of the reference class
+(/root/reference/graph_ltpl/Graph_LTPL.py:26-532) for the online planning path, executed by the sm_100a kernels.
+
+Kept signatures (same names, argument meaning, return structure and error behaviour):
+
+    Graph_LTPL(path_dict, visual_mode=False, log_to_file=True)                                   LTPL:41-181
+    graph_init(veh_param_dyn_model_exp=1.0, veh_param_dragcoeff=0.85, veh_param_mass=1000.0)     LTPL:189-258
+    set_startpos(pos_est, heading_est, vel_est=0.0) -> out_of_track                              LTPL:262-296
+    calc_paths(prev_action_id, prev_traj_idx=0, object_list=None, blocked_zones=None) -> dict    LTPL:300-340
+    calc_vel_profile(pos_est, vel_est, vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0),
+                     ax_max_machines=[[100.0, 5.0]], safety_d=30.0, incl_emerg_traj=False)
+                     -> (action_set, action_set_id, traj_time)                                   LTPL:344-408
+
+plus the batched variants ``set_startpos_batch`` / ``calc_paths_batch`` / ``calc_vel_profile_batch`` / ``plan_batch``
+over a ``ScenarioBatch`` (thousands of independent ego-start x obstacle scenarios per call).
+
+Scope: ticks are stateless -- ``calc_paths`` plans the first tick after ``set_startpos``; the reference's
+iterative memory across ticks depends on the wall clock (OTH:353-378) and is a listed next row, as are blocked zones,
+location dependent ``local_gg`` dicts and the emergency trajectory.  Offline graph generation is replaced by the flat
+lattice blob (lattice.py); logging and visualisation of the reference are out of scope.
+"""
+
+from __future__ import annotations
+
+import logging
+import time
+
+import numpy as np
+
+from . import capi
+from .lattice import load_or_build_lattice
+from .planner import BatchPlanner, read_online_config
+from .scenarios import ScenarioBatch
+
+# required path dict entries (LTPL:22-23)
+REQ_PATH_DICT_ENTRIES = ['globtraj_input_path', 'graph_store_path', 'ltpl_offline_param_path', 'ltpl_online_param_path',
+                         'graph_log_id', 'log_path']
+
+
+class Graph_LTPL(object):
+    def __init__(self, path_dict: dict, visual_mode: bool = False, log_to_file: bool = True, device=None) -> None:
+        for entry in REQ_PATH_DICT_ENTRIES:   # LTPL:62-68
+            if entry not in path_dict:
+                if log_to_file or 'log' not in entry:
+                    raise ValueError('Missing path specification in path_dict (Missing entry: "' + entry + '")!')
+        if visual_mode:
+            raise NotImplementedError("live visualisation is out of scope of the B200 planning path (SURVEY 2, row 20)")
+        self.__log = logging.getLogger("local_trajectory_logger")
+        self.__path_dict = path_dict
+        self.__device = device
+        self.__online = read_online_config(path_dict['ltpl_online_param_path'])
+        self.__planner = None
+        self.__lattice = None
+        self.__state = None          # None | "start" | "paths"
+        self.__records = None
+        self.__start_vel = 0.0
+        self.__pos = None
+        self.__heading = None
+        self.__objects = None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def graph_init(self, veh_param_dyn_model_exp: float = 1.0, veh_param_dragcoeff: float = 0.85,
+                   veh_param_mass: float = 1000.0, lattice_overrides: dict = None) -> None:
+        """load (md5-keyed cache) or build the lattice, upload it, create the planner (LTPL:189-258)."""
+        self.__lattice, _ = load_or_build_lattice(self.__path_dict['globtraj_input_path'],
+                                                  self.__path_dict['ltpl_offline_param_path'],
+                                                  store_path=self.__path_dict.get('graph_store_path'),
+                                                  overrides=lattice_overrides)
+        self.__planner = BatchPlanner(self.__lattice, online=self.__online, device=self.__device,
+                                      veh_param_dyn_model_exp=veh_param_dyn_model_exp,
+                                      veh_param_dragcoeff=veh_param_dragcoeff, veh_param_mass=veh_param_mass)
+
+    @property
+    def lattice(self):
+        return self.__lattice
+
+    @property
+    def planner(self) -> BatchPlanner:
+        if self.__planner is None:
+            raise ValueError("Graph is not initialized yet. Call graph_init() first!")
+        return self.__planner
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # single-scenario API (reference signatures)
+    # ------------------------------------------------------------------------------------------------------------------
+    def set_startpos(self, pos_est: np.ndarray, heading_est: float, vel_est: float = 0.0) -> bool:
+        if self.__planner is None:   # LTPL:277-280
+            raise ValueError("Could not set start position, since graph is not initialized yet. "
+                             "Call graph_init() first!")
+        self.__pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
+        self.__heading = float(np.asarray(heading_est).reshape(-1)[0])
+        self.__start_vel = float(vel_est)
+        sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel], [[]])
+        pl = self.__planner
+        pl.stage_scenarios(sc)
+        pl.upload()
+        pl.set_startpos()
+        flags = int(pl.fetch("sc_flags")["sc_flags"][0])
+        if flags & capi.SC_OUT_OF_TRACK:
+            self.__log.warning("Vehicle is out of track, check if correct reference line is provided!")
+        if flags & capi.SC_HEADING_MISMATCH:
+            self.__log.warning("Heading mismatch between vehicle and track grid, check if vehicle oriented correctly!")
+        if flags & capi.SC_CAPACITY:
+            raise RuntimeError("start pose too far from the lattice for the constant-segment capacity")
+        out_of_track = bool(flags & (capi.SC_OUT_OF_TRACK | capi.SC_HEADING_MISMATCH))
+        self.__state = None if out_of_track else "start"
+        return out_of_track
+
+    def calc_paths(self, prev_action_id: str, prev_traj_idx: int = 0, object_list: list = None,
+                   blocked_zones: dict = None) -> dict:
+        if blocked_zones:
+            raise NotImplementedError("blocked zones are not part of the batched planning path yet (SURVEY 8(f) rank 3)")
+        if self.__state is None:
+            raise NotImplementedError("calc_paths() plans the first tick after set_startpos(); the reference's "
+                                      "wall-clock dependent multi-tick memory (OTH:346-414) is SURVEY 8(f) rank 1")
+        sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel],
+                                             [[o for o in (object_list or []) if o.get('type') == 'physical']])
+        for o in (object_list or []):
+            if o.get('type') != 'physical':   # OLI:140-141
+                self.__log.warning("Found non-supported object of type '%s' in object list!" % o.get('type'))
+        pl = self.__planner
+        pl.stage_scenarios(sc)
+        pl.upload()
+        pl.set_startpos()
+        pl.calc_paths()
+        self.__records = pl.records()[0]
+        self.__state = "paths"
+        if not self.__records["paths"]:
+            self.__log.critical("Could not find a path solution for any of the points in the given destination layer! "
+                                "Track useems to be blocked.")
+        return {k: [a.copy() for a in v] for k, v in self.__records["paths"].items()}
+
+    def calc_vel_profile(self, pos_est: np.ndarray, vel_est: float, vel_max: float = 100.0, gg_scale: float = 1.0,
+                         local_gg: dict = (5.0, 5.0), ax_max_machines: np.ndarray = np.atleast_2d([100.0, 5.0]),
+                         safety_d: float = 30.0, incl_emerg_traj: bool = False) -> tuple:
+        if self.__state != "paths":
+            raise ValueError("calc_paths() must be called before calc_vel_profile()")
+        if incl_emerg_traj:
+            raise NotImplementedError("the optional emergency trajectory is SURVEY 8(f) rank 4")
+        if type(local_gg) is dict:
+            raise NotImplementedError("location dependent friction (local_gg dict) is not batched yet; pass a tuple")
+        pl = self.__planner
+        pl.set_vel_params(vel_max=vel_max, gg_scale=gg_scale, local_gg=local_gg, ax_max_machines=ax_max_machines,
+                          safety_d=safety_d)
+        pl.t["vel_est"].fill_(float(vel_est))
+        pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
+        if not np.array_equal(pos, self.__pos):
+            # the position estimate only enters the follow-mode distance (OTH:779-784) on the first tick
+            pl.h_in["pos"].numpy()[0] = pos
+            pl.t["pos"].copy_(pl.h_in["pos"])
+        pl.calc_vel_profile()
+        rec = pl.records()[0]
+        if rec.get("error", 0) & capi.SC_BRAKE_PREFIX:
+            raise ValueError("vel_plan exceeds vel_max: the reference's brake-prefix branch (OTH:747-754) yields arrays "
+                             "of mismatching length and raises; not planned")
+        self.__records = rec
+        for name, st in rec["status"].items():
+            if st & capi.ST_TOO_CLOSE:
+                self.__log.warning("Too close to object! Entering safety distance... [Follow-Mode]")
+            if (st & capi.ST_VEL_BOUND_VIOL) and not (st & capi.ST_TRAJ_VALID):
+                self.__log.warning("Removed action set, since vel constraints were broken! (Action Set: " + name + ")")
+        self.__state = None
+        return ({k: [a.copy() for a in v] for k, v in rec["traj"].items()}, dict(rec["ids"]), time.time())
+
+    def last_node_sequences(self) -> dict:
+        """node sequences of the last calc_paths() call ({action: [[[layer, node], ...]]}, cf. OTH:509)."""
+        return {} if self.__records is None else dict(self.__records["nodes"])
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # batched API
+    # ------------------------------------------------------------------------------------------------------------------
+    def set_startpos_batch(self, scenarios: ScenarioBatch, vel_est=None) -> None:
+        pl = self.planner
+        pl.stage_scenarios(scenarios, vel_est=vel_est)
+        pl.upload()
+        pl.set_startpos()
+
+    def calc_paths_batch(self) -> None:
+        self.planner.calc_paths()
+
+    def calc_vel_profile_batch(self, **vel_kwargs) -> dict:
+        pl = self.planner
+        if vel_kwargs:
+            pl.set_vel_params(**vel_kwargs)
+        pl.calc_vel_profile()
+        return pl.download()
+
+    def plan_batch(self, scenarios: ScenarioBatch = None, synchronize: bool = True) -> dict:
+        """One end-to-end batched tick: host scenario arrays -> (H2D) -> set_startpos -> calc_paths -> calc_vel_profile
+        -> (D2H) -> pinned host action sets {traj [NSLOT][B][n_export][7] fp32, traj_len, traj_id, action_id, status,
+        sc_flags}.  With ``scenarios=None`` the previously staged batch is planned again."""
+        pl = self.planner
+        if scenarios is not None:
+            pl.stage_scenarios(scenarios)
+        pl.upload()
+        pl.set_startpos()
+        pl.tick()
+        out = pl.download()
+        if synchronize:
+            import torch
+            torch.cuda.current_stream(pl.device).synchronize()
+        return out

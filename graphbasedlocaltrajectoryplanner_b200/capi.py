@@ -62,7 +62,7 @@ class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "k_obj", "p0_max", "p_max", "h_max", "n_export", "pad0", "pad1")]
 
 
-BUFFER_FIELDS = ("pos", "heading", "vel", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
+BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
                  "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj",
                  "path_len", "path", "coeff", "vel_scratch", "s_vx_ax", "traj", "traj_len", "traj_id")
 
@@ -78,7 +78,7 @@ class VelBatch(C.Structure):
 
 EXPORTS = ("ltpl_version", "ltpl_last_error", "ltpl_sizeof", "ltpl_lattice_create", "ltpl_lattice_destroy",
            "ltpl_set_startpos_batch", "ltpl_calc_paths_batch", "ltpl_calc_vel_profile_batch", "ltpl_tick_batch",
-           "ltpl_velprofile_batch", "ltpl_launch_count")
+           "ltpl_velprofile_batch", "ltpl_launch_count", "ltpl_launch_stage")
 
 
 def build_library(verbose: bool = False) -> str:
@@ -124,6 +124,9 @@ def load_library():
                lib.ltpl_tick_batch):
         fn.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Dims), C.POINTER(Buffers), C.c_void_p]
         fn.restype = C.c_int
+    lib.ltpl_launch_stage.argtypes = [C.c_int, C.c_void_p, C.POINTER(Params), C.POINTER(Dims), C.POINTER(Buffers),
+                                      C.c_void_p]
+    lib.ltpl_launch_stage.restype = C.c_int
     lib.ltpl_velprofile_batch.argtypes = [C.POINTER(Params), C.POINTER(VelBatch), C.c_void_p]
     lib.ltpl_velprofile_batch.restype = C.c_int
     if lib.ltpl_version() != ABI_VERSION:

@@ -191,6 +191,43 @@ int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDim
     return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
 }
 
+int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,
+                      const LtplBuffers* bf, void* stream) {
+    if (int r = check_common(lat, prm, dm, bf)) return r;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nq = LTPL_NSLOT * dm->batch;
+    switch (stage) {
+        case 0: return ltpl_set_startpos_batch(lat, prm, dm, bf, stream);
+        case 1:
+        case 2: {
+            const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
+            const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
+            const size_t smem_plan = plan_smem_bytes_per_warp(maxn, dm->h_max, mask_words) * LTPL_WARPS_PER_CTA;
+            const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
+            if (stage == 1) {
+                if (smem_plan > 48 * 1024)
+                    cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
+                k_plan<<<(dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem_plan,
+                         st>>>(lat->d, *prm, *dm, *bf, maxn, dm->h_max, mask_words);
+                return check_launch("k_plan");
+            }
+            if (smem_path > 48 * 1024)
+                cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path);
+            k_path<<<(nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(
+                lat->d, *prm, *dm, *bf);
+            return check_launch("k_path");
+        }
+        case 3:
+            k_vel<<<(nq + 127) / 128, 128, 0, st>>>(lat->d, *prm, *dm, *bf);
+            return check_launch("k_vel");
+        case 4:
+            k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT,
+                       LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(*dm, *bf);
+            return check_launch("k_export");
+        default: return fail("ltpl_launch_stage: unknown stage");
+    }
+}
+
 int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* stream) {
     if (!prm || !vb) return fail("null argument");
     if (vb->n_paths <= 0 || vb->n_points < 2) return fail("velprofile: need n_paths > 0 and n_points >= 2");

@@ -319,7 +319,7 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
     double* ax = vx + pplane;
 
     const double vel_plan = bf.vel[b];  // __v_start (OTH:595)
-    const double vel_est = bf.vel[b];
+    const double vel_est = bf.vel_est[b];
     if (vel_plan > prm.vel_max + 0.1) {  // VPFB:106: brake prefix -> the reference raises further down (see header)
         atomicOr(&bf.sc_flags[b], LTPL_SC_BRAKE_PREFIX);
         return;

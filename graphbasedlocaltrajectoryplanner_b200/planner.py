@@ -144,7 +144,8 @@ class BatchPlanner(object):
         f64, i32, f32 = torch.float64, torch.int32, torch.float32
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
         t = dict(
-            pos=z((B, 2), f64), heading=z((B,), f64), vel=z((B,), f64), n_obj=z((B,), i32), obj=z((B, K, 5), f64),
+            pos=z((B, 2), f64), heading=z((B,), f64), vel=z((B,), f64), vel_est=z((B,), f64), n_obj=z((B,), i32),
+            obj=z((B, K, 5), f64),
             sc_flags=z((B,), i32), start_node=z((B, 2), i32), const_len=z((B,), i32), const_seg=z((5, B, P0), f64),
             const_coeff=z((B, 8), f64), action_id=z((NSLOT, B), i32), status=z((NSLOT, B), i32),
             n_nodes=z((NSLOT, B), i32), nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
@@ -158,7 +159,8 @@ class BatchPlanner(object):
         self.t, self.buf, self.dims = t, buf, d
         # pinned host staging for the per-tick host <-> device copies
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()   # noqa: E731
-        self.h_in = dict(pos=pin((B, 2), f64), heading=pin((B,), f64), vel=pin((B,), f64), n_obj=pin((B,), i32),
+        self.h_in = dict(pos=pin((B, 2), f64), heading=pin((B,), f64), vel=pin((B,), f64), vel_est=pin((B,), f64),
+                         n_obj=pin((B,), i32),
                          obj=pin((B, K, 5), f64))
         self.h_out = dict(traj=pin((NSLOT, B, NE, 7), f32), traj_len=pin((NSLOT, B), i32),
                           traj_id=pin((NSLOT, B), i32), action_id=pin((NSLOT, B), i32), status=pin((NSLOT, B), i32),
@@ -178,7 +180,7 @@ class BatchPlanner(object):
     def d2h_bytes(self) -> int:
         return int(sum(v.numel() * v.element_size() for v in self.h_out.values()))
 
-    def stage_scenarios(self, sc: ScenarioBatch) -> None:
+    def stage_scenarios(self, sc: ScenarioBatch, vel_est=None) -> None:
         """copy a scenario batch into the pinned staging buffers (host-side preparation, not part of a tick)."""
         if self.dims is None or sc.size != self.dims.batch or sc.obj.shape[1] > self.dims.k_obj:
             self.allocate(sc.size, sc.obj.shape[1])
@@ -186,6 +188,7 @@ class BatchPlanner(object):
         self.h_in["pos"].numpy()[...] = sc.pos
         self.h_in["heading"].numpy()[...] = sc.heading
         self.h_in["vel"].numpy()[...] = sc.vel
+        self.h_in["vel_est"].numpy()[...] = sc.vel if vel_est is None else vel_est
         self.h_in["n_obj"].numpy()[...] = sc.n_obj
         self.h_in["obj"].numpy()[...] = 0.0
         self.h_in["obj"].numpy()[:, :k, :] = sc.obj

@@ -140,7 +140,8 @@ typedef struct LtplBuffers {
     /* scenario inputs (Graph_LTPL.set_startpos / calc_paths arguments)                                                 */
     const double* pos;        /* [B][2]                                                                                  */
     const double* heading;    /* [B]                                                                                     */
-    const double* vel;        /* [B]  start velocity == vel_est of the first tick                                        */
+    const double* vel;        /* [B]  start velocity of set_startpos (planned velocity of the first tick, OTH:595)       */
+    const double* vel_est;    /* [B]  velocity estimate passed to calc_vel_profile (follow-mode controller, OTH:794)     */
     const int32_t* n_obj;     /* [B]                                                                                     */
     const double* obj;        /* [B][K][5] X, Y, theta, v, length (OLI:96-141)                                           */
     /* set_startpos results (OTH:262-268 iterative memory of the forced 'straight' action)                               */
@@ -202,6 +203,10 @@ int ltpl_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, c
 /* calc_paths + calc_vel_profile back to back (one planning tick)                                                        */
 int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims, const LtplBuffers* buf,
                     void* stream);
+/* one kernel of the tick on its own (profiling / per-kernel roofline timing in bench.py):                               */
+/* stage 0 k_startpos, 1 k_plan, 2 k_path, 3 k_vel, 4 k_export                                                            */
+int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims,
+                      const LtplBuffers* buf, void* stream);
 /* tph.calc_vel_profile(closed=False, loc_gg mode) over dense arrays                                                     */
 int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* stream);
 

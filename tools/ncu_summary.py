@@ -1,0 +1,31 @@
+"""summarise an .ncu-rep (ncu --set full) into a small text table: python tools/ncu_summary.py in.ncu-rep out.txt"""
+import csv, subprocess, sys
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio',
+        'smsp__average_warp_latency_per_inst_issued.ratio', 'launch__registers_per_thread',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__grid_size',
+        'launch__block_size', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio']
+raw = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], stdout=subprocess.PIPE, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr, units = rows[0], rows[1]
+out = []
+for r in rows[2:]:
+    out.append("== %s  (launch id %s)" % (r[hdr.index('Kernel Name')], r[hdr.index('ID')]))
+    for k in KEYS:
+        if k in hdr:
+            out.append("   %-82s %18s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
+    rd, wr = float(r[hdr.index('dram__bytes_read.sum')]), float(r[hdr.index('dram__bytes_write.sum')])
+    out.append("   %-82s %18.3f %s" % ("traffic = dram read + write", rd + wr, units[hdr.index('dram__bytes_read.sum')]))
+open(sys.argv[2], 'w').write("\n".join(out) + "\n")
+print("\n".join(out))
