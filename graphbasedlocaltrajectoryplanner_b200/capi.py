@@ -55,7 +55,7 @@ class Params(C.Structure):
                 ("dyn_model_exp", C.c_double), ("drag_coeff", C.c_double), ("m_veh", C.c_double),
                 ("vel_max", C.c_double), ("gg_scale", C.c_double), ("gg_ax", C.c_double), ("gg_ay", C.c_double),
                 ("safety_d", C.c_double), ("n_axm", C.c_int32), ("traj_base_id", C.c_int32),
-                ("axm_v", C.c_double * MAX_AXM), ("axm_a", C.c_double * MAX_AXM)]
+                ("axm_v", C.c_double * MAX_AXM), ("axm_a", C.c_double * MAX_AXM), ("axm_s", C.c_double * MAX_AXM)]
 
 
 class Dims(C.Structure):
@@ -64,7 +64,7 @@ class Dims(C.Structure):
 
 BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
                  "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj",
-                 "path_len", "path", "coeff", "vel_scratch", "s_vx_ax", "traj", "traj_len", "traj_id")
+                 "path_len", "path", "coeff", "queue", "queue_cnt", "vel_scratch", "s_vx_ax", "traj", "traj_len", "traj_id")
 
 
 class Buffers(C.Structure):

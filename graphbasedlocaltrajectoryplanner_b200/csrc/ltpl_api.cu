@@ -9,6 +9,12 @@
 #include <string>
 
 #define LTPL_WARPS_PER_CTA_EXPORT 8
+#define LTPL_VEL_BLOCK 64
+#ifndef LTPL_VEL_LANES
+#define LTPL_VEL_LANES 8   // work items (paths) per warp in k_vel, see ltpl_vel.cuh
+#endif
+// threads needed so that every queued path gets a lane (both queue classes padded to LTPL_VEL_LANES)
+#define LTPL_VEL_GRID(nq) ((int)((((size_t)(nq) / LTPL_VEL_LANES + 2) * 32 + LTPL_VEL_BLOCK - 1) / LTPL_VEL_BLOCK))
 #include "ltpl_path.cuh"
 #include "ltpl_plan.cuh"
 #include "ltpl_vel.cuh"
@@ -153,6 +159,7 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
             return fail("cudaFuncSetAttribute(k_path) failed");
         attr_path = smem_path;
     }
+    if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
     const int grid_plan = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
     k_plan<<<grid_plan, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
     if (int r = check_launch("k_plan")) return r;
@@ -165,7 +172,7 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
 static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                       cudaStream_t st) {
     const int nq = LTPL_NSLOT * dm->batch;
-    k_vel<<<(nq + 127) / 128, 128, 0, st>>>(lat->d, *prm, *dm, *bf);
+    k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
     if (int r = check_launch("k_vel")) return r;
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
         *dm, *bf);
@@ -213,12 +220,14 @@ int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, 
             }
             if (smem_path > 48 * 1024)
                 cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path);
+            if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess)
+                return fail("memset(queue_cnt) failed");
             k_path<<<(nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(
                 lat->d, *prm, *dm, *bf);
             return check_launch("k_path");
         }
         case 3:
-            k_vel<<<(nq + 127) / 128, 128, 0, st>>>(lat->d, *prm, *dm, *bf);
+            k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
             return check_launch("k_vel");
         case 4:
             k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT,
@@ -234,8 +243,20 @@ int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* s
     if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");
     if (prm->axm_v[prm->n_axm - 1] < prm->vel_max)
         return fail("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!");
-    k_velprofile_dense<<<(vb->n_paths + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
+    k_velprofile_dense<<<(vb->n_paths + LTPL_VEL_BLOCK - 1) / LTPL_VEL_BLOCK, LTPL_VEL_BLOCK, 0,
+                         static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
     return check_launch("k_velprofile_dense");
 }
+
+#ifdef LTPL_PROFILE_PHASES
+int ltpl_debug_phases(unsigned long long* out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, g_phase, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_phase, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 }  // extern "C"

@@ -104,10 +104,11 @@ __device__ __forceinline__ ArgMinD warp_argmin(double v, int i) {
 }
 
 // np.argmin of squared distances between pos and n points (closest_path_index.py:24-30, GIE:41-42, GB:341-345)
-__device__ __forceinline__ ArgMinD warp_closest_point(const double2* __restrict__ pts, int n, double px, double py,
+__device__ __noinline__ ArgMinD warp_closest_point(const double2* __restrict__ pts, int n, double px, double py,
                                                       int lane) {
     double bv = LTPL_INF;
     int bi = 0x7fffffff;
+    #pragma unroll 1
     for (int i = lane; i < n; i += 32) {
         double2 p = pts[i];
         double d = dist2_rn(p.x, p.y, px, py);
@@ -121,7 +122,7 @@ __device__ __forceinline__ ArgMinD warp_closest_point(const double2* __restrict_
 
 // get_s_coord.py:8-99 on a CLOSED polyline with explicit s_array (s_array[0] <= 0.05, i.e. no leading-zero insertion).
 // Warp-collective; returns the s coordinate; idx_out = closest_indexes (pair)
-__device__ __forceinline__ double s_coord_closed(const double2* __restrict__ pts, const double* __restrict__ s_arr, int n,
+__device__ __noinline__ double s_coord_closed(const double2* __restrict__ pts, const double* __restrict__ s_arr, int n,
                                                  double px, double py, int lane, int* i0_out, int* i1_out) {
     ArgMinD m = warp_closest_point(pts, n, px, py, lane);
     int nb = m.i;
@@ -161,7 +162,7 @@ __device__ __forceinline__ double s_coord_closed(const double2* __restrict__ pts
 }
 
 // check_inside_bounds.py:26-59 (warp-collective)
-__device__ __forceinline__ bool inside_bounds(const LatDev& lt, double px, double py, int lane) {
+__device__ __noinline__ bool inside_bounds(const LatDev& lt, double px, double py, int lane) {
     int i0, i1;
     {
         // get_s_coord(centerline, pos, only_index=True, closed=True)[1]
@@ -186,6 +187,7 @@ __device__ __forceinline__ bool inside_bounds(const LatDev& lt, double px, doubl
     double stx = __ddiv_rn(c1.x - c0.x, 49.0), sty = __ddiv_rn(c1.y - c0.y, 49.0);
     double bv = LTPL_INF;
     int bi = 0x7fffffff;
+    #pragma unroll 1
     for (int k = lane; k < 50; k += 32) {
         double cx = (k == 49) ? c1.x : __dadd_rn(__dmul_rn((double)k, stx), c0.x);
         double cy = (k == 49) ? c1.y : __dadd_rn(__dmul_rn((double)k, sty), c0.y);

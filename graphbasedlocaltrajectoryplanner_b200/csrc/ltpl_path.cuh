@@ -11,6 +11,14 @@ __host__ __device__ inline size_t path_smem_bytes_per_warp(int h_max) {
     return (s + 15) & ~(size_t)15;
 }
 
+// append path q to the dense work queue of its class (0: follow, 1: straight / left / right) for k_vel
+__device__ __forceinline__ void enqueue_path(const LtplBuffers& bf, const LtplDims& dm, int q) {
+    const int nq = LTPL_NSLOT * dm.batch;
+    const int cls = (bf.action_id[q] == LTPL_ACT_FOLLOW) ? 0 : 1;
+    const int pos = atomicAdd(&bf.queue_cnt[cls], 1);
+    if (pos < nq) bf.queue[cls * nq + pos] = q;
+}
+
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
 k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,6 +63,7 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             node_idx[1] = p0 - 1;
             for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
             bf.path_len[q] = p0;
+            enqueue_path(bf, dm, q);
         }
         return;
     }
@@ -141,6 +150,7 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         node_idx[0] = 0;
         for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
         bf.path_len[q] = p_tot;
+        enqueue_path(bf, dm, q);
     }
     for (int i = lane; i < nseg; i += 32) {
         const double e0 = kel[i];

@@ -93,6 +93,7 @@ k_startpos(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplB
     const double dstep = len / (double)(p0 - 1);
     const size_t plane = (size_t)dm.batch * dm.p0_max;
     double* cs = bf.const_seg + (size_t)b * dm.p0_max;
+    #pragma unroll 1
     for (int k = lane; k < p0; k += 32) {
         double t, x, y, tn, xn, yn;
         if (k < p0 - 1) {
@@ -149,11 +150,13 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
                                       const unsigned* __restrict__ mask, int e_base, int rem_layer, int rem_lo,
                                       int rem_hi, int* tie_out) {
     const int maxn = c.maxn;
+    #pragma unroll 1
     for (int j = lane; j < maxn; j += 32) c.dist[j] = LTPL_INF;
     __syncwarp();
     if (lane == 0) c.dist[start_node] = 0.0;
     __syncwarp();
     int cur = 0, tie = 0, reach = 0, layer = start_layer;
+    #pragma unroll 1
     for (int li = 1; li <= n_steps; ++li) {
         int nxt = layer + 1;
         if (nxt >= lt.L) nxt = 0;
@@ -162,11 +165,13 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
         const double* dcur = c.dist + cur * maxn;
         double* dnxt = c.dist + (cur ^ 1) * maxn;
         int any = 0;
+        #pragma unroll 1
         for (int j = lane; j < maxn; j += 32) {
             double best = LTPL_INF, best_ds = LTPL_INF;
             int best_k = 255;
             if (j < nl && !(nxt == rem_layer && j >= rem_lo && j < rem_hi)) {
                 const int2 io = lt.in_off[nbase + j];
+                #pragma unroll 1
                 for (int k = 0; k < io.y; ++k) {
                     const int e = io.x + k;
                     const double ds = dcur[lt.edge_src[e]];
@@ -211,6 +216,7 @@ __device__ __forceinline__ int dp_goal(const LatDev& lt, int lane, const DpCtx& 
     const double* d = c.dist + c.cur * c.maxn;
     double best = LTPL_INF, best_ds = LTPL_INF;
     int best_j = 0x7fffffff, tie = 0;
+    #pragma unroll 1
     for (int j = lane; j < nl; j += 32) {
         const double ds = d[j];
         if (!(ds < LTPL_INF)) continue;
@@ -261,6 +267,7 @@ __device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, do
     const int e0 = lt.edge_layer_off[a], e1 = lt.edge_layer_off[a + 1];
     if (e1 <= e0) return;
     const int s0 = lt.samp_off[e0], s1 = lt.samp_off[e1];
+    #pragma unroll 1
     for (int s = s0 + lane; s < s1; s += 32) {
         const double2 p = lt.samp_xy[s];
         const double x = __dsub_rn(p.x, ox), y = __dsub_rn(p.y, oy);
@@ -274,7 +281,7 @@ __device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, do
 }
 
 // get_intersec_edges (GIE:36-63) for one disc; returns obj_layer or -1 when outside the planning range
-__device__ __forceinline__ int intersect_disc(const LatDev& lt, int lane, double ox, double oy, double radius,
+__device__ __noinline__ int intersect_disc(const LatDev& lt, int lane, double ox, double oy, double radius,
                                               int p_start, int p_end, unsigned* mask, int e_base) {
     const ArgMinD m = warp_closest_point(lt.refline, lt.L, ox, oy, lane);
     const int o = m.i;
@@ -322,6 +329,8 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         bf.status[lane * B + b] = 0;
         bf.n_nodes[lane * B + b] = 0;
         bf.path_len[lane * B + b] = 0;
+        bf.traj_len[lane * B + b] = 0;
+        bf.traj_id[lane * B + b] = -1;
     }
     if (lane == 0) {
         bf.closest_obj[b] = -1;
@@ -339,6 +348,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     {
         int n_in = bf.n_obj[b];
         if (n_in > dm.k_obj) n_in = dm.k_obj;
+        #pragma unroll 1
         for (int k = 0; k < n_in; ++k) {
             const double* o = bf.obj + ((size_t)b * dm.k_obj + k) * 5;
             const double ox = o[0], oy = o[1];
@@ -356,6 +366,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             }
         }
     }
+    #pragma unroll 1
     for (int i = lane; i < mask_words; i += 32) mask[i] = 0u;
     __syncwarp();
 
@@ -372,6 +383,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         }
         // bisect.bisect_left(s_raceline, des): first index with s >= des
         int cnt = 0;
+        #pragma unroll 1
         for (int i = lane; i < lt.L; i += 32) cnt += (lt.s_rl[i] < des) ? 1 : 0;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(LTPL_FULL, cnt, o);
@@ -393,6 +405,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
 
     // ---- obstacles -> blocked edges, closest object (GLNT:165-213) ----
     int closest_dist = -1, closest_idx = -1, con_layer = -1, con_node = -1;
+    #pragma unroll 1
     for (int v = 0; v < n_veh; ++v) {
         const double ox = ps->vx[v], oy = ps->vy[v], rr = ps->vr[v];
         int obj_layer = intersect_disc(lt, lane, ox, oy, rr, start_layer, end_layer, mask, e_base);
@@ -423,6 +436,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         const double s_start = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sx0, sy0, lane, nullptr, nullptr);
         const double s_end = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sxe, sye, lane, nullptr, nullptr);
         double smallest = LTPL_INF;
+        #pragma unroll 1
         for (int v = 0; v < n_veh; ++v) {
             const double ox = ps->vx[v], oy = ps->vy[v];
             const double s_obj = s_coord_closed(lt.raceline, lt.s_rl, lt.L, ox, oy, lane, nullptr, nullptr);
@@ -439,6 +453,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
                 }
                 const double oref = sq_rn(__dadd_rn(ps->vr[v], __ddiv_rn(lt.veh_width, 2.0)));
                 int hit = 0;
+                #pragma unroll 1
                 for (int k = lane; k < p0; k += 32) hit |= (dist2_rn(cs[k], cs[cplane + k], ox, oy) <= oref) ? 1 : 0;
                 if (__any_sync(LTPL_FULL, hit)) obj_in_const = true;
             }
@@ -483,6 +498,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     c.maxn = maxn;
     const int goal_steps = planning_dist;
     int mod_steps = goal_steps;
+    #pragma unroll 1
     for (int a = 0; a < n_act; ++a) {
         int name = names[a];
         const int f = filt[a];
@@ -540,6 +556,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
                 nd[0] = -1;
                 nd[1] = -1;
                 int j = gj, layer = c.layer;
+                #pragma unroll 1
                 for (int li = reach; li >= 1; --li) {
                     nd[2 * (li + 1)] = layer;
                     nd[2 * (li + 1) + 1] = j;

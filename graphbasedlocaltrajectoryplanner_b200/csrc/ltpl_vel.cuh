@@ -1,120 +1,216 @@
 // ltpl_vel.cuh -- forward/backward ggv-limited velocity profiles.
-//   device functions: ax_poss (tph.calc_ax_poss), brake_profile (tph.calc_vel_profile_brake), fb_profile
-//   (tph.calc_vel_profile, closed=False, loc_gg mode), follow_profile (helper_funcs/calc_vel_profile_follow.py:78-313)
+//   device functions: acc_tire / acc_forw / acc_decel (tph.calc_ax_poss), brake_profile_w (tph.calc_vel_profile_brake),
+//   fb_profile_w (tph.calc_vel_profile, closed=False, loc_gg mode), follow_profile
+//   (helper_funcs/calc_vel_profile_follow.py:78-313)
 //   kernels: k_vel (OTH.calc_vel_profile per action, OTH:688-1025), k_export (OTH:941 + LTPL:401-406),
 //            k_velprofile_dense (stand-alone solver over dense arrays, BASELINE config 5)
-// One THREAD per path: the solver is a serial recurrence over the points of one path (SURVEY hard part 4).
+//
+// One THREAD per path: the solver is a serial recurrence over the points of one path (SURVEY hard part 4), so the
+// kernel is bound by the latency of the dependent chain of one path, not by bandwidth.  Two algebraic rewrites keep
+// that chain short while staying in float64:
+//   * the recurrences are carried in w = v^2: v_next^2 = v^2 + 2 a(v^2) ds needs no sqrt and no division on the chain
+//     (ay_used = v^2 / radius = w * |kappa|); only the machine limit of the forward pass needs v = sqrt(w).
+//     vx = sqrt(w) and ax = (w1 - w0) / (2 ds) are evaluated afterwards, off the chain.  Differences to the
+//     reference's v-domain arithmetic are O(1e-16) relative.
+//   * "is index i the start of an acceleration phase" (tph scans the INITIAL profile for rising edges) only needs the
+//     original values at i-1, i, i+1, which are still unmodified when the single forward / backward scan reaches i.
 #pragma once
 #include "ltpl_common.cuh"
 
+// optional phase timing (debug builds only: -DLTPL_PROFILE_PHASES): cycles per phase summed over lane 0 of every warp
+#ifdef LTPL_PROFILE_PHASES
+__device__ unsigned long long g_phase[16];
+#define LTPL_PH_INIT long long _t0 = clock64();
+#define LTPL_PH(k)                                                                                   \
+    {                                                                                                \
+        long long _t1 = clock64();                                                                   \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[k], (unsigned long long)(_t1 - _t0));        \
+        _t0 = clock64();                                                                             \
+    }
+#else
+#define LTPL_PH_INIT
+#define LTPL_PH(k)
+#endif
+
 struct VelCfg {
-    double ax_max, ay_max;  // local gg * gg_scale (VPFB:213-214)
-    double exp_, drag, mass;
+    double ax_max, ay_max, inv_ay;  // local gg * gg_scale (VPFB:213-214)
+    double exp_, dm;                // friction-ellipse exponent, drag_coeff / m_veh
     const double* axm_v;
     const double* axm_a;
+    const double* axm_s;
     int n_axm;
 };
 
-enum { MODE_ACCEL_FORW = 0, MODE_DECEL_FORW = 1, MODE_DECEL_BACKW = 2 };
-
-__device__ __forceinline__ double radius_of(double kappa) {
-    // radii = abs(1 / kappa), inf where kappa == 0
-    return (kappa != 0.0) ? fabs(1.0 / kappa) : LTPL_INF;
+__device__ __forceinline__ VelCfg make_velcfg(const LtplParams& prm) {
+    VelCfg c;
+    c.ax_max = prm.gg_ax * prm.gg_scale;
+    c.ay_max = prm.gg_ay * prm.gg_scale;
+    c.inv_ay = 1.0 / c.ay_max;
+    c.exp_ = prm.dyn_model_exp;
+    c.dm = prm.drag_coeff / prm.m_veh;
+    c.axm_v = prm.axm_v;
+    c.axm_a = prm.axm_a;
+    c.axm_s = prm.axm_s;
+    c.n_axm = prm.n_axm;
+    return c;
 }
 
-// tph.calc_vel_profile.calc_ax_poss with a single-row ggv (loc_gg mode: no velocity dependence), mu = 1
-__device__ __forceinline__ double ax_poss(double v, double radius, double ax_max_tires, double ay_max_tires, int mode,
-                                          const VelCfg& c) {
-    const double v2 = v * v;
-    const double ay_used = v2 / radius;
-    const double ratio = ay_used / ay_max_tires;
-    const double radicand = 1.0 - ((c.exp_ == 1.0) ? ratio : pow(ratio, c.exp_));
-    double avail = 0.0;
-    if (radicand > 0.0) avail = ax_max_tires * ((c.exp_ == 1.0) ? radicand : pow(radicand, 1.0 / c.exp_));
-    if (mode == MODE_ACCEL_FORW) {
-        const double axm = interp_table(v, c.axm_v, c.axm_a, c.n_axm);
-        avail = fmin(avail, axm);
+// available longitudinal tyre acceleration at w = v^2 on curvature |kappa| (friction ellipse with exponent exp)
+__device__ __forceinline__ double acc_tire(double w, double kabs, double ax_max, double inv_ay, double exp_) {
+    const double ratio = w * kabs * inv_ay;  // ay_used / ay_max, ay_used = v^2 / radius
+    if (exp_ == 1.0) {
+        const double radicand = 1.0 - ratio;
+        return (radicand > 0.0) ? ax_max * radicand : 0.0;
     }
-    const double ax_drag = -v2 * c.drag / c.mass;
-    return (mode == MODE_DECEL_BACKW) ? (avail - ax_drag) : (avail + ax_drag);
+    const double radicand = 1.0 - pow(ratio, exp_);
+    return (radicand > 0.0) ? ax_max * pow(radicand, 1.0 / exp_) : 0.0;
 }
 
-// tph.calc_vel_profile_brake: v[0] = v_start, forward integration with full braking, zeros after standstill
-__device__ __forceinline__ void brake_profile(const double* kap, const double* el, int n, double v_start,
-                                              double ax_max, double ay_max, const VelCfg& c, double* v) {
+// np.interp on the machine table with a moving hint (v changes slowly along a path)
+__device__ __forceinline__ double interp_hint(double v, const double* __restrict__ xp, const double* __restrict__ fp,
+                                              const double* __restrict__ sp, int n, int& j) {
+    if (v <= xp[0]) return fp[0];
+    if (v >= xp[n - 1]) return fp[n - 1];
+    while (j < n - 2 && v >= xp[j + 1]) ++j;
+    while (j > 0 && v < xp[j]) --j;
+    return fma(sp[j], v - xp[j], fp[j]);
+}
+
+// mode 'accel_forw': min(tyre, machine(v)) + drag,  drag = -v^2 drag_coeff / m
+__device__ __forceinline__ double acc_forw(double w, double kabs, const VelCfg& c, int& hint) {
+    double a = acc_tire(w, kabs, c.ax_max, c.inv_ay, c.exp_);
+    const double axm = interp_hint(sqrt(w), c.axm_v, c.axm_a, c.axm_s, c.n_axm, hint);
+    a = fmin(a, axm);
+    return fma(-w, c.dm, a);
+}
+
+// mode 'decel_backw': tyre - drag
+__device__ __forceinline__ double acc_backw(double w, double kabs, const VelCfg& c) {
+    return fma(w, c.dm, acc_tire(w, kabs, c.ax_max, c.inv_ay, c.exp_));
+}
+
+// mode 'decel_forw' with ggv (ax_max, ay_max): -tyre + drag (both negative)
+__device__ __forceinline__ double acc_brake(double w, double kabs, double ax_max, double inv_ay, double exp_, double dm) {
+    return fma(-w, dm, -acc_tire(w, kabs, ax_max, inv_ay, exp_));
+}
+
+// tph.calc_vel_profile_brake in w: w[0] = v_start^2, forward integration with full braking, zeros after standstill.
+// returns the number of leading entries with v > 0.1 (== "id_brake" of CVPF:161-163) and their summed element length.
+__device__ __forceinline__ int brake_profile_w(const double* __restrict__ kap, const double* __restrict__ el, int n,
+                                               double v_start, const VelCfg& c, double* w, double* stop_dist) {
     if (v_start < 0.0) v_start = 0.0;
-    double cur = v_start;
-    v[0] = cur;
-    int i = 0;
+    double cur = v_start * v_start;
+    w[0] = cur;
+    int i = 0, id_brake = 0;
+    double dist = 0.0;
+    bool counting = true;
     for (; i < n - 1; ++i) {
-        const double a = ax_poss(cur, radius_of(kap[i]), -ax_max, ay_max, MODE_DECEL_FORW, c);
-        const double rad = cur * cur + 2 * a * el[i];
-        if (rad < 0.0) break;
-        cur = sqrt(rad);
-        v[i + 1] = cur;
+        const double e = el[i];
+        if (counting) {
+            if (cur > 0.01) {
+                ++id_brake;
+                dist += e;
+            } else {
+                counting = false;
+            }
+        }
+        const double a = acc_brake(cur, fabs(kap[i]), c.ax_max, c.inv_ay, c.exp_, c.dm);
+        const double nx = fma(2.0 * a, e, cur);
+        if (nx < 0.0) break;
+        cur = nx;
+        w[i + 1] = cur;
     }
-    for (int k = i + 1; k < n; ++k) v[k] = 0.0;
+    if (i == n - 1) {  // ran to the end without standstill: the last entry still has to be counted
+        if (counting && cur > 0.01) {
+            ++id_brake;
+            dist += el[n - 1];
+        }
+    } else {
+        for (int k = i + 1; k < n; ++k) w[k] = 0.0;
+    }
+    *stop_dist = dist;
+    return id_brake;
 }
 
-// tph.calc_vel_profile(closed=False): initial profile sqrt(ay_max * radius) clipped to v_max, forward acceleration
-// phases started at the rising edges of the INITIAL profile, v_end clamp, backward deceleration phases with one
-// look-ahead correction (tph __solver_fb_unclosed / __solver_fb_acc_profile).  Single forward + single backward scan:
-// "is index i the start of an acceleration phase" only needs the original values at i-1, i, i+1, which are still
-// unmodified when the scan reaches i.
-// Returns the final v[0] (callers test it against the planned start velocity, OTH:907).
-__device__ __forceinline__ double fb_profile(const double* kap, const double* el, int n, double v_max, double v_start,
-                                             bool has_end, double v_end, const VelCfg& c, double* v) {
+// tph.calc_vel_profile(closed=False, loc_gg mode) in w = v^2.  Returns w[0] after the backward pass.
+__device__ __forceinline__ double fb_profile_w(const double* __restrict__ kap, const double* __restrict__ el, int n,
+                                               double v_max, double v_start, bool has_end, double v_end,
+                                               const VelCfg& c, double* w) {
     if (v_start < 0.0) v_start = 0.0;
     if (has_end && v_end < 0.0) v_end = 0.0;
-    // ---- forward ----
-    double o_i = sqrt(c.ay_max * radius_of(kap[0]));
-    if (o_i > v_max) o_i = v_max;
-    if (o_i > v_start) o_i = v_start;
+    const double wmax = v_max * v_max;
+    int hint = 0;
+    // ---- forward (mode accel_forw) ----
+    double k_i = fabs(kap[0]);
+    double o_i = fmin(c.ay_max / k_i, wmax);  // (sqrt(ay * radius))^2, radius = 1 / |kappa| (inf for kappa == 0)
+    o_i = fmin(o_i, v_start * v_start);
     double cur = o_i;
-    v[0] = cur;
+    w[0] = cur;
     bool prev_rise = false, active = false;
+    double k_n = (n > 1) ? fabs(kap[1]) : 0.0;
+    double e_i = (n > 1) ? el[0] : 0.0;
     for (int i = 0; i < n - 1; ++i) {
-        double o_n = sqrt(c.ay_max * radius_of(kap[i + 1]));
-        if (o_n > v_max) o_n = v_max;
-        const bool rise = (o_n - o_i) > 0.0;
+        // software pipelining: next iteration's operands are requested before this iteration's dependent math
+        const double k_nn = (i + 2 < n) ? fabs(kap[i + 2]) : 0.0;
+        const double e_n = (i + 1 < n - 1) ? el[i + 1] : 0.0;
+        const double o_n = fmin(c.ay_max / k_n, wmax);
+        const bool rise = o_n > o_i;
         if (!active && rise && !prev_rise) active = true;
         double nxt = o_n;
         if (active) {
-            const double a = ax_poss(cur, radius_of(kap[i]), c.ax_max, c.ay_max, MODE_ACCEL_FORW, c);
-            const double vn = sqrt(cur * cur + 2 * a * el[i]);
-            if (vn < o_n) nxt = vn;
-            if (vn > v_max) active = false;
+            const double a = acc_forw(cur, k_i, c, hint);
+            const double wn = fma(2.0 * a, e_i, cur);
+            if (wn < o_n) nxt = wn;
+            if (wn > wmax) active = false;
         }
-        v[i + 1] = nxt;
+        w[i + 1] = nxt;
         cur = nxt;
         prev_rise = rise;
         o_i = o_n;
+        k_i = k_n;
+        k_n = k_nn;
+        e_i = e_n;
     }
-    if (has_end && v[n - 1] > v_end) v[n - 1] = v_end;
-    // ---- backward (flipped arrays, mode decel_backw) ----
-    o_i = v[n - 1];
-    cur = o_i;
+    if (has_end) {
+        const double we = v_end * v_end;
+        if (cur > we) {
+            cur = we;
+            w[n - 1] = cur;
+        }
+    }
+    // ---- backward (flipped arrays, mode decel_backw, one look-ahead correction) ----
+    o_i = cur;
     prev_rise = false;
     active = false;
+    double k_p = fabs(kap[n - 1]);
+    double o_n = (n > 1) ? w[n - 2] : 0.0;
+    double k_pn = (n > 1) ? fabs(kap[n - 2]) : 0.0;
+    double e_pn = (n > 1) ? el[n - 2] : 0.0;
     for (int j = 0; j < n - 1; ++j) {
-        const int p = n - 1 - j, pn = p - 1;
-        const double o_n = v[pn];
-        const bool rise = (o_n - o_i) > 0.0;
+        const int pn = n - 2 - j;
+        const double o_nn = (pn > 0) ? w[pn - 1] : 0.0;
+        const double k_pnn = (pn > 0) ? fabs(kap[pn - 1]) : 0.0;
+        const double e_pnn = (pn > 0) ? el[pn - 1] : 0.0;
+        const bool rise = o_n > o_i;
         if (!active && rise && !prev_rise) active = true;
         double nxt = o_n;
         if (active) {
-            const double a = ax_poss(cur, radius_of(kap[p]), c.ax_max, c.ay_max, MODE_DECEL_BACKW, c);
-            double vn = sqrt(cur * cur + 2 * a * el[pn]);
-            const double a2 = ax_poss(vn, radius_of(kap[pn]), c.ax_max, c.ay_max, MODE_DECEL_BACKW, c);
-            const double vt = sqrt(cur * cur + 2 * a2 * el[pn]);
-            if (vt < vn) vn = vt;
-            if (vn < o_n) nxt = vn;
-            if (vn > v_max) active = false;
+            const double a = acc_backw(cur, k_p, c);
+            double wn = fma(2.0 * a, e_pn, cur);
+            const double a2 = acc_backw(wn, k_pn, c);
+            const double wt = fma(2.0 * a2, e_pn, cur);
+            wn = fmin(wn, wt);
+            if (wn < o_n) nxt = wn;
+            if (wn > wmax) active = false;
+            w[pn] = nxt;
         }
-        v[pn] = nxt;
         cur = nxt;
         prev_rise = rise;
         o_i = o_n;
+        o_n = o_nn;
+        k_p = k_pn;
+        k_pn = k_pnn;
+        e_pn = e_pnn;
     }
     return cur;
 }
@@ -154,13 +250,14 @@ __device__ __forceinline__ double s_coord_open_path(const double* __restrict__ x
     return __dadd_rn(sbase, ds);
 }
 
-// calc_vel_profile_follow (CVPF:78-313).  kap / el / s have n entries (el[n-1] == 0).  vb, prof, compl: n-entry scratch.
-// returns flags: bit0 too_close, bit1 vel_bound violated; result (np.minimum(prof, compl)) is written to `out`.
+// calc_vel_profile_follow (CVPF:78-313) in w = v^2.  kap / el / s have n entries (el[n-1] == 0).
+// wb, prof, compl_: n-entry scratch rows.  returns flags: bit0 too_close, bit1 vel_bound violated; the result
+// (np.minimum(prof, compl), squared) is written to `out`.
 __device__ __forceinline__ int follow_profile(const LatDev& lt, const LtplParams& prm, const VelCfg& c,
-                                              const double* kap, const double* el, const double* s, int n,
-                                              double v_start, double v_ego, double v_obj, double obj_dist,
-                                              double obj_x, double obj_y, double* vb, double* prof, double* compl_,
-                                              double* out) {
+                                              const double* __restrict__ kap, const double* __restrict__ el,
+                                              const double* __restrict__ s, int n, double v_start, double v_ego,
+                                              double v_obj, double obj_dist, double obj_x, double obj_y, double* wb,
+                                              double* prof, double* compl_, double* out) {
     int flags = 0;
     const double v_max = prm.vel_max;
     const double control_d = prm.follow_c_p * prm.safety_d + lt.veh_length;
@@ -168,15 +265,14 @@ __device__ __forceinline__ int follow_profile(const LatDev& lt, const LtplParams
     if ((obj_dist - safety_d) < 0) flags |= 1;
 
     // ego brake profile on the local path (CVPF:152-165)
-    brake_profile(kap, el, n, v_start, c.ax_max, c.ay_max, c, vb);
-    int id_brake = 0;
-    while (id_brake < n && vb[id_brake] > 0.1) ++id_brake;
-    double ego_stop_dist = 0.0;
-    for (int i = 0; i < id_brake; ++i) ego_stop_dist += el[i];
+    LTPL_PH_INIT
+    double ego_stop_dist;
+    brake_profile_w(kap, el, n, v_start, c, wb, &ego_stop_dist);
+    LTPL_PH(2)
 
     // opponent matched to the (closed) global race line, rolled to start at its position (CVPF:166-179)
     const int ng = lt.n_glob - 1;
-    const double* G = lt.glob_rl;
+    const double* __restrict__ G = lt.glob_rl;
     int start;
     {
         double bv = LTPL_INF;
@@ -194,29 +290,26 @@ __device__ __forceinline__ int follow_profile(const LatDev& lt, const LtplParams
         const double ang2 = fabs(angle3pt(G[6 * nb + 1], G[6 * nb + 2], obj_x, obj_y, G[6 * idx2 + 1], G[6 * idx2 + 2]));
         start = (ang1 >= ang2) ? idx1 : nb;  // closest_indexes[0]
     }
+    LTPL_PH(3)
     // opponent brake profile with ggv = [100, 14, 14] (CVPF:134, 185-199): only the stop distance is needed
     double opp_stop_dist = 0.0;
     {
-        double v = fmin(v_obj, G[6 * start + 4]);
-        if (v < 0.0) v = 0.0;
+        double v0 = fmin(v_obj, G[6 * start + 4]);
+        if (v0 < 0.0) v0 = 0.0;
+        double w = v0 * v0;
         int id = 0;
-        bool stopped = false;
-        while (id < ng && v > 0.1) {
+        while (id < ng && w > 0.01) {
             int r = start + id;
             if (r >= ng) r -= ng;
-            opp_stop_dist += G[6 * r + 5];
+            const double e = G[6 * r + 5];
+            opp_stop_dist += e;
             ++id;
-            if (id <= ng - 1 && !stopped) {
-                const double a = ax_poss(v, radius_of(G[6 * r + 3]), -14.0, 14.0, MODE_DECEL_FORW, c);
-                const double rad = v * v + 2 * a * G[6 * r + 5];
-                if (rad < 0.0) {
-                    stopped = true;
-                    v = 0.0;
-                } else {
-                    v = sqrt(rad);
-                }
+            if (id <= ng - 1) {
+                const double a = acc_brake(w, fabs(G[6 * r + 3]), 14.0, 1.0 / 14.0, c.exp_, c.dm);
+                const double nx = fma(2.0 * a, e, w);
+                w = (nx < 0.0) ? 0.0 : nx;
             } else {
-                v = 0.0;
+                w = 0.0;
             }
         }
     }
@@ -252,70 +345,88 @@ __device__ __forceinline__ int follow_profile(const LatDev& lt, const LtplParams
     }
     v_control = fmin(fmax(v_control, 0.0), v_max);
 
-    const double* src = vb;
+    LTPL_PH(4)
+    const double* src = wb;
     if (ego_stop_dist < s_stop) {
         int idx_c;
         double vcs;
         if (v_start > v_control && stop_idx >= 2) {
+            const double wc = v_control * v_control;
             int first = 0;
             for (int i = 0; i < n; ++i)
-                if (vb[i] <= v_control) {
+                if (wb[i] <= wc) {
                     first = i;
                     break;
                 }
             idx_c = min(first, stop_idx);
             if (idx_c == 0) idx_c = stop_idx;
-            vcs = vb[idx_c];
+            vcs = sqrt(wb[idx_c]);
         } else {
             if (!(stop_idx >= 2)) flags |= 2;
             idx_c = 0;
             vcs = v_start;
         }
-        for (int i = 0; i < idx_c; ++i) prof[i] = vb[i];
+        for (int i = 0; i < idx_c; ++i) prof[i] = wb[i];
         double v0c = vcs;
         if (stop_idx - idx_c > 0) {
-            v0c = fb_profile(kap + idx_c, el + idx_c, stop_idx - idx_c + 1, v_control, vcs, true, v_end, c,
-                             prof + idx_c);
+            v0c = sqrt(fb_profile_w(kap + idx_c, el + idx_c, stop_idx - idx_c + 1, v_control, vcs, true, v_end, c,
+                                    prof + idx_c));
             if (fabs(v0c - vcs) > 1.0) flags |= 2;
         } else {
-            prof[idx_c] = vcs;
+            prof[idx_c] = vcs * vcs;
         }
         for (int i = stop_idx + 1; i < n; ++i) prof[i] = 0.0;
         const double prof0 = (idx_c == 0) ? v0c : fmax(v_start, 0.0);
         if (fabs(prof0 - v_start) > 1.0) flags |= 2;
         src = prof;
     }
+    LTPL_PH(5)
     // complete (unconstrained) profile and intersection (CVPF:296-310)
-    fb_profile(kap, el, n, v_max, v_start, false, 0.0, c, compl_);
+    fb_profile_w(kap, el, n, v_max, v_start, false, 0.0, c, compl_);
+    LTPL_PH(6)
     for (int i = 0; i < n; ++i) out[i] = fmin(src[i], compl_[i]);
+    LTPL_PH(7)
     return flags;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// k_vel: OTH.get_ref_idx (never planned before, OTH:590-599) + OTH.calc_vel_profile per action (OTH:688-1025)
+// k_vel: OTH.get_ref_idx (never planned before, OTH:590-599) + OTH.calc_vel_profile per action (OTH:688-1025).
+// Work items come from two dense queues filled by k_path (class 0: follow, class 1: straight / left / right), so that
+// every warp is full and runs one code path.
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LTPL_VEL_BLOCK)
 k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     const int B = dm.batch;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= LTPL_NSLOT * B) return;
+    const int nq = LTPL_NSLOT * B;
+    // LTPL_VEL_LANES work items per warp (remaining lanes idle): the kernel is bound by the memory / dependent-issue
+    // latency of one path and there are only ~13 k paths per 10 k-scenario batch, so spreading them over more warps
+    // buys latency overlap per SM at the price of issue slots that would be idle anyway.
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((gt & 31) >= LTPL_VEL_LANES) return;
+    const int t = (gt >> 5) * LTPL_VEL_LANES + (gt & 31);
+    const int n_follow = bf.queue_cnt[0], n_other = bf.queue_cnt[1];
+    const int n_follow_pad = (n_follow + LTPL_VEL_LANES - 1) / LTPL_VEL_LANES * LTPL_VEL_LANES;
+    int q;
+    if (t < n_follow)
+        q = bf.queue[t];
+    else if (t >= n_follow_pad && t - n_follow_pad < n_other)
+        q = bf.queue[nq + (t - n_follow_pad)];
+    else
+        return;
     const int b = q % B;
     int st = bf.status[q];
-    bf.traj_len[q] = 0;
-    bf.traj_id[q] = -1;
-    if (!(st & LTPL_ST_FOUND)) return;
     const int action = bf.action_id[q];
     const int n = bf.path_len[q];
-    const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
-    const double* px = bf.path + (size_t)q * dm.p_max;
-    const double* py = px + pplane;
-    const double* kap = px + 3 * pplane;
-    const double* el = px + 4 * pplane;
+    const size_t pplane = (size_t)nq * dm.p_max;
+    const double* __restrict__ px = bf.path + (size_t)q * dm.p_max;
+    const double* __restrict__ py = px + pplane;
+    const double* __restrict__ kap = px + 3 * pplane;
+    const double* __restrict__ el = px + 4 * pplane;
     double* sc0 = bf.vel_scratch + (size_t)q * dm.p_max;
     double* sc1 = sc0 + pplane;
     double* sc2 = sc1 + pplane;
     double* s = bf.s_vx_ax + (size_t)q * dm.p_max;
-    double* vx = s + pplane;
+    double* vx = s + pplane;   // holds w = v^2 until the final conversion
     double* ax = vx + pplane;
 
     const double vel_plan = bf.vel[b];  // __v_start (OTH:595)
@@ -324,17 +435,10 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
         atomicOr(&bf.sc_flags[b], LTPL_SC_BRAKE_PREFIX);
         return;
     }
-    VelCfg c;
-    c.ax_max = prm.gg_ax * prm.gg_scale;
-    c.ay_max = prm.gg_ay * prm.gg_scale;
-    c.exp_ = prm.dyn_model_exp;
-    c.drag = prm.drag_coeff;
-    c.mass = prm.m_veh;
-    c.axm_v = prm.axm_v;
-    c.axm_a = prm.axm_a;
-    c.n_axm = prm.n_axm;
+    const VelCfg c = make_velcfg(prm);
 
     // s = [0, cumsum(el[:-1])]  (OTH:743)
+    LTPL_PH_INIT
     {
         double acc = 0.0;
         s[0] = 0.0;
@@ -343,6 +447,7 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
             s[i] = acc;
         }
     }
+    LTPL_PH(0)
     const bool red = (st & LTPL_ST_REDUCED_HORIZON) != 0;
     bool vel_bound = true;
     double* result = vx;
@@ -352,11 +457,13 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
         const double s_obj = s_coord_open_path(px, py, s, el, n, ox, oy);
         const double s_start = s_coord_open_path(px, py, s, el, n, bf.pos[2 * b], bf.pos[2 * b + 1]);
         const double obj_dist = s_obj - s_start;
+        LTPL_PH(1)
         const int fl = follow_profile(lt, prm, c, kap, el, s, n, vel_plan, vel_est, ov, obj_dist, ox, oy, sc0, sc1, sc2,
                                       vx);
         if (fl & 1) st |= LTPL_ST_TOO_CLOSE;
         vel_bound = !(fl & 2);
         result = sc0;  // a second profile (reduced horizon) goes to scratch
+        LTPL_PH(10)
     }
     if (action != LTPL_ACT_FOLLOW || red) {  // OTH:834-923
         const int nn = bf.n_nodes[q];
@@ -389,7 +496,7 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
         }
         double v_first = 0.0;
         if (v_idx > 1) {
-            v_first = fb_profile(kap, el, v_idx, prm.vel_max, vel_plan, true, v_end, c, result);
+            v_first = sqrt(fb_profile_w(kap, el, v_idx, prm.vel_max, vel_plan, true, v_end, c, result));
         } else {
             result[0] = 0.0;
             v_idx = 1;
@@ -404,13 +511,22 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
             }
         }
     }
-    // tph.conv_filt(window = 1) is the identity; ax profile + standstill fix-up (OTH:926-941)
-    for (int i = 0; i < n - 1; ++i) {
-        const double a = (vx[i + 1] * vx[i + 1] - vx[i] * vx[i]) / (2 * (s[i + 1] - s[i]));
-        ax[i] = (fabs(vx[i]) <= 1e-8 && fabs(a) <= 1e-8) ? -5.0 : a;
+    LTPL_PH(8)
+    // tph.conv_filt(window = 1) is the identity; vx = sqrt(w); ax profile + standstill fix-up (OTH:926-941)
+    {
+        double w0 = vx[0];
+        for (int i = 0; i < n - 1; ++i) {
+            const double w1 = vx[i + 1];
+            const double a = (w1 - w0) / (2 * (s[i + 1] - s[i]));
+            ax[i] = (w0 <= 1e-16 && fabs(a) <= 1e-8) ? -5.0 : a;
+            vx[i] = sqrt(w0);
+            w0 = w1;
+        }
+        vx[n - 1] = sqrt(w0);
+        ax[n - 1] = 0.0;
     }
-    ax[n - 1] = 0.0;
 
+    LTPL_PH(9)
     if (!vel_bound) st |= LTPL_ST_VEL_BOUND_VIOL;
     if (vel_bound || action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT) {  // OTH:945-948 (no backup plan yet)
         st |= LTPL_ST_TRAJ_VALID;
@@ -449,25 +565,24 @@ k_export(const LtplDims dm, const LtplBuffers bf) {
 // ---------------------------------------------------------------------------------------------------------------------
 // stand-alone solver over dense arrays (BASELINE.json config 5: 100 k paths x 500 points)
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(LTPL_VEL_BLOCK)
 k_velprofile_dense(const LtplParams prm, const LtplVelBatch vb) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= vb.n_paths) return;
-    VelCfg c;
-    c.ax_max = prm.gg_ax * prm.gg_scale;
-    c.ay_max = prm.gg_ay * prm.gg_scale;
-    c.exp_ = prm.dyn_model_exp;
-    c.drag = prm.drag_coeff;
-    c.mass = prm.m_veh;
-    c.axm_v = prm.axm_v;
-    c.axm_a = prm.axm_a;
-    c.n_axm = prm.n_axm;
+    const VelCfg c = make_velcfg(prm);
     const int n = vb.n_points;
-    const double* kap = vb.kappa + (size_t)i * n;
-    const double* el = vb.el + (size_t)i * n;
+    const double* __restrict__ kap = vb.kappa + (size_t)i * n;
+    const double* __restrict__ el = vb.el + (size_t)i * n;
     double* v = vb.vx + (size_t)i * n;
     double* a = vb.ax + (size_t)i * n;
-    fb_profile(kap, el, n, prm.vel_max, vb.v_start[i], true, vb.v_end[i], c, v);
-    for (int k = 0; k < n - 1; ++k) a[k] = (v[k + 1] * v[k + 1] - v[k] * v[k]) / (2 * el[k]);
+    fb_profile_w(kap, el, n, prm.vel_max, vb.v_start[i], true, vb.v_end[i], c, v);
+    double w0 = v[0];
+    for (int k = 0; k < n - 1; ++k) {
+        const double w1 = v[k + 1];
+        a[k] = (w1 - w0) / (2 * el[k]);
+        v[k] = sqrt(w0);
+        w0 = w1;
+    }
+    v[n - 1] = sqrt(w0);
     a[n - 1] = 0.0;
 }

@@ -63,7 +63,7 @@ def gather_action_sets(traj: torch.Tensor, traj_len: torch.Tensor, traj_id: torc
     world = dist.get_world_size()
     outs = []
     for t in (traj, traj_len, traj_id):
-        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous())
-        outs.append(out)
+        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous())   # concatenated along dim 0 (valid for nccl and gloo)
+        outs.append(out.view((world,) + tuple(t.shape)))
     return tuple(outs)

@@ -127,6 +127,8 @@ class BatchPlanner(object):
         for i in range(axm.shape[0]):
             p.axm_v[i] = axm[i, 0]
             p.axm_a[i] = axm[i, 1]
+        for i in range(axm.shape[0] - 1):   # slopes exactly as np.interp forms them
+            p.axm_s[i] = (axm[i + 1, 1] - axm[i, 1]) / (axm[i + 1, 0] - axm[i, 0])
 
     # -- buffers -----------------------------------------------------------------------------------------------------------
     def allocate(self, batch: int, k_obj: int = 3) -> None:
@@ -150,7 +152,8 @@ class BatchPlanner(object):
             const_coeff=z((B, 8), f64), action_id=z((NSLOT, B), i32), status=z((NSLOT, B), i32),
             n_nodes=z((NSLOT, B), i32), nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
             edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), path_len=z((NSLOT, B), i32),
-            path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), vel_scratch=z((3, NSLOT * B, P), f64),
+            path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), queue=z((2, NSLOT * B), i32),
+            queue_cnt=z((4,), i32), vel_scratch=z((3, NSLOT * B, P), f64),
             s_vx_ax=z((3, NSLOT * B, P), f64), traj=z((NSLOT, B, NE, 7), f32), traj_len=z((NSLOT, B), i32),
             traj_id=z((NSLOT, B), i32))
         buf = capi.Buffers()

@@ -122,6 +122,7 @@ typedef struct LtplParams {
     int32_t traj_base_id;        /* OTH:669 (+10 per calc_vel_profile call)           */
     double axm_v[LTPL_MAX_AXM];
     double axm_a[LTPL_MAX_AXM];
+    double axm_s[LTPL_MAX_AXM];  /* slopes (a[i+1] - a[i]) / (v[i+1] - v[i]) exactly as np.interp forms them  */
 } LtplParams;
 
 /* capacities chosen by the host from the lattice (see lattice_blob.py: capacities()) */
@@ -162,8 +163,10 @@ typedef struct LtplBuffers {
     int32_t* path_len;        /* [NSLOT][B]                                                                              */
     double* path;             /* [5][NSLOT*B][p_max] planes x, y, psi, kappa, el  (path_dict of calc_paths)              */
     double* coeff;            /* [NSLOT*B][h_max][8] (MOPG:305-309 spline_coeff_mat, stitched OTH:470-472)               */
+    int32_t* queue;           /* [2][NSLOT*B] dense work queues of path ids q: class 0 follow, class 1 other (k_path->k_vel) */
+    int32_t* queue_cnt;       /* [4] fill counts of the two queues (zeroed by the library before k_plan / k_path)         */
     /* calc_vel_profile results                                                                                          */
-    double* vel_scratch;      /* [3][NSLOT*B][p_max] brake / follow / complete profiles (CVPF:152,263,297)               */
+    double* vel_scratch;     /* [3][NSLOT*B][p_max] brake / follow / complete profiles (CVPF:152,263,297)               */
     double* s_vx_ax;          /* [3][NSLOT*B][p_max] planes s, vx, ax                                                    */
     float* traj;              /* [NSLOT][B][n_export][7] s, x, y, psi, kappa, vx, ax (OTH:941, LTPL:401-406)             */
     int32_t* traj_len;        /* [NSLOT][B]                                                                              */

@@ -1,0 +1,109 @@
+"""host-side logic that needs no GPU: C-ABI library loads and exports every declared symbol, struct mirrors match,
+scenario generator, facade argument checks, product never imports the oracle, NCCL plumbing on gloo (world size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+
+def test_capi_library_exports_every_declared_symbol():
+    from graphbasedlocaltrajectoryplanner_b200 import capi
+    capi.build_library()
+    lib = capi.load_library()
+    header = open(os.path.join(H.REPO, "include", "ltpl_b200.h")).read()
+    declared = set(re.findall(r"\b(ltpl_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ltpl_version() == capi.ABI_VERSION
+    for which, st in enumerate((capi.LatticeHeader, capi.Params, capi.Dims, capi.Buffers, capi.VelBatch)):
+        assert lib.ltpl_sizeof(which) == ctypes.sizeof(st)
+    # error convention without touching a GPU: null arguments are rejected with a message
+    assert lib.ltpl_lattice_create(None, None, None) != 0
+    assert b"null" in lib.ltpl_last_error()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(H.REPO, "graphbasedlocaltrajectoryplanner_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_missing_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
+    with pytest.raises(RuntimeError):
+        BatchPlanner(H.lattice_for("l216"))
+
+
+def test_scenarios_deterministic_and_in_track():
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios, ScenarioBatch
+    from oracle.ltpl_oracle import OracleLTPL, check_inside_bounds
+    tr = Track(H.TRACK_CSV)
+    a = make_scenarios(tr, 64, seed=5)
+    b = make_scenarios(tr, 64, seed=5)
+    assert np.array_equal(a.obj, b.obj) and np.array_equal(a.pos, b.pos)
+    assert a.n_obj.min() >= 1 and a.n_obj.max() <= 3
+    orc = OracleLTPL(H.lattice_for("l216"))
+    inside = [check_inside_bounds(orc.bound1, orc.bound2, a.pos[i]) for i in range(a.size)]
+    assert all(inside)
+    sh = a.shard(1, 2)
+    assert sh.size == 32 and np.array_equal(sh.pos[0], a.pos[1])
+    ol = a.object_list(0)
+    rt = ScenarioBatch.from_object_lists([a.pos[0]], [a.heading[0]], [a.vel[0]], [ol], k_max=3)
+    assert np.allclose(rt.obj[0, :len(ol)], a.obj[0, :len(ol)])
+
+
+def test_facade_argument_checks():
+    from graphbasedlocaltrajectoryplanner_b200.Graph_LTPL import Graph_LTPL
+    with pytest.raises(ValueError):   # LTPL:62-68 missing path entries
+        Graph_LTPL(path_dict={'globtraj_input_path': H.TRACK_CSV}, log_to_file=False)
+    pd = {'globtraj_input_path': H.TRACK_CSV, 'graph_store_path': "/tmp/_x.npz",
+          'ltpl_offline_param_path': H.OFFLINE_INI, 'ltpl_online_param_path': H.ONLINE_INI}
+    obj = Graph_LTPL(path_dict=pd, log_to_file=False)
+    with pytest.raises(ValueError):   # LTPL:277-280 graph not initialised
+        obj.set_startpos(np.zeros(2), 0.0)
+
+
+GLOO_SCRIPT = r'''
+import os, sys
+sys.path.insert(0, %(repo)r)
+import numpy as np, torch, torch.distributed as dist
+from tests import helpers as H
+from graphbasedlocaltrajectoryplanner_b200 import parallel
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lat = H.lattice_for("l216") if rank == 0 else None
+header, cap, blob = parallel.broadcast_lattice(lat, torch.device("cpu"), src=0)
+ref = H.lattice_for("l216")
+from graphbasedlocaltrajectoryplanner_b200.lattice_blob import pack_lattice
+h2, blob2, cap2 = pack_lattice(ref)
+assert bytes(header) == bytes(h2) and cap == cap2 and np.array_equal(blob.numpy(), blob2)
+traj = torch.full((3, 4, 5, 7), float(rank), dtype=torch.float32)
+tl = torch.full((3, 4), rank, dtype=torch.int32)
+out = parallel.gather_action_sets(traj, tl, tl.clone())
+assert out[0].shape == (world, 3, 4, 5, 7) and all(float(out[0][r].mean()) == r for r in range(world))
+assert parallel.shard_indices(10, rank, world).tolist() == list(range(rank, 10, world))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_parallel_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "gloo_w2.py"
+    script.write_text(GLOO_SCRIPT % {"repo": H.REPO})
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0 and res.stdout.count("ok") == 2, res.stdout[-2000:]
