@@ -188,8 +188,10 @@ class Graph_LTPL(object):
 
     def plan_batch(self, scenarios: ScenarioBatch = None, synchronize: bool = True) -> dict:
         """One end-to-end batched tick: host scenario arrays -> (H2D) -> set_startpos -> calc_paths -> calc_vel_profile
-        -> (D2H) -> pinned host action sets {traj [NSLOT][B][n_export][7] fp32, traj_len, traj_id, action_id, status,
-        sc_flags}.  With ``scenarios=None`` the previously staged batch is planned again."""
+        -> (D2H) -> pinned host action sets: ``traj`` [n_rows][n_export][7] fp32 (compact: one row per kept
+        trajectory), ``exp_q`` (row -> path id q = slot * B + b), ``traj_row`` [NSLOT][B] (path -> row or -1),
+        ``traj_len``, ``traj_id``, ``action_id``, ``status``, ``sc_flags``, ``n_rows``.
+        With ``scenarios=None`` the previously staged batch is planned again."""
         pl = self.planner
         if scenarios is not None:
             pl.stage_scenarios(scenarios)
@@ -201,3 +203,9 @@ class Graph_LTPL(object):
             import torch
             torch.cuda.current_stream(pl.device).synchronize()
         return out
+
+    def plan_stream(self, batches, vel_est=None, device_hook=None):
+        """Pipelined variant of ``plan_batch`` over an iterable of ScenarioBatch objects: yields one result dict per
+        batch, in order; the device-to-host copy of step i overlaps the kernels of step i + 1
+        (``BatchPlanner.plan_stream``)."""
+        return self.planner.plan_stream(batches, vel_est=vel_est, device_hook=device_hook)

@@ -172,6 +172,7 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
 static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                       cudaStream_t st) {
     const int nq = LTPL_NSLOT * dm->batch;
+    if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
     k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
     if (int r = check_launch("k_vel")) return r;
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
@@ -227,6 +228,8 @@ int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, 
             return check_launch("k_path");
         }
         case 3:
+            if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess)
+                return fail("memset(export count) failed");
             k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
             return check_launch("k_vel");
         case 4:

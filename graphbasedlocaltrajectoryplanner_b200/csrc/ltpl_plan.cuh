@@ -331,6 +331,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         bf.path_len[lane * B + b] = 0;
         bf.traj_len[lane * B + b] = 0;
         bf.traj_id[lane * B + b] = -1;
+        bf.traj_row[lane * B + b] = -1;
     }
     if (lane == 0) {
         bf.closest_obj[b] = -1;

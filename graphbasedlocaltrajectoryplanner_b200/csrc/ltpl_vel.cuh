@@ -532,6 +532,9 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
         st |= LTPL_ST_TRAJ_VALID;
         bf.traj_len[q] = min(n, dm.n_export);
         bf.traj_id[q] = prm.traj_base_id + action;
+        const int e = atomicAdd(&bf.queue_cnt[2], 1);  // row in the compact export list
+        bf.exp_q[e] = q;
+        bf.traj_row[q] = e;
     }
     bf.status[q] = st;
 }
@@ -541,14 +544,14 @@ __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA_EXPORT * 32)
 k_export(const LtplDims dm, const LtplBuffers bf) {
     const int B = dm.batch;
     const int lane = threadIdx.x & 31;
-    const int q = blockIdx.x * LTPL_WARPS_PER_CTA_EXPORT + (threadIdx.x >> 5);
-    if (q >= LTPL_NSLOT * B) return;
+    const int e = blockIdx.x * LTPL_WARPS_PER_CTA_EXPORT + (threadIdx.x >> 5);  // row of the compact export list
+    if (e >= bf.queue_cnt[2]) return;
+    const int q = bf.exp_q[e];
     const int n = bf.traj_len[q];
-    if (n <= 0) return;
     const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
     const double* pp = bf.path + (size_t)q * dm.p_max;
     const double* sv = bf.s_vx_ax + (size_t)q * dm.p_max;
-    float* out = bf.traj + (size_t)q * dm.n_export * 7;
+    float* out = bf.traj + (size_t)e * dm.n_export * 7;
     for (int i = lane; i < n * 7; i += 32) {
         const int r = i / 7, col = i - 7 * r;
         double v;

@@ -153,21 +153,29 @@ class BatchPlanner(object):
             n_nodes=z((NSLOT, B), i32), nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
             edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), path_len=z((NSLOT, B), i32),
             path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), queue=z((2, NSLOT * B), i32),
-            queue_cnt=z((4,), i32), vel_scratch=z((3, NSLOT * B, P), f64),
-            s_vx_ax=z((3, NSLOT * B, P), f64), traj=z((NSLOT, B, NE, 7), f32), traj_len=z((NSLOT, B), i32),
+            queue_cnt=z((4,), i32), exp_q=z((NSLOT * B,), i32), traj_row=z((NSLOT, B), i32),
+            vel_scratch=z((3, NSLOT * B, P), f64),
+            s_vx_ax=z((3, NSLOT * B, P), f64), traj=z((NSLOT * B, NE, 7), f32), traj_len=z((NSLOT, B), i32),
             traj_id=z((NSLOT, B), i32))
         buf = capi.Buffers()
         for name in capi.BUFFER_FIELDS:
             setattr(buf, name, t[name].data_ptr())
         self.t, self.buf, self.dims = t, buf, d
-        # pinned host staging for the per-tick host <-> device copies
+        # second compact export buffer: the pipelined stream planner lets the D2H of step i overlap step i + 1
+        self.traj_bufs = [t["traj"], z((NSLOT * B, NE, 7), f32)]
+        # pinned host staging for the per-tick host <-> device copies (two sets for the pipelined path)
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()   # noqa: E731
-        self.h_in = dict(pos=pin((B, 2), f64), heading=pin((B,), f64), vel=pin((B,), f64), vel_est=pin((B,), f64),
-                         n_obj=pin((B,), i32),
-                         obj=pin((B, K, 5), f64))
-        self.h_out = dict(traj=pin((NSLOT, B, NE, 7), f32), traj_len=pin((NSLOT, B), i32),
-                          traj_id=pin((NSLOT, B), i32), action_id=pin((NSLOT, B), i32), status=pin((NSLOT, B), i32),
-                          sc_flags=pin((B,), i32))
+        self.h_in_sets = [dict(pos=pin((B, 2), f64), heading=pin((B,), f64), vel=pin((B,), f64),
+                               vel_est=pin((B,), f64), n_obj=pin((B,), i32), obj=pin((B, K, 5), f64))
+                          for _ in range(2)]
+        self.h_out_sets = [dict(traj=pin((NSLOT * B, NE, 7), f32), exp_q=pin((NSLOT * B,), i32),
+                                traj_row=pin((NSLOT, B), i32), traj_len=pin((NSLOT, B), i32),
+                                traj_id=pin((NSLOT, B), i32), action_id=pin((NSLOT, B), i32),
+                                status=pin((NSLOT, B), i32), sc_flags=pin((B,), i32), queue_cnt=pin((4,), i32))
+                           for _ in range(2)]
+        self.h_in, self.h_out = self.h_in_sets[0], self.h_out_sets[0]
+        self._meta_names = ("exp_q", "traj_row", "traj_len", "traj_id", "action_id", "status", "sc_flags", "queue_cnt")
+        self._row_bytes = NE * 7 * 4
 
     def device_bytes(self) -> int:
         return int(sum(v.numel() * v.element_size() for v in self.t.values()) + self.blob.numel())
@@ -180,30 +188,104 @@ class BatchPlanner(object):
     def h2d_bytes(self) -> int:
         return int(sum(v.numel() * v.element_size() for v in self.h_in.values()))
 
-    def d2h_bytes(self) -> int:
-        return int(sum(v.numel() * v.element_size() for v in self.h_out.values()))
+    def d2h_bytes(self, n_rows: int = None) -> int:
+        """bytes of one result download: the small per-path arrays + n_rows compact trajectory rows."""
+        meta = sum(self.h_out[n].numel() * self.h_out[n].element_size() for n in self._meta_names)
+        rows = self.h_out["traj"].shape[0] if n_rows is None else n_rows
+        return int(meta + rows * self._row_bytes)
 
-    def stage_scenarios(self, sc: ScenarioBatch, vel_est=None) -> None:
-        """copy a scenario batch into the pinned staging buffers (host-side preparation, not part of a tick)."""
+    def stage_scenarios(self, sc: ScenarioBatch, vel_est=None, which: int = 0) -> None:
+        """copy a scenario batch into the pinned staging buffers (host memcpy)."""
         if self.dims is None or sc.size != self.dims.batch or sc.obj.shape[1] > self.dims.k_obj:
             self.allocate(sc.size, sc.obj.shape[1])
+        h = self.h_in_sets[which]
         k = sc.obj.shape[1]
-        self.h_in["pos"].numpy()[...] = sc.pos
-        self.h_in["heading"].numpy()[...] = sc.heading
-        self.h_in["vel"].numpy()[...] = sc.vel
-        self.h_in["vel_est"].numpy()[...] = sc.vel if vel_est is None else vel_est
-        self.h_in["n_obj"].numpy()[...] = sc.n_obj
-        self.h_in["obj"].numpy()[...] = 0.0
-        self.h_in["obj"].numpy()[:, :k, :] = sc.obj
+        h["pos"].numpy()[...] = sc.pos
+        h["heading"].numpy()[...] = sc.heading
+        h["vel"].numpy()[...] = sc.vel
+        h["vel_est"].numpy()[...] = sc.vel if vel_est is None else vel_est
+        h["n_obj"].numpy()[...] = sc.n_obj
+        if k < h["obj"].shape[1]:
+            h["obj"].numpy()[:, k:, :] = 0.0
+        h["obj"].numpy()[:, :k, :] = sc.obj
 
-    def upload(self) -> None:
-        for name, src in self.h_in.items():
+    def upload(self, which: int = 0) -> None:
+        for name, src in self.h_in_sets[which].items():
             self.t[name].copy_(src, non_blocking=True)
 
-    def download(self) -> dict:
-        for name, dst in self.h_out.items():
-            dst.copy_(self.t[name], non_blocking=True)
-        return self.h_out
+    def download(self, which: int = 0) -> dict:
+        """synchronous-style download on the current stream: per-path arrays + the filled rows of the compact
+        trajectory list (the row count is read back first)."""
+        out = self.h_out_sets[which]
+        for name in self._meta_names:
+            out[name].copy_(self.t[name], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        n = int(out["queue_cnt"][2])
+        if n:
+            out["traj"][:n].copy_(self.t["traj"][:n], non_blocking=True)
+        out["n_rows"] = n
+        return out
+
+    def plan_stream(self, batches, vel_est=None, device_hook=None):
+        """Pipelined end-to-end planning of a sequence of ScenarioBatch objects (generator of result dicts, in order).
+
+        Per step: host staging (pinned) -> H2D -> k_startpos -> tick kernels -> D2H of the per-path arrays on the compute
+        stream; the large D2H of the compact trajectory rows runs on a second stream and overlaps the kernels of the
+        next step (two export buffers, CUDA events for the hand-over).  Results are views of pinned host memory that
+        stay valid until two further steps have been submitted."""
+        dev = self.device
+        compute = torch.cuda.current_stream(dev)
+        copy_stream = getattr(self, "_copy_stream", None)
+        if copy_stream is None:
+            copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
+        ev_meta = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_d2h = [None, None]
+        pending = []          # [(index, set)] submitted, trajectory copy not yet issued
+        inflight = []         # [(index, set, n_rows)] trajectory copy issued
+
+        def issue_copy(k):
+            ev_meta[k].synchronize()
+            out = self.h_out_sets[k]
+            n = int(out["queue_cnt"][2])
+            with torch.cuda.stream(copy_stream):
+                if n:
+                    out["traj"][:n].copy_(self.traj_bufs[k][:n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            ev_d2h[k] = ev
+            out["n_rows"] = n
+            return n
+
+        i = 0
+        for sc in batches:
+            k = i & 1
+            if ev_d2h[k] is not None:
+                # results of step i - 2 (same buffers) must have left the device; hand them out before reuse
+                ev_d2h[k].synchronize()
+                yield self.h_out_sets[k]
+                inflight.pop(0)
+            self.stage_scenarios(sc, vel_est=vel_est, which=k)
+            self.buf.traj = self.traj_bufs[k].data_ptr()
+            self.upload(which=k)
+            self.set_startpos()
+            self.tick()
+            if device_hook is not None:     # e.g. an all-gather of the device-side action sets (multi-GPU)
+                device_hook(k)
+            for name in self._meta_names:
+                self.h_out_sets[k][name].copy_(self.t[name], non_blocking=True)
+            ev_meta[k].record(compute)
+            pending.append(k)
+            if len(pending) > 1:            # issue the trajectory copy of the previous step; it overlaps this step
+                pk = pending.pop(0)
+                inflight.append((pk, issue_copy(pk)))
+            i += 1
+        while pending:
+            pk = pending.pop(0)
+            inflight.append((pk, issue_copy(pk)))
+        for pk, _ in inflight:
+            ev_d2h[pk].synchronize()
+            yield self.h_out_sets[pk]
+        self.buf.traj = self.traj_bufs[0].data_ptr()
 
     # -- kernels ---------------------------------------------------------------------------------------------------------------
     def _call(self, fn, what):
@@ -239,7 +321,8 @@ class BatchPlanner(object):
         """per-scenario result dicts in the reference's vocabulary ({action: [ndarray]}), for parity tests and the
         single-scenario facade.  Copies every result buffer to the host."""
         f = self.fetch("sc_flags", "start_node", "action_id", "status", "n_nodes", "nodes", "node_idx", "closest_obj",
-                       "path_len", "path", "coeff", "s_vx_ax", "traj", "traj_len", "traj_id", "const_seg", "const_len")
+                       "path_len", "path", "coeff", "s_vx_ax", "traj", "traj_row", "traj_len", "traj_id", "const_seg",
+                       "const_len")
         B = self.dims.batch
         out = []
         for b in (range(B) if indices is None else indices):
@@ -279,7 +362,7 @@ class BatchPlanner(object):
                                             f["s_vx_ax"][2, q, :n]))
                     rec["traj_full"][name] = [full]
                     tl = int(f["traj_len"][s, b])
-                    rec["traj"][name] = [f["traj"][s, b, :tl].astype(np.float64)]
+                    rec["traj"][name] = [f["traj"][int(f["traj_row"][s, b]), :tl].astype(np.float64)]
                     rec["ids"][name] = int(f["traj_id"][s, b])
             out.append(rec)
         return out

@@ -164,11 +164,15 @@ typedef struct LtplBuffers {
     double* path;             /* [5][NSLOT*B][p_max] planes x, y, psi, kappa, el  (path_dict of calc_paths)              */
     double* coeff;            /* [NSLOT*B][h_max][8] (MOPG:305-309 spline_coeff_mat, stitched OTH:470-472)               */
     int32_t* queue;           /* [2][NSLOT*B] dense work queues of path ids q: class 0 follow, class 1 other (k_path->k_vel) */
-    int32_t* queue_cnt;       /* [4] fill counts of the two queues (zeroed by the library before k_plan / k_path)         */
+    int32_t* queue_cnt;       /* [4] fill counts of the two queues ([0], [1]) and number of exported trajectories ([2]);   */
+                              /*     zeroed by the library before k_plan / k_path / k_vel                                 */
+    int32_t* exp_q;           /* [NSLOT*B] path id q of every exported trajectory row (compact export list)               */
+    int32_t* traj_row;        /* [NSLOT][B] row of path q in `traj`, or -1                                                 */
     /* calc_vel_profile results                                                                                          */
     double* vel_scratch;     /* [3][NSLOT*B][p_max] brake / follow / complete profiles (CVPF:152,263,297)               */
     double* s_vx_ax;          /* [3][NSLOT*B][p_max] planes s, vx, ax                                                    */
-    float* traj;              /* [NSLOT][B][n_export][7] s, x, y, psi, kappa, vx, ax (OTH:941, LTPL:401-406)             */
+    float* traj;              /* [NSLOT*B][n_export][7] s, x, y, psi, kappa, vx, ax (OTH:941, LTPL:401-406); COMPACT: only  */
+                              /* the first queue_cnt[2] rows are filled (one per kept trajectory, row -> path via exp_q)   */
     int32_t* traj_len;        /* [NSLOT][B]                                                                              */
     int32_t* traj_id;         /* [NSLOT][B] traj_base_id + action id (OTH:696-697)                                       */
 } LtplBuffers;

@@ -82,3 +82,38 @@ def test_cuda_matches_oracle_seeded(tag, n, omin, omax):
         H.compare_records(recs[b], want, ctx="%s scenario %d" % (tag, b))
     fails = _collect(one, sc.size)
     assert not fails, "%d/%d scenarios differ from the oracle:\n%s" % (len(fails), sc.size, "\n".join(fails[:10]))
+
+
+def test_plan_stream_pipelining_matches_plan_batch():
+    """the pipelined end-to-end API (two export buffers, D2H overlapping the next step) returns, for every step, the
+    same action sets as the synchronous plan_batch call."""
+    from graphbasedlocaltrajectoryplanner_b200.Graph_LTPL import Graph_LTPL
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios
+    g = H.golden("ticks_default.npz")
+    pd = {'globtraj_input_path': H.TRACK_CSV, 'graph_store_path': "/tmp/_lat_default_test.npz",
+          'ltpl_offline_param_path': H.OFFLINE_INI, 'ltpl_online_param_path': H.ONLINE_INI}
+    ltpl = Graph_LTPL(path_dict=pd, log_to_file=False, device="cuda:0")
+    ltpl.graph_init()
+    ltpl.planner.set_vel_params(ax_max_machines=g["ax_max_machines"], **VEL)
+    tr = Track(H.TRACK_CSV)
+    batches = [make_scenarios(tr, 512, seed=100 + i, n_obj_min=0, n_obj_max=3) for i in range(5)]
+
+    def snapshot(out):
+        n = int(out["n_rows"])
+        order = np.argsort(out["exp_q"][:n].numpy())          # rows are appended in arbitrary (atomic) order
+        return (n, out["exp_q"][:n].numpy()[order].copy(), out["traj"][:n].numpy()[order].copy(),
+                out["traj_len"].numpy().copy(), out["action_id"].numpy().copy(), out["status"].numpy().copy())
+
+    want = [snapshot(ltpl.plan_batch(sc)) for sc in batches]
+    got = [snapshot(out) for out in ltpl.plan_stream(iter(batches))]
+    assert len(got) == len(want) == 5
+    for a, b in zip(got, want):
+        assert a[0] == b[0] and a[0] > 0
+        for x, y in zip(a[1:], b[1:]):
+            assert np.array_equal(x, y)
+    # rows <-> paths bookkeeping
+    out = ltpl.plan_batch(batches[0])
+    n = int(out["n_rows"])
+    rows = out["traj_row"].numpy().reshape(-1)
+    q = out["exp_q"][:n].numpy()
+    assert np.array_equal(rows[q], np.arange(n)) and int((rows >= 0).sum()) == n
