@@ -64,7 +64,8 @@ class Dims(C.Structure):
 
 BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
                  "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj",
-                 "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "vel_scratch", "s_vx_ax", "traj", "traj_len", "traj_id")
+                 "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "vel_scratch", "s_vx_ax",
+                 "vel_t", "traj", "traj_len", "traj_id")
 
 
 class Buffers(C.Structure):

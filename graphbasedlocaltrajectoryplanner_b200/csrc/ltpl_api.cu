@@ -18,6 +18,28 @@
 #include "ltpl_path.cuh"
 #include "ltpl_plan.cuh"
 #include "ltpl_vel.cuh"
+#include "ltpl_vel_tiled.cuh"
+
+#ifndef LTPL_VEL_TILED
+#define LTPL_VEL_TILED 1   // 1: tile-streamed velocity kernel (ltpl_vel_tiled.cuh), 0: thread-per-path k_vel
+#endif
+
+static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                                cudaStream_t st) {
+    const int nq = LTPL_NSLOT * dm->batch;
+#if LTPL_VEL_TILED
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_vel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_vel_tiled<<<nq / 32 + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
+#else
+    k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
+#endif
+    return cudaSuccess;
+}
 
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
@@ -173,7 +195,7 @@ static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplD
                       cudaStream_t st) {
     const int nq = LTPL_NSLOT * dm->batch;
     if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
-    k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
+    if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: cudaFuncSetAttribute failed");
     if (int r = check_launch("k_vel")) return r;
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
         *dm, *bf);
@@ -230,7 +252,7 @@ int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, 
         case 3:
             if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess)
                 return fail("memset(export count) failed");
-            k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
+            if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: cudaFuncSetAttribute failed");
             return check_launch("k_vel");
         case 4:
             k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT,

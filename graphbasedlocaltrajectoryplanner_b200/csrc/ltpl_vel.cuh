@@ -41,16 +41,29 @@ struct VelCfg {
     int n_axm;
 };
 
-__device__ __forceinline__ VelCfg make_velcfg(const LtplParams& prm) {
+// The machine table is indexed with a per-lane velocity: read from the kernel-parameter (constant) bank that is a
+// divergent constant load which the hardware serialises lane by lane (measured: ~2.8 k cycles per recurrence step).
+// Every velocity kernel therefore first copies the three small tables to shared memory (stage_axm) and points the
+// configuration at that copy.
+__device__ __forceinline__ void stage_axm(const LtplParams& prm, double* s_axm /* [3 * LTPL_MAX_AXM] shared */) {
+    for (int i = threadIdx.x; i < LTPL_MAX_AXM; i += blockDim.x) {
+        s_axm[i] = prm.axm_v[i];
+        s_axm[LTPL_MAX_AXM + i] = prm.axm_a[i];
+        s_axm[2 * LTPL_MAX_AXM + i] = prm.axm_s[i];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ VelCfg make_velcfg(const LtplParams& prm, const double* s_axm) {
     VelCfg c;
     c.ax_max = prm.gg_ax * prm.gg_scale;
     c.ay_max = prm.gg_ay * prm.gg_scale;
     c.inv_ay = 1.0 / c.ay_max;
     c.exp_ = prm.dyn_model_exp;
     c.dm = prm.drag_coeff / prm.m_veh;
-    c.axm_v = prm.axm_v;
-    c.axm_a = prm.axm_a;
-    c.axm_s = prm.axm_s;
+    c.axm_v = s_axm;
+    c.axm_a = s_axm + LTPL_MAX_AXM;
+    c.axm_s = s_axm + 2 * LTPL_MAX_AXM;
     c.n_axm = prm.n_axm;
     return c;
 }
@@ -396,6 +409,8 @@ __device__ __forceinline__ int follow_profile(const LatDev& lt, const LtplParams
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LTPL_VEL_BLOCK)
 k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
+    __shared__ double s_axm[3 * LTPL_MAX_AXM];
+    stage_axm(prm, s_axm);
     const int B = dm.batch;
     const int nq = LTPL_NSLOT * B;
     // LTPL_VEL_LANES work items per warp (remaining lanes idle): the kernel is bound by the memory / dependent-issue
@@ -435,7 +450,7 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
         atomicOr(&bf.sc_flags[b], LTPL_SC_BRAKE_PREFIX);
         return;
     }
-    const VelCfg c = make_velcfg(prm);
+    const VelCfg c = make_velcfg(prm, s_axm);
 
     // s = [0, cumsum(el[:-1])]  (OTH:743)
     LTPL_PH_INIT
@@ -570,9 +585,11 @@ k_export(const LtplDims dm, const LtplBuffers bf) {
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(LTPL_VEL_BLOCK)
 k_velprofile_dense(const LtplParams prm, const LtplVelBatch vb) {
+    __shared__ double s_axm[3 * LTPL_MAX_AXM];
+    stage_axm(prm, s_axm);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= vb.n_paths) return;
-    const VelCfg c = make_velcfg(prm);
+    const VelCfg c = make_velcfg(prm, s_axm);
     const int n = vb.n_points;
     const double* __restrict__ kap = vb.kappa + (size_t)i * n;
     const double* __restrict__ el = vb.el + (size_t)i * n;

@@ -155,7 +155,8 @@ class BatchPlanner(object):
             path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), queue=z((2, NSLOT * B), i32),
             queue_cnt=z((4,), i32), exp_q=z((NSLOT * B,), i32), traj_row=z((NSLOT, B), i32),
             vel_scratch=z((3, NSLOT * B, P), f64),
-            s_vx_ax=z((3, NSLOT * B, P), f64), traj=z((NSLOT * B, NE, 7), f32), traj_len=z((NSLOT, B), i32),
+            s_vx_ax=z((3, NSLOT * B, P), f64), vel_t=z((5, P, NSLOT * B + 64), f64),
+            traj=z((NSLOT * B, NE, 7), f32), traj_len=z((NSLOT, B), i32),
             traj_id=z((NSLOT, B), i32))
         buf = capi.Buffers()
         for name in capi.BUFFER_FIELDS:

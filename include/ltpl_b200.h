@@ -171,6 +171,7 @@ typedef struct LtplBuffers {
     /* calc_vel_profile results                                                                                          */
     double* vel_scratch;     /* [3][NSLOT*B][p_max] brake / follow / complete profiles (CVPF:152,263,297)               */
     double* s_vx_ax;          /* [3][NSLOT*B][p_max] planes s, vx, ax                                                    */
+    double* vel_t;            /* [5][p_max][NSLOT*B + 64] transposed (point-major) scratch of the tiled velocity kernel  */
     float* traj;              /* [NSLOT*B][n_export][7] s, x, y, psi, kappa, vx, ax (OTH:941, LTPL:401-406); COMPACT: only  */
                               /* the first queue_cnt[2] rows are filled (one per kept trajectory, row -> path via exp_q)   */
     int32_t* traj_len;        /* [NSLOT][B]                                                                              */

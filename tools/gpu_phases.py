@@ -22,7 +22,7 @@ pl.tick(); torch.cuda.synchronize()
 pl.lib.ltpl_debug_phases(out, 0)
 cnt = pl.t["queue_cnt"].cpu().numpy()
 nw = (cnt[0] + 31) // 32 + (cnt[1] + 31) // 32
-names = {0: "cumsum s", 1: "2x s_coord on path", 2: "ego brake", 3: "glob_rl match", 4: "opp brake+stop idx+vctrl",
+names = {0: "pass A", 1: "scalars", 2: "pass B fwd", 3: "pass C bwd", 4: "single profile", 5: "output pass"} if os.environ.get("TILED", "1") == "1" else {0: "cumsum s", 1: "2x s_coord on path", 2: "ego brake", 3: "glob_rl match", 4: "opp brake+stop idx+vctrl",
          5: "control profile", 6: "complete profile", 7: "min", 8: "non-follow fb / red", 9: "ax+sqrt", 10: "follow total tail"}
 print("queue counts", cnt[:2], "warps", nw)
 tot = sum(out)
