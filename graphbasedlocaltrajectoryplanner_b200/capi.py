@@ -45,7 +45,7 @@ class LatticeHeader(C.Structure):
                     "off_raceline", "off_bound1", "off_bound2", "off_centerline", "off_node_xy", "off_node_psi",
                     "off_node_layer", "off_in_off", "off_edge_layer_off", "off_edge_src", "off_edge_dst",
                     "off_edge_cost", "off_edge_len", "off_edge_psi1", "off_samp_off", "off_samp_xy", "off_samp_el",
-                    "off_samp_edge", "off_glob_rl", "blob_bytes")])
+                    "off_samp_edge", "off_glob_rl", "off_glob_xy", "blob_bytes")])
 
 
 class Params(C.Structure):
@@ -63,7 +63,7 @@ class Dims(C.Structure):
 
 
 BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
-                 "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj",
+                 "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj", "cobj_start",
                  "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "vel_scratch", "s_vx_ax",
                  "vel_t", "traj", "traj_len", "traj_id")
 

@@ -34,7 +34,7 @@ static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, c
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_vel_tiled<<<nq / 32 + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
+    k_vel_tiled<<<nq / VT_P + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
 #else
     k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
 #endif
@@ -132,6 +132,7 @@ int ltpl_lattice_create(const LtplLatticeHeader* h, const void* dev_blob, LtplLa
     LTPL_PTR(samp_el, double, off_samp_el);
     LTPL_PTR(samp_edge, int, off_samp_edge);
     LTPL_PTR(glob_rl, double, off_glob_rl);
+    LTPL_PTR(glob_xy, double2, off_glob_xy);
 #undef LTPL_PTR
     *out = lat;
     return 0;

@@ -43,6 +43,7 @@ struct LatDev {
     const double* samp_el;
     const int* samp_edge;
     const double* glob_rl;  // [n_glob - 1][6]
+    const double2* glob_xy; // [n_glob - 1]
 };
 
 struct LtplLattice {

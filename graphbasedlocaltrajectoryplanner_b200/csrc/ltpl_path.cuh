@@ -19,7 +19,10 @@ __device__ __forceinline__ void enqueue_path(const LtplBuffers& bf, const LtplDi
     if (pos < nq) bf.queue[cls * nq + pos] = q;
 }
 
-__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
+#ifndef LTPL_PATH_MINB
+#define LTPL_PATH_MINB 8
+#endif
+__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32, LTPL_PATH_MINB)
 k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;

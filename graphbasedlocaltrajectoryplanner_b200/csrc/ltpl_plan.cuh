@@ -308,7 +308,10 @@ __device__ __noinline__ int intersect_disc(const LatDev& lt, int lane, double ox
     return o;
 }
 
-__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
+#ifndef LTPL_PLAN_MINB
+#define LTPL_PLAN_MINB 10  // resident CTAs per SM the register allocation is held to (occupancy hides the L1/L2 latency)
+#endif
+__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32, LTPL_PLAN_MINB)
 k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf, const int maxn, const int hl,
        const int mask_words) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -459,6 +462,20 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
                 if (__any_sync(LTPL_FULL, hit)) obj_in_const = true;
             }
         }
+    }
+    // match the closest object to the (closed) global race line: get_s_coord(glob_rl[:, 1:3], obj_pos, closed=True)[1][0]
+    // (CVPF:166-172) -- warp-parallel here instead of a serial 800-point scan per follow path in the velocity kernel
+    if (closest_idx >= 0) {
+        const int ng = lt.n_glob - 1;
+        const double ox = ps->vx[closest_idx], oy = ps->vy[closest_idx];
+        const ArgMinD m = warp_closest_point(lt.glob_xy, ng, ox, oy, lane);
+        const int nb = m.i;
+        const int i1 = (nb - 1 < 0) ? ng - 1 : nb - 1;
+        const int i2 = (nb + 1 > ng - 1) ? 0 : nb + 1;
+        const double2 gn = lt.glob_xy[nb], g1 = lt.glob_xy[i1], g2 = lt.glob_xy[i2];
+        const double a1 = fabs(angle3pt(gn.x, gn.y, ox, oy, g1.x, g1.y));
+        const double a2 = fabs(angle3pt(gn.x, gn.y, ox, oy, g2.x, g2.y));
+        if (lane == 0) bf.cobj_start[b] = (a1 >= a2) ? i1 : nb;
     }
     if (lane == 0) {
         bf.closest_obj[b] = closest_idx;

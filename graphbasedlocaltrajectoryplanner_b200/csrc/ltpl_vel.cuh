@@ -269,7 +269,7 @@ __device__ __forceinline__ double s_coord_open_path(const double* __restrict__ x
 __device__ __forceinline__ int follow_profile(const LatDev& lt, const LtplParams& prm, const VelCfg& c,
                                               const double* __restrict__ kap, const double* __restrict__ el,
                                               const double* __restrict__ s, int n, double v_start, double v_ego,
-                                              double v_obj, double obj_dist, double obj_x, double obj_y, double* wb,
+                                              double v_obj, double obj_dist, int glob_start, double* wb,
                                               double* prof, double* compl_, double* out) {
     int flags = 0;
     const double v_max = prm.vel_max;
@@ -283,26 +283,11 @@ __device__ __forceinline__ int follow_profile(const LatDev& lt, const LtplParams
     brake_profile_w(kap, el, n, v_start, c, wb, &ego_stop_dist);
     LTPL_PH(2)
 
-    // opponent matched to the (closed) global race line, rolled to start at its position (CVPF:166-179)
+    // opponent matched to the (closed) global race line, rolled to start at its position (CVPF:166-179):
+    // `start` = closest_indexes[0], computed warp-parallel in k_plan (LtplBuffers.cobj_start)
     const int ng = lt.n_glob - 1;
     const double* __restrict__ G = lt.glob_rl;
-    int start;
-    {
-        double bv = LTPL_INF;
-        int nb = 0;
-        for (int i = 0; i < ng; ++i) {
-            const double d = dist2_rn(G[6 * i + 1], G[6 * i + 2], obj_x, obj_y);
-            if (d < bv) {
-                bv = d;
-                nb = i;
-            }
-        }
-        const int idx1 = (nb - 1 < 0) ? ng - 1 : nb - 1;
-        const int idx2 = (nb + 1 > ng - 1) ? 0 : nb + 1;
-        const double ang1 = fabs(angle3pt(G[6 * nb + 1], G[6 * nb + 2], obj_x, obj_y, G[6 * idx1 + 1], G[6 * idx1 + 2]));
-        const double ang2 = fabs(angle3pt(G[6 * nb + 1], G[6 * nb + 2], obj_x, obj_y, G[6 * idx2 + 1], G[6 * idx2 + 2]));
-        start = (ang1 >= ang2) ? idx1 : nb;  // closest_indexes[0]
-    }
+    const int start = glob_start;
     LTPL_PH(3)
     // opponent brake profile with ggv = [100, 14, 14] (CVPF:134, 185-199): only the stop distance is needed
     double opp_stop_dist = 0.0;
@@ -473,8 +458,8 @@ k_vel(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
         const double s_start = s_coord_open_path(px, py, s, el, n, bf.pos[2 * b], bf.pos[2 * b + 1]);
         const double obj_dist = s_obj - s_start;
         LTPL_PH(1)
-        const int fl = follow_profile(lt, prm, c, kap, el, s, n, vel_plan, vel_est, ov, obj_dist, ox, oy, sc0, sc1, sc2,
-                                      vx);
+        const int fl = follow_profile(lt, prm, c, kap, el, s, n, vel_plan, vel_est, ov, obj_dist, bf.cobj_start[b], sc0,
+                                      sc1, sc2, vx);
         if (fl & 1) st |= LTPL_ST_TOO_CLOSE;
         vel_bound = !(fl & 2);
         result = sc0;  // a second profile (reduced horizon) goes to scratch

@@ -114,6 +114,7 @@ def pack_lattice(lat: Lattice) -> tuple:
         ("off_samp_el", lat.samp_el.astype(np.float64)),
         ("off_samp_edge", samp_edge),
         ("off_glob_rl", glob6.astype(np.float64)),
+        ("off_glob_xy", np.ascontiguousarray(glob6[:, 1:3]).astype(np.float64)),
     ]
     h = capi.LatticeHeader()
     h.abi_version = capi.ABI_VERSION

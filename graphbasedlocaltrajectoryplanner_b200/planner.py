@@ -151,7 +151,7 @@ class BatchPlanner(object):
             sc_flags=z((B,), i32), start_node=z((B, 2), i32), const_len=z((B,), i32), const_seg=z((5, B, P0), f64),
             const_coeff=z((B, 8), f64), action_id=z((NSLOT, B), i32), status=z((NSLOT, B), i32),
             n_nodes=z((NSLOT, B), i32), nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
-            edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), path_len=z((NSLOT, B), i32),
+            edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), cobj_start=z((B,), i32), path_len=z((NSLOT, B), i32),
             path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), queue=z((2, NSLOT * B), i32),
             queue_cnt=z((4,), i32), exp_q=z((NSLOT * B,), i32), traj_row=z((NSLOT, B), i32),
             vel_scratch=z((3, NSLOT * B, P), f64),

@@ -101,6 +101,7 @@ typedef struct LtplLatticeHeader {
     uint64_t off_samp_edge;      /* int32 [S] owning edge                             */
     /* global race line, rows (s, x, y, kappa, vel, el) with el = diff(s) (CVPF:166)  */
     uint64_t off_glob_rl;        /* f64 [n_glob_rl - 1][6]                            */
+    uint64_t off_glob_xy;        /* f64x2 [n_glob_rl - 1] x, y (coalesced matching)   */
     uint64_t blob_bytes;
 } LtplLatticeHeader;
 
@@ -160,6 +161,7 @@ typedef struct LtplBuffers {
     int32_t* edge_seq;        /* [NSLOT][B][h_max] lattice edge ids of the new plan (scratch for path assembly)          */
     int32_t* closest_obj;     /* [B] closest_obj_index (into the on-track object list) or -1 (GLNT:191-203, MOPG:113)    */
     double* cobj;             /* [B][4] x, y, v, valid of that object (OTH:770-771)                                      */
+    int32_t* cobj_start;      /* [B] index of that object on the global race line = closest_indexes[0] of CVPF:169-172    */
     int32_t* path_len;        /* [NSLOT][B]                                                                              */
     double* path;             /* [5][NSLOT*B][p_max] planes x, y, psi, kappa, el  (path_dict of calc_paths)              */
     double* coeff;            /* [NSLOT*B][h_max][8] (MOPG:305-309 spline_coeff_mat, stitched OTH:470-472)               */
