@@ -78,6 +78,7 @@ __device__ __forceinline__ void tile_store_t(const WarpCtx& w, const double* til
 // ---- recurrence state machines (same arithmetic as fb_profile_w in ltpl_vel.cuh) ----
 struct FwdSt {
     double o_prev, cur, k_prev, e_prev;
+    double xlo, xhi, x0, f0, sl;   // cached segment of the machine table: axm(v) = f0 + sl * (v - x0) on [xlo, xhi)
     bool prev_rise, active;
     int hint;
 };
@@ -90,7 +91,44 @@ __device__ __forceinline__ double fwd_init(FwdSt& s, double oraw, double kabs, d
     s.prev_rise = false;
     s.active = false;
     s.hint = 0;
+    s.xlo = 1.0;   // empty cache interval
+    s.xhi = 0.0;
+    s.x0 = 0.0;
+    s.f0 = 0.0;
+    s.sl = 0.0;
     return o;
+}
+// np.interp on the machine table with the current segment cached in registers: v moves slowly along a path, so the
+// shared-memory search only runs when v leaves [xlo, xhi)
+__device__ __forceinline__ double axm_cached(FwdSt& s, double v, const VelCfg& c) {
+    if (!(v >= s.xlo && v < s.xhi)) {
+        const int n = c.n_axm;
+        if (v <= c.axm_v[0]) {
+            s.xlo = -LTPL_INF;
+            s.xhi = c.axm_v[0];
+            s.x0 = 0.0;
+            s.f0 = c.axm_a[0];
+            s.sl = 0.0;
+            if (v == s.xhi) return s.f0;
+        } else if (v >= c.axm_v[n - 1]) {
+            s.xlo = c.axm_v[n - 1];
+            s.xhi = LTPL_INF;
+            s.x0 = 0.0;
+            s.f0 = c.axm_a[n - 1];
+            s.sl = 0.0;
+        } else {
+            int j = s.hint;
+            while (j < n - 2 && v >= c.axm_v[j + 1]) ++j;
+            while (j > 0 && v < c.axm_v[j]) --j;
+            s.hint = j;
+            s.xlo = c.axm_v[j];
+            s.xhi = c.axm_v[j + 1];
+            s.x0 = s.xlo;
+            s.f0 = c.axm_a[j];
+            s.sl = c.axm_s[j];
+        }
+    }
+    return fma(s.sl, v - s.x0, s.f0);
 }
 __device__ __forceinline__ double fwd_step(FwdSt& s, double oraw, double kabs, double e, double wmax, const VelCfg& c) {
     const double o_n = fmin(oraw, wmax);
@@ -98,7 +136,10 @@ __device__ __forceinline__ double fwd_step(FwdSt& s, double oraw, double kabs, d
     if (!s.active && rise && !s.prev_rise) s.active = true;
     double nxt = o_n;
     if (s.active) {
-        const double a = acc_forw(s.cur, s.k_prev, c, s.hint);
+        // mode 'accel_forw': min(tyre, machine(v)) + drag (acc_forw of ltpl_vel.cuh with the cached table segment)
+        double a = acc_tire(s.cur, s.k_prev, c.ax_max, c.inv_ay, c.exp_);
+        a = fmin(a, axm_cached(s, sqrt(s.cur), c));
+        a = fma(-s.cur, c.dm, a);
         const double wn = fma(2.0 * a, s.e_prev, s.cur);
         if (wn < o_n) nxt = wn;
         if (wn > wmax) s.active = false;
@@ -280,6 +321,8 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     int* qs = reinterpret_cast<int*>(tiles + VT_NTILES * VT_TILE);
     int* ns = qs + VT_P;
     __shared__ double s_axm[3 * LTPL_MAX_AXM];
+    __shared__ double sp_wcapc[VT_P], sp_wnx[VT_P], sp_snx[VT_P];   // per path slot: final-pass parameters
+    __shared__ int sp_idx_c[VT_P], sp_stop[VT_P], sp_mode[VT_P];
     stage_axm(prm, s_axm);
     const int lane = threadIdx.x;
     const int pl = lane % VT_P;          // path slot of this lane
@@ -339,6 +382,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     const VelCfg c = make_velcfg(prm, s_axm);
     const double wmax = prm.vel_max * prm.vel_max;
     const bool red = (st & LTPL_ST_REDUCED_HORIZON) != 0;
+    const bool any_red = __any_sync(LTPL_FULL, follow_cls && live && n > 0 && red);   // warp uniform
     bool vel_bound = true;
 
     double* t0 = tiles;
@@ -556,10 +600,18 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         }
         const double w_first = profile_sweeps(w, tiles, k_pl, e_pl, np, pl, compute && n > 0, role, lo, hi, n, wcap, we,
                                               wmx, false, c, T_M, T_C, true);
-        // intersection pass (backward order is irrelevant here): out = min(src, complete)
         const double v0c = (role == 1 && use_prof && has_ctrl) ? sqrt(w_first) : vcs;
         const double v0c_r1 = __shfl_sync(LTPL_FULL, v0c, partner);
-        for (int tl = 0; tl < ntile; ++tl) {
+        // parameters of the intersection out = min(src, complete) for the fused final pass
+        if (role == 0) {
+            sp_idx_c[pl] = idx_c;
+            sp_stop[pl] = stop_idx;
+            sp_mode[pl] = (use_prof ? 1 : 0) | (has_ctrl ? 2 : 0);
+            sp_wcapc[pl] = wcap_c;
+        }
+        __syncwarp();
+        // a reduced-horizon follow path needs the intersection materialised (second profile + merge below)
+        for (int tl = 0; tl < (any_red ? ntile : 0); ++tl) {
             const int p0 = tl << 5;
             tile_load_t(w, t2, T_C, p0, np);
             tile_load_t(w, t3, T_M, p0, np);
@@ -665,42 +717,73 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     // pass D (backward): role 0: vx = sqrt(w), s;  role 1: ax = (w1 - w0) / (2 ds) with the standstill fix-up
     // (OTH:926-941); row-major output planes
     // ------------------------------------------------------------------------------------------------------------------
+    // No recurrence here: every tile element is independent, so all 32 lanes work on the 32 x VT_P elements of a tile
+    // (element e = it * 32 + lane -> point e / VT_P, path slot e % VT_P).  For follow paths without a reduced horizon
+    // the intersection min(src, complete) (CVPF:297-310) is evaluated on the fly instead of in a sweep of its own.
     {
+        const bool fused = follow_cls && !any_red;
         double* s_pl = bf.s_vx_ax;
         double* vx_pl = s_pl + pplane;
         double* ax_pl = vx_pl + pplane;
-        double w_next = 0.0, s_next = 0.0;
+        if (lane < VT_P) {
+            sp_wnx[lane] = 0.0;
+            sp_snx[lane] = 0.0;
+        }
         for (int tl = ntile - 1; tl >= 0; --tl) {
             const int p0 = tl << 5;
-            tile_load_t(w, t0, T_F, p0, np);
-            tile_load_t(w, t1, T_S, p0, np);
+            if (fused) {
+                tile_load_t(w, t0, T_C, p0, np);
+                tile_load_t(w, t1, T_M, p0, np);
+                tile_load_t(w, t2, T_B, p0, np);
+            } else {
+                tile_load_t(w, t1, T_F, p0, np);
+            }
+            tile_load_t(w, t3, T_S, p0, np);
             cp_async_wait_all();
             __syncwarp();
-            if (role == 0) {
-#pragma unroll 1
-                for (int k = 31; k >= 0; --k)
-                    if (p0 + k < n) t2[k * VT_W + pl] = sqrt(t0[k * VT_W + pl]);
-            } else if (role == 1) {
-#pragma unroll 1
-                for (int k = 31; k >= 0; --k) {
-                    const int p = p0 + k;
-                    if (p < n) {
-                        const double w0 = t0[k * VT_W + pl], s0 = t1[k * VT_W + pl];
-                        double a = 0.0;
-                        if (p < n - 1) {
-                            a = (w_next - w0) / (2 * (s_next - s0));
-                            if (w0 <= 1e-16 && fabs(a) <= 1e-8) a = -5.0;
+            if (fused) {
+#pragma unroll
+                for (int it = 0; it < VT_P; ++it) {
+                    const int e = it * 32 + lane, k = e / VT_P, cc = e % VT_P, p = p0 + k;
+                    if (p < ns[cc]) {
+                        double src = t2[k * VT_W + cc];   // ego brake profile
+                        const int mode = sp_mode[cc];
+                        if ((mode & 1) && p >= sp_idx_c[cc]) {
+                            if (p > sp_stop[cc])
+                                src = 0.0;
+                            else
+                                src = (mode & 2) ? t0[k * VT_W + cc] : sp_wcapc[cc];
                         }
-                        t3[k * VT_W + pl] = a;
-                        w_next = w0;
-                        s_next = s0;
+                        t1[k * VT_W + cc] = fmin(src, t1[k * VT_W + cc]);
                     }
+                }
+                __syncwarp();
+            }
+#pragma unroll
+            for (int it = 0; it < VT_P; ++it) {
+                const int e = it * 32 + lane, k = e / VT_P, cc = e % VT_P, p = p0 + k;
+                const int nn = ns[cc];
+                if (p < nn) {
+                    const double w0 = t1[k * VT_W + cc], s0 = t3[k * VT_W + cc];
+                    double a = 0.0;
+                    if (p < nn - 1) {
+                        const double w1 = (k < 31) ? t1[(k + 1) * VT_W + cc] : sp_wnx[cc];
+                        const double s1 = (k < 31) ? t3[(k + 1) * VT_W + cc] : sp_snx[cc];
+                        a = (w1 - w0) / (2 * (s1 - s0));
+                        if (w0 <= 1e-16 && fabs(a) <= 1e-8) a = -5.0;
+                    }
+                    t4[k * VT_W + cc] = sqrt(w0);
+                    t5[k * VT_W + cc] = a;
                 }
             }
             __syncwarp();
-            tile_store_rows(w, t1, s_pl, p0);
-            tile_store_rows(w, t2, vx_pl, p0);
-            tile_store_rows(w, t3, ax_pl, p0);
+            if (lane < VT_P) {   // first row of this tile = successor of the last row of the next (lower) tile
+                sp_wnx[lane] = t1[lane];
+                sp_snx[lane] = t3[lane];
+            }
+            tile_store_rows(w, t3, s_pl, p0);
+            tile_store_rows(w, t4, vx_pl, p0);
+            tile_store_rows(w, t5, ax_pl, p0);
             __syncwarp();
         }
     }
