@@ -269,9 +269,13 @@ int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* s
     if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");
     if (prm->axm_v[prm->n_axm - 1] < prm->vel_max)
         return fail("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!");
+#if LTPL_VEL_TILED
+    k_velprofile_tiled<<<(vb->n_paths + 31) / 32, 32, VD_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
+#else
     k_velprofile_dense<<<(vb->n_paths + LTPL_VEL_BLOCK - 1) / LTPL_VEL_BLOCK, LTPL_VEL_BLOCK, 0,
                          static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
-    return check_launch("k_velprofile_dense");
+#endif
+    return check_launch("k_velprofile");
 }
 
 #ifdef LTPL_PROFILE_PHASES

@@ -24,7 +24,11 @@ __device__ __forceinline__ void head_curv(double ax1, double ax2, double ax3, do
     double yd = ay1 + 2 * ay2 * t + 3 * ay3 * t2;
     double xdd = 2 * ax2 + 6 * ax3 * t;
     double ydd = 2 * ay2 + 6 * ay3 * t;
-    *psi = normalize_psi(atan2(yd, xd) - LTPL_PI / 2);
+    // tph.normalize_psi(atan2(y', x') - pi/2): the argument lies in [-3 pi / 2, pi / 2], where the modulo of the
+    // reference is the identity and only the "< -pi -> + 2 pi" branch can fire
+    double h = atan2(yd, xd) - LTPL_PI / 2;
+    if (h < -LTPL_PI) h += 2 * LTPL_PI;
+    *psi = h;
     double q = xd * xd + yd * yd;
     *kappa = (xd * ydd - yd * xdd) / (q * sqrt(q));
 }

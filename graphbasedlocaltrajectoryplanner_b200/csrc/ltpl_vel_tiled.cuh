@@ -802,3 +802,123 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         bf.status[q] = st;
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_velprofile_tiled: stand-alone forward/backward solver over dense [n_paths][n_points] arrays (BASELINE config 5).
+// Throughput regime (100 k paths): one warp = 32 paths, one lane = one path, tiles of 32 points x 32 paths.
+//   sweep 1 (forward):  kappa, el tiles in (cp.async, transposing)  -> w = v^2 tile -> rows of `vx` (used as scratch)
+//   sweep 2 (backward): kappa, el, w tiles in -> final w; vx = sqrt(w) and ax = (w1 - w0) / (2 el) in the same sweep
+// HBM traffic: 5 reads + 3 writes of n_paths * n_points * 8 bytes (algorithmic minimum: 2 reads + 2 writes).
+// ---------------------------------------------------------------------------------------------------------------------
+#define VD_W 33
+#ifndef VD_H
+#define VD_H 16                            // points per tile (power of two <= 32): smaller tiles -> more resident warps
+#endif
+#define VD_TILE (VD_H * VD_W)
+#define VD_SMEM_BYTES (3 * VD_TILE * 8)   // kappa, el, w tiles; vx / ax are produced in place
+
+// one request covers 32 / VD_H path rows x VD_H consecutive points
+__device__ __forceinline__ void vd_load(double* tile, const double* base, int path0, int n_paths, int n_points, int p0,
+                                        int lane) {
+    const int pt = lane % VD_H, sub = lane / VD_H;
+#pragma unroll 4
+    for (int r = sub; r < 32; r += 32 / VD_H) {
+        if (path0 + r < n_paths && p0 + pt < n_points)
+            cp_async8(&tile[pt * VD_W + r], base + (size_t)(path0 + r) * n_points + p0 + pt);
+    }
+}
+__device__ __forceinline__ void vd_store(const double* tile, double* base, int path0, int n_paths, int n_points, int p0,
+                                         int lane) {
+    const int pt = lane % VD_H, sub = lane / VD_H;
+#pragma unroll 4
+    for (int r = sub; r < 32; r += 32 / VD_H) {
+        if (path0 + r < n_paths && p0 + pt < n_points)
+            base[(size_t)(path0 + r) * n_points + p0 + pt] = tile[pt * VD_W + r];
+    }
+}
+
+__global__ void __launch_bounds__(32)
+k_velprofile_tiled(const LtplParams prm, const LtplVelBatch vb) {
+    extern __shared__ __align__(16) unsigned char vd_smem[];
+    double* t_k = reinterpret_cast<double*>(vd_smem);
+    double* t_e = t_k + VD_TILE;
+    double* t_w = t_e + VD_TILE;
+    double* t_v = t_w;   // sqrt(w) replaces w in place
+    double* t_a = t_k;   // ax replaces kappa in place (kappa of the element is consumed before ax is written)
+    __shared__ double s_axm[3 * LTPL_MAX_AXM];
+    stage_axm(prm, s_axm);
+    const int lane = threadIdx.x;
+    const int path0 = blockIdx.x * 32;
+    const int n = vb.n_points;
+    const bool live = path0 + lane < vb.n_paths;
+    const VelCfg c = make_velcfg(prm, s_axm);
+    const double wmax = prm.vel_max * prm.vel_max;
+    double vs = live ? vb.v_start[path0 + lane] : 0.0;
+    double ve = live ? vb.v_end[path0 + lane] : 0.0;
+    if (vs < 0.0) vs = 0.0;
+    if (ve < 0.0) ve = 0.0;
+    const int ntile = (n + VD_H - 1) / VD_H;
+    FwdSt f;
+    f.cur = 0.0;
+    f.hint = 0;
+    for (int tl = 0; tl < ntile; ++tl) {
+        const int p0 = tl * VD_H;
+        vd_load(t_k, vb.kappa, path0, vb.n_paths, n, p0, lane);
+        vd_load(t_e, vb.el, path0, vb.n_paths, n, p0, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        if (live) {
+#pragma unroll 1
+            for (int k = 0; k < VD_H; ++k) {
+                const int p = p0 + k;
+                if (p < n) {
+                    const double kabs = fabs(t_k[k * VD_W + lane]);
+                    const double e = t_e[k * VD_W + lane];
+                    const double oraw = c.ay_max / kabs;
+                    double v = (p == 0) ? fwd_init(f, oraw, kabs, e, vs * vs, wmax) : fwd_step(f, oraw, kabs, e, wmax, c);
+                    if (p == n - 1 && v > ve * ve) v = ve * ve;
+                    t_w[k * VD_W + lane] = v;
+                }
+            }
+        }
+        __syncwarp();
+        vd_store(t_w, vb.vx, path0, vb.n_paths, n, p0, lane);
+        __syncwarp();
+    }
+    BwdSt b;
+    b.cur = 0.0;
+    double w_next = 0.0;
+    for (int tl = ntile - 1; tl >= 0; --tl) {
+        const int p0 = tl * VD_H;
+        vd_load(t_k, vb.kappa, path0, vb.n_paths, n, p0, lane);
+        vd_load(t_e, vb.el, path0, vb.n_paths, n, p0, lane);
+        vd_load(t_w, vb.vx, path0, vb.n_paths, n, p0, lane);
+        cp_async_wait_all();
+        __syncwarp();
+        if (live) {
+#pragma unroll 1
+            for (int k = VD_H - 1; k >= 0; --k) {
+                const int p = p0 + k;
+                if (p < n) {
+                    const double kabs = fabs(t_k[k * VD_W + lane]);
+                    const double e = t_e[k * VD_W + lane];
+                    double wv = t_w[k * VD_W + lane];
+                    double a = 0.0;
+                    if (p == n - 1) {
+                        bwd_init(b, wv, kabs);
+                    } else {
+                        wv = bwd_step(b, wv, kabs, e, wmax, c);
+                        a = (w_next - wv) / (2 * e);
+                    }
+                    t_v[k * VD_W + lane] = sqrt(wv);
+                    t_a[k * VD_W + lane] = a;
+                    w_next = wv;
+                }
+            }
+        }
+        __syncwarp();
+        vd_store(t_v, vb.vx, path0, vb.n_paths, n, p0, lane);
+        vd_store(t_a, vb.ax, path0, vb.n_paths, n, p0, lane);
+        __syncwarp();
+    }
+}

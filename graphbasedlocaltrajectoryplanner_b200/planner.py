@@ -145,19 +145,38 @@ class BatchPlanner(object):
         dev = self.device
         f64, i32, f32 = torch.float64, torch.int32, torch.float32
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
+
+        # The scenario inputs live in ONE packed device buffer (one H2D copy per tick) and the small per-path result
+        # arrays in another (one D2H copy per tick); the named tensors below are views into them.
+        def packed(spec, make):
+            offs, total = {}, 0
+            for name, shape, dt in spec:
+                nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+                offs[name] = (total, nbytes, shape, dt)
+                total += (nbytes + 255) // 256 * 256
+            raw = make(total)
+            views = {name: raw[o:o + nb].view(dt).view(shape) for name, (o, nb, shape, dt) in offs.items()}
+            return raw, views
+
+        in_spec = [("pos", (B, 2), f64), ("heading", (B,), f64), ("vel", (B,), f64), ("vel_est", (B,), f64),
+                   ("n_obj", (B,), i32), ("obj", (B, K, 5), f64)]
+        meta_spec = [("exp_q", (NSLOT * B,), i32), ("traj_row", (NSLOT, B), i32), ("traj_len", (NSLOT, B), i32),
+                     ("traj_id", (NSLOT, B), i32), ("action_id", (NSLOT, B), i32), ("status", (NSLOT, B), i32),
+                     ("sc_flags", (B,), i32), ("queue_cnt", (4,), i32)]
+        self.d_in_raw, t_in = packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
+        self.d_meta_raw, t_meta = packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
         t = dict(
-            pos=z((B, 2), f64), heading=z((B,), f64), vel=z((B,), f64), vel_est=z((B,), f64), n_obj=z((B,), i32),
-            obj=z((B, K, 5), f64),
-            sc_flags=z((B,), i32), start_node=z((B, 2), i32), const_len=z((B,), i32), const_seg=z((5, B, P0), f64),
-            const_coeff=z((B, 8), f64), action_id=z((NSLOT, B), i32), status=z((NSLOT, B), i32),
+            start_node=z((B, 2), i32), const_len=z((B,), i32), const_seg=z((5, B, P0), f64),
+            const_coeff=z((B, 8), f64),
             n_nodes=z((NSLOT, B), i32), nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
-            edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), cobj_start=z((B,), i32), path_len=z((NSLOT, B), i32),
+            edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), cobj_start=z((B,), i32),
+            path_len=z((NSLOT, B), i32),
             path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), queue=z((2, NSLOT * B), i32),
-            queue_cnt=z((4,), i32), exp_q=z((NSLOT * B,), i32), traj_row=z((NSLOT, B), i32),
             vel_scratch=z((3, NSLOT * B, P), f64),
             s_vx_ax=z((3, NSLOT * B, P), f64), vel_t=z((5, P, NSLOT * B + 64), f64),
-            traj=z((NSLOT * B, NE, 7), f32), traj_len=z((NSLOT, B), i32),
-            traj_id=z((NSLOT, B), i32))
+            traj=z((NSLOT * B, NE, 7), f32))
+        t.update(t_in)
+        t.update(t_meta)
         buf = capi.Buffers()
         for name in capi.BUFFER_FIELDS:
             setattr(buf, name, t[name].data_ptr())
@@ -166,16 +185,17 @@ class BatchPlanner(object):
         self.traj_bufs = [t["traj"], z((NSLOT * B, NE, 7), f32)]
         # pinned host staging for the per-tick host <-> device copies (two sets for the pipelined path)
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()   # noqa: E731
-        self.h_in_sets = [dict(pos=pin((B, 2), f64), heading=pin((B,), f64), vel=pin((B,), f64),
-                               vel_est=pin((B,), f64), n_obj=pin((B,), i32), obj=pin((B, K, 5), f64))
-                          for _ in range(2)]
-        self.h_out_sets = [dict(traj=pin((NSLOT * B, NE, 7), f32), exp_q=pin((NSLOT * B,), i32),
-                                traj_row=pin((NSLOT, B), i32), traj_len=pin((NSLOT, B), i32),
-                                traj_id=pin((NSLOT, B), i32), action_id=pin((NSLOT, B), i32),
-                                status=pin((NSLOT, B), i32), sc_flags=pin((B,), i32), queue_cnt=pin((4,), i32))
-                           for _ in range(2)]
+        self.h_in_raw, self.h_in_sets, self.h_meta_raw, self.h_out_sets = [], [], [], []
+        for _ in range(2):
+            raw, views = packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
+            self.h_in_raw.append(raw)
+            self.h_in_sets.append(views)
+            raw, views = packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
+            views["traj"] = pin((NSLOT * B, NE, 7), f32)
+            self.h_meta_raw.append(raw)
+            self.h_out_sets.append(views)
         self.h_in, self.h_out = self.h_in_sets[0], self.h_out_sets[0]
-        self._meta_names = ("exp_q", "traj_row", "traj_len", "traj_id", "action_id", "status", "sc_flags", "queue_cnt")
+        self._meta_names = tuple(n for n, _, _ in meta_spec)
         self._row_bytes = NE * 7 * 4
 
     def device_bytes(self) -> int:
@@ -211,15 +231,16 @@ class BatchPlanner(object):
         h["obj"].numpy()[:, :k, :] = sc.obj
 
     def upload(self, which: int = 0) -> None:
-        for name, src in self.h_in_sets[which].items():
-            self.t[name].copy_(src, non_blocking=True)
+        self.d_in_raw.copy_(self.h_in_raw[which], non_blocking=True)      # one packed H2D copy
+
+    def _download_meta(self, which: int) -> None:
+        self.h_meta_raw[which].copy_(self.d_meta_raw, non_blocking=True)  # one packed D2H copy
 
     def download(self, which: int = 0) -> dict:
         """synchronous-style download on the current stream: per-path arrays + the filled rows of the compact
         trajectory list (the row count is read back first)."""
         out = self.h_out_sets[which]
-        for name in self._meta_names:
-            out[name].copy_(self.t[name], non_blocking=True)
+        self._download_meta(which)
         torch.cuda.current_stream(self.device).synchronize()
         n = int(out["queue_cnt"][2])
         if n:
@@ -272,8 +293,7 @@ class BatchPlanner(object):
             self.tick()
             if device_hook is not None:     # e.g. an all-gather of the device-side action sets (multi-GPU)
                 device_hook(k)
-            for name in self._meta_names:
-                self.h_out_sets[k][name].copy_(self.t[name], non_blocking=True)
+            self._download_meta(k)
             ev_meta[k].record(compute)
             pending.append(k)
             if len(pending) > 1:            # issue the trajectory copy of the previous step; it overlaps this step

@@ -28,6 +28,16 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
         def one(stage=stage):
             capi.check(pl.lib, pl.lib.ltpl_launch_stage(stage, pl.handle, C.byref(pl.params), C.byref(pl.dims), C.byref(pl.buf), pl.stream), name)
         one(); res[name] = timed(one)
+    if os.environ.get("TUNE_VEL"):
+        import numpy as np
+        from graphbasedlocaltrajectoryplanner_b200.scenarios import make_velocity_microbench
+        from graphbasedlocaltrajectoryplanner_b200.velprofile import velprofile_batch_device
+        mb = make_velocity_microbench(100000, 500)
+        d = {k: torch.from_numpy(np.ascontiguousarray(mb[k])).cuda() for k in ("kappa", "el", "v_start", "v_end")}
+        vx = torch.empty_like(d["kappa"]); ax = torch.empty_like(d["kappa"])
+        pl.set_vel_params(vel_max=60.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=bench.ax_max_machines(), safety_d=30.0)
+        vp = lambda: velprofile_batch_device(pl, d["kappa"], d["el"], d["v_start"], d["v_end"], vx, ax)
+        vp(); res["velprofile_ms"] = timed(vp, 5)
     print(json.dumps(res))
     sys.exit(0)
 from graphbasedlocaltrajectoryplanner_b200 import capi
