@@ -79,16 +79,17 @@ int ltpl_sizeof(int which) {
     }
 }
 
-int ltpl_lattice_create(const LtplLatticeHeader* h, const void* dev_blob, LtplLattice** out) {
+int ltpl_lattice_create(const LtplLatticeHeader* h, void* dev_blob, LtplLattice** out) {
     if (!h || !dev_blob || !out) return fail("ltpl_lattice_create: null argument");
     if (h->abi_version != LTPL_ABI_VERSION) return fail("ltpl_lattice_create: ABI version mismatch");
     if (h->max_nodes_per_layer > 64 || h->max_nodes_per_layer < 1)
         return fail("ltpl_lattice_create: max_nodes_per_layer must be in [1, 64]");
+    if (h->tab_stride < 3 || h->tab_stride > 255) return fail("ltpl_lattice_create: tab_stride must be in [3, 255]");
     if (h->num_layers < 4) return fail("ltpl_lattice_create: lattice needs at least 4 layers");
     LtplLattice* lat = new (std::nothrow) LtplLattice;
     if (!lat) return fail("ltpl_lattice_create: out of host memory");
     lat->h = *h;
-    const unsigned char* p = static_cast<const unsigned char*>(dev_blob);
+    unsigned char* p = static_cast<unsigned char*>(dev_blob);
     LatDev& d = lat->d;
     d.L = h->num_layers;
     d.Nn = h->num_nodes;
@@ -133,7 +134,36 @@ int ltpl_lattice_create(const LtplLatticeHeader* h, const void* dev_blob, LtplLa
     LTPL_PTR(samp_edge, int, off_samp_edge);
     LTPL_PTR(glob_rl, double, off_glob_rl);
     LTPL_PTR(glob_xy, double2, off_glob_xy);
+    LTPL_PTR(edge_rec, LtplEdgeRec, off_edge_rec);
+    LTPL_PTR(tab_reach, int, off_tab_reach);
+    LTPL_PTR(tab_node, unsigned char, off_tab_node);
+    LTPL_PTR(tab_edge, int, off_tab_edge);
 #undef LTPL_PTR
+    d.tab_stride = h->tab_stride;
+    {  // follow table: one warp per node (k_follow_table), once per lattice
+        const int maxn = ((h->max_nodes_per_layer + 31) / 32) * 32;
+        const size_t smem = table_smem_bytes_per_warp(maxn, h->tab_stride) * LTPL_WARPS_PER_CTA;
+        cudaError_t e = cudaSuccess;
+        if (smem > 200 * 1024) {
+            delete lat;
+            return fail("ltpl_lattice_create: planning range too large for shared memory");
+        }
+        if (smem > 48 * 1024)
+            e = cudaFuncSetAttribute(k_follow_table, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            k_follow_table<<<(h->num_nodes + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem>>>(
+                d, maxn, reinterpret_cast<int*>(p + h->off_tab_reach), p + h->off_tab_node,
+                reinterpret_cast<int*>(p + h->off_tab_edge));
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            g_err = std::string("ltpl_lattice_create: k_follow_table: ") + cudaGetErrorString(e);
+            delete lat;
+            return -2;
+        }
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     *out = lat;
     return 0;
 }
@@ -279,10 +309,10 @@ int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* s
 }
 
 #ifdef LTPL_PROFILE_PHASES
-int ltpl_debug_phases(unsigned long long* out16, int reset) {
-    if (out16) cudaMemcpyFromSymbol(out16, g_phase, sizeof(unsigned long long) * 16);
+int ltpl_debug_phases(unsigned long long* out32, int reset) {
+    if (out32) cudaMemcpyFromSymbol(out32, g_phase, sizeof(unsigned long long) * 32);
     if (reset) {
-        unsigned long long z[16] = {0};
+        unsigned long long z[32] = {0};
         cudaMemcpyToSymbol(g_phase, z, sizeof(z));
     }
     return 0;

@@ -11,6 +11,22 @@
 
 #include "ltpl_b200.h"
 
+// optional phase timing (debug builds only: -DLTPL_PROFILE_PHASES): cycles per phase summed over lane 0 of every warp
+// (slots 0..15: velocity kernels, 16..31: k_plan)
+#ifdef LTPL_PROFILE_PHASES
+__device__ unsigned long long g_phase[32];
+#define LTPL_PH_INIT long long _t0 = clock64();
+#define LTPL_PH(k)                                                                                   \
+    {                                                                                                \
+        long long _t1 = clock64();                                                                   \
+        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[k], (unsigned long long)(_t1 - _t0));        \
+        _t0 = clock64();                                                                             \
+    }
+#else
+#define LTPL_PH_INIT
+#define LTPL_PH(k)
+#endif
+
 #define LTPL_FULL 0xffffffffu
 #define LTPL_PI 3.141592653589793
 #define LTPL_INF CUDART_INF
@@ -44,6 +60,11 @@ struct LatDev {
     const int* samp_edge;
     const double* glob_rl;  // [n_glob - 1][6]
     const double2* glob_xy; // [n_glob - 1]
+    const LtplEdgeRec* edge_rec;   // [E] (cost, src, dst) of every edge in one 16-byte record (DP inner loop)
+    const int* tab_reach;          // [Nn] follow table (k_follow_table): steps | tie << 8
+    const unsigned char* tab_node; // [Nn][tab_stride] node index per step
+    const int* tab_edge;           // [Nn][tab_stride] edge id per step
+    int tab_stride;
 };
 
 struct LtplLattice {

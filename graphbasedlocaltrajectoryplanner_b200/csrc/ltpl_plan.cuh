@@ -143,29 +143,83 @@ k_startpos(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplB
 // ---------------------------------------------------------------------------------------------------------------------
 struct DpCtx {
     double* dist;        // [2][maxn]
+    double* dsave;       // [maxn] dist after step snap_li: prefix shared by the overtake-left / -right searches
     unsigned char* pred; // [hl][maxn]  k-th in-edge of the node, 255 = unreachable
+    const int4* meta;    // [hl] per layer step li: (first node of the next layer, #nodes, first edge of the pair, #edges)
     int maxn;
     int cur;             // which half of dist holds the last completed layer
     int layer;           // lattice layer of the last completed step
+    int tie;             // an equal-cost alternative was seen (igraph's pick then depends on heap order)
+    int snap_li;         // step whose result dsave holds (0: no snapshot)
+    int tie_save;        // tie flag at the snapshot
 };
 
-// runs up to n_steps layer transitions; returns the number completed (last layer with a reachable node)
+// planning range (GLNT:104-142): layer the plan has to reach from start_layer
+__device__ __forceinline__ int plan_end_layer(const LatDev& lt, int start_layer, int lane) {
+    if (lt.plan_mode == 0) {
+        double des = __dadd_rn(lt.s_rl[start_layer], lt.min_plan_horizon);
+        const double s_last = lt.s_rl[lt.L - 1];
+        if (des > s_last) {
+            if (lt.closed)
+                des = __dsub_rn(des, s_last);
+            else
+                des = s_last;
+        }
+        // bisect.bisect_left(s_raceline, des): first index with s >= des
+        int cnt = 0;
+        #pragma unroll 1
+        for (int i = lane; i < lt.L; i += 32) cnt += (lt.s_rl[i] < des) ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(LTPL_FULL, cnt, o);
+        return cnt;
+    }
+    const int hz = (int)lt.min_plan_horizon;
+    if (lt.closed) return (start_layer + hz) % lt.L;
+    return max(start_layer + hz, lt.L - 1);  // quirk q7
+}
+
+// per-step lattice offsets of the planning range (shared by all searches of a scenario)
+__device__ __forceinline__ void dp_fill_meta(const LatDev& lt, int lane, int4* meta, int start_layer, int planning_dist) {
+    #pragma unroll 1
+    for (int li = 1 + lane; li <= planning_dist; li += 32) {
+        int lay = start_layer + li - 1;
+        if (lay >= lt.L) lay -= lt.L;
+        const int nxt = (lay + 1 >= lt.L) ? 0 : lay + 1;
+        const int nb = lt.node_off[nxt], e0 = lt.edge_layer_off[lay];
+        meta[li] = make_int4(nb, lt.node_off[nxt + 1] - nb, e0, lt.edge_layer_off[lay + 1] - e0);
+    }
+    __syncwarp();
+}
+
+// Runs the layer transitions li_begin .. n_steps; returns the number of completed steps (last layer with a reachable
+// node).  li_begin == 1 starts at start_node; li_begin > 1 resumes from the snapshot in c.dsave (the pred rows below
+// li_begin are those of the run that took the snapshot).  After step snap_at the state is saved to c.dsave.
+// Each lane owns one node of the next layer and scans its in-edges IN CSC ORDER, which keeps igraph's relaxation order
+// and tie rule (strict <, then smaller dist[src]) bit for bit.
 __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int start_layer, int start_node, int n_steps,
-                                      const unsigned* __restrict__ mask, int e_base, int rem_layer, int rem_lo,
-                                      int rem_hi, int* tie_out) {
+                                      const unsigned* mask, int e_base, int rem_layer, int rem_lo, int rem_hi,
+                                      int li_begin, int snap_at) {
     const int maxn = c.maxn;
-    #pragma unroll 1
-    for (int j = lane; j < maxn; j += 32) c.dist[j] = LTPL_INF;
+    int tie = 0;
+    if (li_begin == 1) {
+        #pragma unroll 1
+        for (int j = lane; j < maxn; j += 32) c.dist[j] = (j == start_node) ? 0.0 : LTPL_INF;
+    } else {
+        #pragma unroll 1
+        for (int j = lane; j < maxn; j += 32) c.dist[j] = c.dsave[j];
+        tie = c.tie_save;
+    }
     __syncwarp();
-    if (lane == 0) c.dist[start_node] = 0.0;
-    __syncwarp();
-    int cur = 0, tie = 0, reach = 0, layer = start_layer;
+    int cur = 0, reach = li_begin - 1;
+    int layer = start_layer + li_begin - 1;
+    if (layer >= lt.L) layer -= lt.L;
     #pragma unroll 1
-    for (int li = 1; li <= n_steps; ++li) {
+    for (int li = li_begin; li <= n_steps; ++li) {
         int nxt = layer + 1;
         if (nxt >= lt.L) nxt = 0;
-        const int nbase = lt.node_off[nxt];
-        const int nl = lt.node_off[nxt + 1] - nbase;
+        const int4 mt = c.meta[li];
+        const int nbase = mt.x, nl = mt.y;
+        const int moff = (mt.z >= e_base) ? -e_base : lt.E - e_base;  // edge id -> bit of the window mask
         const double* dcur = c.dist + cur * maxn;
         double* dnxt = c.dist + (cur ^ 1) * maxn;
         int any = 0;
@@ -178,14 +232,14 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
                 #pragma unroll 1
                 for (int k = 0; k < io.y; ++k) {
                     const int e = io.x + k;
-                    const double ds = dcur[lt.edge_src[e]];
+                    const LtplEdgeRec r = lt.edge_rec[e];
+                    const double ds = dcur[r.src];
                     if (!(ds < LTPL_INF)) continue;
                     if (mask) {
-                        int idx = e - e_base;
-                        if (idx < 0) idx += lt.E;
+                        const int idx = e + moff;
                         if ((mask[idx >> 5] >> (idx & 31)) & 1u) continue;
                     }
-                    const double alt = __dadd_rn(ds, lt.edge_cost[e]);
+                    const double alt = __dadd_rn(ds, r.cost);
                     if (alt < best || (alt == best && ds < best_ds)) {
                         best = alt;
                         best_ds = ds;
@@ -205,10 +259,16 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
         cur ^= 1;
         reach = li;
         layer = nxt;
+        if (li == snap_at) {
+            #pragma unroll 1
+            for (int j = lane; j < maxn; j += 32) c.dsave[j] = dnxt[j];
+            c.tie_save = __any_sync(LTPL_FULL, tie) ? 1 : 0;
+            c.snap_li = li;
+        }
     }
     c.cur = cur;
     c.layer = layer;
-    if (__any_sync(LTPL_FULL, tie)) *tie_out = 1;
+    c.tie = __any_sync(LTPL_FULL, tie) ? 1 : 0;
     return reach;
 }
 
@@ -256,59 +316,81 @@ __device__ __forceinline__ int dp_goal(const LatDev& lt, int lane, const DpCtx& 
 // ---------------------------------------------------------------------------------------------------------------------
 struct PlanSmem {  // per warp, followed by dist / mask / pred (sizes depend on the lattice)
     double vx[LTPL_KMAX], vy[LTPL_KMAX], vr[LTPL_KMAX], vv[LTPL_KMAX], pxp[LTPL_KMAX], pyp[LTPL_KMAX];
+    double dx[2 * LTPL_KMAX], dy[2 * LTPL_KMAX], dref[2 * LTPL_KMAX];  // obstacle discs: 2 v current, 2 v + 1 predicted
     int n_veh;
-    int pad;
+    int pad[3];
 };
 
+// per warp: PlanSmem | dist f64[2 maxn] | dsave f64[maxn] | meta int4[hl] | mask u32[mask_words] | pred u8[hl maxn]
 __host__ __device__ inline size_t plan_smem_bytes_per_warp(int maxn, int hl, int mask_words) {
-    size_t s = sizeof(PlanSmem) + sizeof(double) * 2 * maxn + sizeof(unsigned) * mask_words + (size_t)hl * maxn;
+    size_t s = sizeof(PlanSmem) + sizeof(double) * 3 * (size_t)maxn + sizeof(int4) * (size_t)hl +
+               sizeof(unsigned) * mask_words + (size_t)hl * maxn;
     return (s + 15) & ~(size_t)15;
 }
 
-// mark edges of layer pair a -> a+1 that hold a sample inside the inflated obstacle disc (GB:626-644)
-__device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, double ox, double oy, double ref,
+// mark edges of layer pair a -> a+1 that hold a sample inside one of the inflated obstacle discs in `discs` (bit d ->
+// ps->dx/dy/dref[d]) (GB:626-644).  All discs that touch the pair share ONE sweep over its samples (the current and the
+// 0.2 s predicted disc of a vehicle nearly always do); four samples per lane are in flight.
+__device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, unsigned discs, const PlanSmem* ps,
                                            unsigned* mask, int e_base) {
     const int e0 = lt.edge_layer_off[a], e1 = lt.edge_layer_off[a + 1];
     if (e1 <= e0) return;
     const int s0 = lt.samp_off[e0], s1 = lt.samp_off[e1];
+    const int moff = (e0 >= e_base) ? -e_base : lt.E - e_base;
     #pragma unroll 1
-    for (int s = s0 + lane; s < s1; s += 32) {
-        const double2 p = lt.samp_xy[s];
-        const double x = __dsub_rn(p.x, ox), y = __dsub_rn(p.y, oy);
-        const double d2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
-        if (d2 <= ref) {
-            int idx = lt.samp_edge[s] - e_base;
-            if (idx < 0) idx += lt.E;
-            atomicOr(&mask[idx >> 5], 1u << (idx & 31));
+    for (int s = s0 + lane; s < s1; s += 128) {
+        double2 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int si = s + 32 * u;
+            p[u] = lt.samp_xy[(si < s1) ? si : s];
+        }
+        unsigned hit = 0;
+        #pragma unroll 1
+        for (unsigned mm = discs; mm; mm &= mm - 1) {
+            const int d = __ffs(mm) - 1;
+            const double ox = ps->dx[d], oy = ps->dy[d], ref = ps->dref[d];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double x = __dsub_rn(p[u].x, ox), y = __dsub_rn(p[u].y, oy);
+                if (__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)) <= ref) hit |= 1u << u;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int si = s + 32 * u;
+            if (((hit >> u) & 1u) && si < s1) {
+                const int idx = lt.samp_edge[si] + moff;
+                atomicOr(&mask[idx >> 5], 1u << (idx & 31));
+            }
         }
     }
 }
 
-// get_intersec_edges (GIE:36-63) for one disc; returns obj_layer or -1 when outside the planning range
-__device__ __noinline__ int intersect_disc(const LatDev& lt, int lane, double ox, double oy, double radius,
-                                              int p_start, int p_end, unsigned* mask, int e_base) {
+// get_intersec_edges (GIE:36-63) for one disc: layer of the disc's centre (or -1 when outside the planning range) and
+// the (up to) two layer pairs pa -> pa+1, pb -> pb+1 whose edges the disc can block (-1: none)
+__device__ __forceinline__ int disc_pairs(const LatDev& lt, int lane, double ox, double oy, int p_start, int p_end,
+                                          int* pa, int* pb) {
+    *pa = -1;
+    *pb = -1;
     const ArgMinD m = warp_closest_point(lt.refline, lt.L, ox, oy, lane);
     const int o = m.i;
     const int lo = 1;
     const bool in_rng = (p_start - lo <= o && o <= p_end + lo) ||
                         (p_start > p_end && (p_start - lo <= o || o <= p_end + lo));
     if (!in_rng) return -1;
-    // obstacle_ref = (r + veh_width / 2)^2 + stepsize^2 / 4  (GB:626-629)
-    const double ref = __dadd_rn(sq_rn(__dadd_rn(radius, __ddiv_rn(lt.veh_width, 2.0))), __ddiv_rn(sq_rn(lt.step), 4.0));
     // layer window {o-1, o, o+1} with the reference's wrap handling (GB:597-600: quirk q4 drops o+1 when o == L-1)
     int s_l = o - lo, e_l = o + lo;
     if (s_l < 0) s_l += lt.L;
     if (e_l > lt.L) e_l -= lt.L;
-    const bool has_prev = true;               // o-1 (mod L) is always part of the window
     const bool has_next = (e_l < lt.L);       // e_l == L  -> layer L does not exist
-    const int prev = s_l;
+    const int prev = s_l;                     // o-1 (mod L) is always part of the window
     const int next = e_l;
-    if (has_prev && layer_in_range(prev, p_start, p_end) && layer_in_range(o, p_start, p_end) &&
-        ((prev + 1) % lt.L) == o)
-        block_pair(lt, lane, prev, ox, oy, ref, mask, e_base);
+    if (layer_in_range(prev, p_start, p_end) && layer_in_range(o, p_start, p_end) && ((prev + 1) % lt.L) == o)
+        *pa = prev;
     if (has_next && layer_in_range(o, p_start, p_end) && layer_in_range(next, p_start, p_end) &&
         ((o + 1) % lt.L) == next)
-        block_pair(lt, lane, o, ox, oy, ref, mask, e_base);
+        *pb = o;
     return o;
 }
 
@@ -326,7 +408,9 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     unsigned char* base = smem_raw + plan_smem_bytes_per_warp(maxn, hl, mask_words) * wib;
     PlanSmem* ps = reinterpret_cast<PlanSmem*>(base);
     double* dist = reinterpret_cast<double*>(base + sizeof(PlanSmem));
-    unsigned* mask = reinterpret_cast<unsigned*>(dist + 2 * maxn);
+    double* dsave = dist + 2 * maxn;
+    int4* meta = reinterpret_cast<int4*>(dsave + maxn);
+    unsigned* mask = reinterpret_cast<unsigned*>(meta + hl);
     unsigned char* pred = reinterpret_cast<unsigned char*>(mask + mask_words);
     const int B = dm.batch;
 
@@ -345,6 +429,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         bf.cobj[4 * b + 3] = 0.0;
     }
     if (bf.sc_flags[b] != 0) return;
+    LTPL_PH_INIT
 
     const int start_layer = bf.start_node[2 * b], start_node = bf.start_node[2 * b + 1];
     const int p0 = bf.const_len[b];
@@ -377,32 +462,10 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     #pragma unroll 1
     for (int i = lane; i < mask_words; i += 32) mask[i] = 0u;
     __syncwarp();
+    LTPL_PH(16)
 
     // ---- planning range (GLNT:104-142) ----
-    int end_layer;
-    if (lt.plan_mode == 0) {
-        double des = __dadd_rn(lt.s_rl[start_layer], lt.min_plan_horizon);
-        const double s_last = lt.s_rl[lt.L - 1];
-        if (des > s_last) {
-            if (lt.closed)
-                des = __dsub_rn(des, s_last);
-            else
-                des = s_last;
-        }
-        // bisect.bisect_left(s_raceline, des): first index with s >= des
-        int cnt = 0;
-        #pragma unroll 1
-        for (int i = lane; i < lt.L; i += 32) cnt += (lt.s_rl[i] < des) ? 1 : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(LTPL_FULL, cnt, o);
-        end_layer = cnt;
-    } else {
-        const int hz = (int)lt.min_plan_horizon;
-        if (lt.closed)
-            end_layer = (start_layer + hz) % lt.L;
-        else
-            end_layer = max(start_layer + hz, lt.L - 1);  // quirk q7
-    }
+    const int end_layer = plan_end_layer(lt, start_layer, lane);
     int planning_dist = end_layer - start_layer;
     if (planning_dist < 0) planning_dist = lt.L - start_layer + end_layer;
     if (end_layer >= lt.L || planning_dist + 1 > hl || planning_dist + 2 > dm.h_max) {
@@ -410,14 +473,32 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         return;
     }
     const int e_base = lt.edge_layer_off[start_layer];
+    LTPL_PH(17)
 
     // ---- obstacles -> blocked edges, closest object (GLNT:165-213) ----
     int closest_dist = -1, closest_idx = -1, con_layer = -1, con_node = -1;
+    int my_pa = -1, my_pb = -1;  // lane d: layer pairs disc d can block
     #pragma unroll 1
     for (int v = 0; v < n_veh; ++v) {
-        const double ox = ps->vx[v], oy = ps->vy[v], rr = ps->vr[v];
-        int obj_layer = intersect_disc(lt, lane, ox, oy, rr, start_layer, end_layer, mask, e_base);
-        obj_layer = intersect_disc(lt, lane, ps->pxp[v], ps->pyp[v], rr, start_layer, end_layer, mask, e_base);  // q14
+        int pa, pb;
+        disc_pairs(lt, lane, ps->vx[v], ps->vy[v], start_layer, end_layer, &pa, &pb);
+        if (lane == 2 * v) {
+            my_pa = pa;
+            my_pb = pb;
+        }
+        const int obj_layer = disc_pairs(lt, lane, ps->pxp[v], ps->pyp[v], start_layer, end_layer, &pa, &pb);  // q14
+        if (lane == 2 * v + 1) {
+            my_pa = pa;
+            my_pb = pb;
+        }
+        if (lane < 2) {
+            // obstacle_ref = (r + veh_width / 2)^2 + stepsize^2 / 4  (GB:626-629)
+            const int d = 2 * v + lane;
+            ps->dx[d] = lane ? ps->pxp[v] : ps->vx[v];
+            ps->dy[d] = lane ? ps->pyp[v] : ps->vy[v];
+            ps->dref[d] = __dadd_rn(sq_rn(__dadd_rn(ps->vr[v], __ddiv_rn(lt.veh_width, 2.0))),
+                                    __ddiv_rn(sq_rn(lt.step), 4.0));
+        }
         if (obj_layer >= 0) {
             int ld = obj_layer - start_layer;
             if (ld < 0) ld = lt.L - start_layer + obj_layer;
@@ -429,12 +510,25 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         }
     }
     __syncwarp();
+    #pragma unroll 1
+    for (int d = 0; d < 2 * n_veh; ++d) {  // one sweep per distinct layer pair, shared by every disc that touches it
+        #pragma unroll 1
+        for (int slot = 0; slot < 2; ++slot) {
+            const int a = __shfl_sync(LTPL_FULL, slot ? my_pb : my_pa, d);
+            if (a < 0) continue;
+            const unsigned discs = __ballot_sync(LTPL_FULL, my_pa == a || my_pb == a);
+            if (discs & ((1u << d) - 1u)) continue;  // swept together with an earlier disc
+            block_pair(lt, lane, a, discs, ps, mask, e_base);
+        }
+    }
+    __syncwarp();
     if (closest_dist >= 0) {  // GLNT:206-213
         const int nb = lt.node_off[con_layer];
         const ArgMinD m = warp_closest_point(lt.node_xy + nb, lt.node_off[con_layer + 1] - nb, ps->vx[closest_idx],
                                              ps->vy[closest_idx], lane);
         con_node = m.i;
     }
+    LTPL_PH(18)
 
     // ---- objects in / beside the constant path segment (MOPG:76-122) ----
     bool obj_in_const = false, obj_beside = false;
@@ -467,6 +561,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             }
         }
     }
+    LTPL_PH(19)
     // match the closest object to the (closed) global race line: get_s_coord(glob_rl[:, 1:3], obj_pos, closed=True)[1][0]
     // (CVPF:166-172) -- warp-parallel here instead of a serial 800-point scan per follow path in the velocity kernel
     if (closest_idx >= 0) {
@@ -481,6 +576,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         const double a2 = fabs(angle3pt(gn.x, gn.y, ox, oy, g2.x, g2.y));
         if (lane == 0) bf.cobj_start[b] = (a1 >= a2) ? i1 : nb;
     }
+    LTPL_PH(20)
     if (lane == 0) {
         bf.closest_obj[b] = closest_idx;
         if (closest_idx >= 0) {
@@ -514,12 +610,29 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     }
 
     // ---- graph search per action (MOPG:188-257) ----
+    // Three observations cut the number of DPs without touching any result:
+    //  * a search on the unblocked lattice (filter 'planning_range', or 'default' with an empty mask) depends only on
+    //    the start node -> read from the follow table built once per lattice (k_follow_table);
+    //  * two consecutive actions with the same filter ('left' and 'right' on 'default') are the same search;
+    //  * 'overtake_left' and 'overtake_right' differ only from the object's layer onwards -> the second one resumes
+    //    from a snapshot of the first one's state one layer before it.
+    unsigned mask_any = 0;
+    #pragma unroll 1
+    for (int i = lane; i < mask_words; i += 32) mask_any |= mask[i];
+    mask_any = __any_sync(LTPL_FULL, mask_any != 0);
+    dp_fill_meta(lt, lane, meta, start_layer, planning_dist);
     DpCtx c;
     c.dist = dist;
+    c.dsave = dsave;
     c.pred = pred;
+    c.meta = meta;
     c.maxn = maxn;
+    c.snap_li = 0;
+    c.tie_save = 0;
     const int goal_steps = planning_dist;
+    const int tab_row = lt.node_off[start_layer] + start_node;
     int mod_steps = goal_steps;
+    int prev_q = -1, prev_f = -1, prev_reach = 0;
     #pragma unroll 1
     for (int a = 0; a < n_act; ++a) {
         int name = names[a];
@@ -534,15 +647,28 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             rem_lo = 0;
             rem_hi = con_node;
         }
+        // 0: follow table, 1: DP, 2: same search as the previous action
+        int src = (f == 0 || (f == 1 && !mask_any)) ? 0 : ((f == 1 && prev_f == 1) ? 2 : 1);
+        const int tr = lt.tab_reach[tab_row];
+        if (src == 0 && (tr & 0xff) > mod_steps) src = 1;  // table rows end at their own goal layer (open track only)
         int st = 0, tie = 0, found = 0, reach = 0;
         if (mod_steps > 0) {
             const bool start_removed = (rem_layer == start_layer && start_node >= rem_lo && start_node < rem_hi);
             if (start_removed) {
                 st |= LTPL_ST_START_BLOCKED;  // GB:882-885
+            } else if (src == 0) {
+                reach = tr & 0xff;
+                tie = (tr >> 8) & 1;
+            } else if (src == 2) {
+                reach = prev_reach;
             } else {
-                reach = dp_run(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
-                               rem_layer, rem_lo, rem_hi, &tie);
+                const int li_begin = (f == 3 && c.snap_li >= 1) ? c.snap_li + 1 : 1;
+                const int snap_at = (f == 2 && a + 1 < n_act && filt[a + 1] == 3) ? closest_dist - 1 : 0;
+                reach = dp_run(lt, lane, c, start_layer, start_node, mod_steps, mask, e_base, rem_layer, rem_lo, rem_hi,
+                               li_begin, snap_at);
+                tie = c.tie;
             }
+            LTPL_PH(21)
             if (name == LTPL_ACT_FOLLOW || name == LTPL_ACT_STRAIGHT) {
                 if (reach < mod_steps) mod_steps = reach;  // goal layer moves towards the vehicle (MOPG:203-220)
                 found = (reach >= 1);
@@ -568,27 +694,50 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         }
         const int slot = (name == LTPL_ACT_LEFT) ? 1 : ((name == LTPL_ACT_RIGHT) ? 2 : 0);
         const int q = slot * B + b;
+        int* nd = bf.nodes + (size_t)q * dm.h_max * 2;
+        int* es = bf.edge_seq + (size_t)q * dm.h_max;
+        if (found && src == 0) {  // rows of the follow table: node / edge of every step
+            const unsigned char* tn = lt.tab_node + (size_t)tab_row * lt.tab_stride;
+            const int* te = lt.tab_edge + (size_t)tab_row * lt.tab_stride;
+            #pragma unroll 1
+            for (int li = 1 + lane; li <= reach; li += 32) {
+                int layer = start_layer + li;
+                if (layer >= lt.L) layer -= lt.L;
+                nd[2 * (li + 1)] = layer;
+                nd[2 * (li + 1) + 1] = tn[li - 1];
+                es[li - 1] = te[li - 1];
+            }
+        } else if (found && src == 2) {  // copy of the previous action's plan
+            const int* pn = bf.nodes + (size_t)prev_q * dm.h_max * 2;
+            const int* pe = bf.edge_seq + (size_t)prev_q * dm.h_max;
+            #pragma unroll 1
+            for (int i = lane; i < 2 * (reach + 2); i += 32) nd[i] = pn[i];
+            #pragma unroll 1
+            for (int i = lane; i < reach; i += 32) es[i] = pe[i];
+            st |= bf.status[prev_q] & LTPL_ST_TIE_AMBIGUOUS;
+        }
         if (found) {
-            const int gj = dp_goal(lt, lane, c, &tie);
+            int gj = 0;
+            if (src == 1) gj = dp_goal(lt, lane, c, &tie);
             if (tie) st |= LTPL_ST_TIE_AMBIGUOUS;
             st |= LTPL_ST_FOUND;
             if (lane == 0) {
-                int* nd = bf.nodes + (size_t)q * dm.h_max * 2;
-                int* es = bf.edge_seq + (size_t)q * dm.h_max;
                 nd[0] = -1;
                 nd[1] = -1;
-                int j = gj, layer = c.layer;
-                #pragma unroll 1
-                for (int li = reach; li >= 1; --li) {
-                    nd[2 * (li + 1)] = layer;
-                    nd[2 * (li + 1) + 1] = j;
-                    const int e = lt.in_off[lt.node_off[layer] + j].x + (int)pred[li * maxn + j];
-                    es[li - 1] = e;
-                    j = lt.edge_src[e];
-                    layer = (layer == 0) ? lt.L - 1 : layer - 1;
-                }
                 nd[2] = start_layer;
-                nd[3] = j;  // == start_node
+                nd[3] = start_node;
+                if (src == 1) {
+                    int j = gj, layer = c.layer;
+                    #pragma unroll 1
+                    for (int li = reach; li >= 1; --li) {
+                        nd[2 * (li + 1)] = layer;
+                        nd[2 * (li + 1) + 1] = j;
+                        const int e = lt.in_off[lt.node_off[layer] + j].x + (int)pred[li * maxn + j];
+                        es[li - 1] = e;
+                        j = lt.edge_src[e];
+                        layer = (layer == 0) ? lt.L - 1 : layer - 1;
+                    }
+                }
                 bf.n_nodes[q] = reach + 2;
                 bf.action_id[q] = name;
                 bf.status[q] = st;
@@ -596,7 +745,11 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         } else if (lane == 0 && bf.action_id[q] == LTPL_ACT_NONE) {
             bf.status[q] = st;
         }
+        prev_q = q;
+        prev_f = f;
+        prev_reach = reach;
         __syncwarp();
+        LTPL_PH(22)
     }
 
     // ---- "track blocked": no action at all -> constant segment only (OTH:475-506) ----
@@ -611,5 +764,63 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             bf.action_id[q] = LTPL_ACT_STRAIGHT;
             bf.status[q] = LTPL_ST_FOUND | LTPL_ST_CONST_ONLY | LTPL_ST_REDUCED_HORIZON;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_follow_table: search on the UNBLOCKED lattice from every node over its planning range (same dp_run / dp_goal as the
+// online kernel; runs once in ltpl_lattice_create).  Row n: tab_reach[n] = steps | tie << 8, then node index and edge id
+// of every step.  k_plan reads these rows instead of repeating a search whose inputs are all lattice constants.
+// ---------------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t table_smem_bytes_per_warp(int maxn, int hl) {
+    size_t s = sizeof(double) * 2 * (size_t)maxn + sizeof(int4) * (size_t)hl + (size_t)hl * maxn;
+    return (s + 15) & ~(size_t)15;
+}
+
+__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
+k_follow_table(const LatDev lt, const int maxn, int* tab_reach, unsigned char* tab_node, int* tab_edge) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int n = blockIdx.x * LTPL_WARPS_PER_CTA + wib;
+    if (n >= lt.Nn) return;
+    const int hl = lt.tab_stride;
+    unsigned char* base = smem_raw + table_smem_bytes_per_warp(maxn, hl) * wib;
+    double* dist = reinterpret_cast<double*>(base);
+    int4* meta = reinterpret_cast<int4*>(dist + 2 * maxn);
+    unsigned char* pred = reinterpret_cast<unsigned char*>(meta + hl);
+    const int start_layer = lt.node_layer[n];
+    const int start_node = n - lt.node_off[start_layer];
+    const int end_layer = plan_end_layer(lt, start_layer, lane);
+    int planning_dist = end_layer - start_layer;
+    if (planning_dist < 0) planning_dist = lt.L - start_layer + end_layer;
+    if (end_layer >= lt.L || planning_dist + 2 > hl || planning_dist < 1) {  // k_plan flags these scenarios itself
+        if (lane == 0) tab_reach[n] = 0;
+        return;
+    }
+    dp_fill_meta(lt, lane, meta, start_layer, planning_dist);
+    DpCtx c;
+    c.dist = dist;
+    c.dsave = dist;
+    c.pred = pred;
+    c.meta = meta;
+    c.maxn = maxn;
+    c.snap_li = 0;
+    c.tie_save = 0;
+    const int reach = dp_run(lt, lane, c, start_layer, start_node, planning_dist, nullptr, 0, -1, 0, 0, 1, 0);
+    int tie = c.tie;
+    int gj = 0;
+    if (reach >= 1) gj = dp_goal(lt, lane, c, &tie);
+    if (lane == 0) {
+        int j = gj, layer = c.layer;
+        #pragma unroll 1
+        for (int li = reach; li >= 1; --li) {
+            const int e = lt.in_off[lt.node_off[layer] + j].x + (int)pred[li * maxn + j];
+            tab_node[(size_t)n * hl + li - 1] = (unsigned char)j;
+            tab_edge[(size_t)n * hl + li - 1] = e;
+            j = lt.edge_src[e];
+            layer = (layer == 0) ? lt.L - 1 : layer - 1;
+        }
+        tab_reach[n] = reach | (tie << 8);
     }
 }

@@ -17,21 +17,6 @@
 #pragma once
 #include "ltpl_common.cuh"
 
-// optional phase timing (debug builds only: -DLTPL_PROFILE_PHASES): cycles per phase summed over lane 0 of every warp
-#ifdef LTPL_PROFILE_PHASES
-__device__ unsigned long long g_phase[16];
-#define LTPL_PH_INIT long long _t0 = clock64();
-#define LTPL_PH(k)                                                                                   \
-    {                                                                                                \
-        long long _t1 = clock64();                                                                   \
-        if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase[k], (unsigned long long)(_t1 - _t0));        \
-        _t0 = clock64();                                                                             \
-    }
-#else
-#define LTPL_PH_INIT
-#define LTPL_PH(k)
-#endif
-
 struct VelCfg {
     double ax_max, ay_max, inv_ay;  // local gg * gg_scale (VPFB:213-214)
     double exp_, dm;                // friction-ellipse exponent, drag_coeff / m_veh

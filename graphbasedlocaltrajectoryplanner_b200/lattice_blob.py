@@ -88,6 +88,9 @@ def pack_lattice(lat: Lattice) -> tuple:
     samp_edge = np.repeat(np.arange(lat.num_edges, dtype=np.int32), nsamp)
     g = lat.glob_rl
     glob6 = np.column_stack((g[:-1], np.diff(g[:, 0])))                     # CVPF:166
+    edge_rec = np.zeros(lat.num_edges, dtype=np.dtype([("cost", "<f8"), ("src", "<i4"), ("dst", "<i4")]))
+    edge_rec["cost"], edge_rec["src"], edge_rec["dst"] = lat.edge_cost, lat.edge_src, lat.edge_dst
+    tab_stride = int(cap["h_max"])
 
     sections = [
         ("off_node_off", lat.node_off.astype(np.int32)),
@@ -115,6 +118,11 @@ def pack_lattice(lat: Lattice) -> tuple:
         ("off_samp_edge", samp_edge),
         ("off_glob_rl", glob6.astype(np.float64)),
         ("off_glob_xy", np.ascontiguousarray(glob6[:, 1:3]).astype(np.float64)),
+        ("off_edge_rec", edge_rec),
+        # follow table: zero here, filled on the device by ltpl_lattice_create (k_follow_table)
+        ("off_tab_reach", np.zeros(nn, dtype=np.int32)),
+        ("off_tab_node", np.zeros(nn * tab_stride, dtype=np.uint8)),
+        ("off_tab_edge", np.zeros(nn * tab_stride, dtype=np.int32)),
     ]
     h = capi.LatticeHeader()
     h.abi_version = capi.ABI_VERSION
@@ -126,6 +134,8 @@ def pack_lattice(lat: Lattice) -> tuple:
         raise ValueError('Unsupported planning horizon mode "' + str(lat.plan_horizon_mode) + '"!')
     h.max_nodes_per_layer = lat.max_nodes_per_layer
     h.max_window_edges = cap["max_window_edges"]
+    h.max_pair_edges = max(int(np.diff(lat.edge_layer_off).max()), 1)
+    h.tab_stride = tab_stride
     h.lat_offset, h.lat_resolution, h.sampled_resolution = lat.lat_offset, lat.lat_resolution, lat.sampled_resolution
     h.vel_decrease_lat, h.veh_width, h.veh_length = lat.vel_decrease_lat, lat.veh_width, lat.veh_length
     h.virt_goal_node_cost, h.min_plan_horizon = lat.virt_goal_node_cost, lat.min_plan_horizon

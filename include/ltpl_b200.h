@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 3
+#define LTPL_ABI_VERSION 4
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -69,7 +69,8 @@ typedef struct LtplLatticeHeader {
     int32_t plan_horizon_mode;   /* 0 = 'distance', 1 = 'layers' (GLNT:104-136)       */
     int32_t max_nodes_per_layer; /* <= 64                                             */
     int32_t max_window_edges;    /* max #edges inside any planning window (+1 layer)  */
-    int32_t pad0, pad1;
+    int32_t max_pair_edges;      /* max #edges between two consecutive layers         */
+    int32_t tab_stride;          /* row length of the follow table (>= max plan layers + 2) */
     double lat_offset, lat_resolution, sampled_resolution, vel_decrease_lat, veh_width, veh_length;
     double virt_goal_node_cost, min_plan_horizon;
     /* per layer [L] */
@@ -102,8 +103,20 @@ typedef struct LtplLatticeHeader {
     /* global race line, rows (s, x, y, kappa, vel, el) with el = diff(s) (CVPF:166)  */
     uint64_t off_glob_rl;        /* f64 [n_glob_rl - 1][6]                            */
     uint64_t off_glob_xy;        /* f64x2 [n_glob_rl - 1] x, y (coalesced matching)   */
+    /* derived sections (search acceleration)                                         */
+    uint64_t off_edge_rec;       /* LtplEdgeRec [E]                                   */
+    uint64_t off_tab_reach;      /* int32 [Nn]             -- zero on input, filled   */
+    uint64_t off_tab_node;       /* uint8 [Nn][tab_stride] -- by ltpl_lattice_create  */
+    uint64_t off_tab_edge;       /* int32 [Nn][tab_stride] -- (k_follow_table)        */
     uint64_t blob_bytes;
 } LtplLatticeHeader;
+
+/* one edge of the lattice as the DP reads it (16 bytes, one load) */
+typedef struct LtplEdgeRec {
+    double cost;  /* GB:818-821 offline edge cost */
+    int32_t src;  /* node index within the start layer */
+    int32_t dst;  /* node index within the end layer */
+} LtplEdgeRec;
 
 typedef struct LtplLattice LtplLattice; /* opaque handle: header copy + resolved device pointers */
 
@@ -197,7 +210,9 @@ const char* ltpl_last_error(void);
 int ltpl_sizeof(int which); /* 0 header, 1 params, 2 dims, 3 buffers, 4 velbatch: ABI self check for the ctypes mirror */
 
 /* lattice handle over a caller-owned device blob -- replaces unpickling GraphBase (main_offline_callback.py:60-66)      */
-int ltpl_lattice_create(const LtplLatticeHeader* header, const void* dev_blob, LtplLattice** out);
+/* Fills the blob's follow table (search on the unblocked lattice from every node: one kernel on the legacy default  */
+/* stream, synchronised before returning) -- the blob is read-only afterwards.                                         */
+int ltpl_lattice_create(const LtplLatticeHeader* header, void* dev_blob, LtplLattice** out);
 int ltpl_lattice_destroy(LtplLattice* lat);
 
 /* Graph_LTPL.set_startpos (LTPL:262-296 -> OTH.set_initial_pose OTH:181-270), batched                                   */

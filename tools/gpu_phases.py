@@ -16,7 +16,7 @@ pl.set_vel_params(**bench.vel_kwargs())
 pl.stage_scenarios(bench.make_batch(tag, 10000)); pl.upload(); pl.set_startpos()
 for _ in range(3): pl.tick()
 torch.cuda.synchronize()
-out = (ctypes.c_ulonglong * 16)()
+out = (ctypes.c_ulonglong * 32)()
 pl.lib.ltpl_debug_phases(None, 1)
 pl.tick(); torch.cuda.synchronize()
 pl.lib.ltpl_debug_phases(out, 0)
@@ -25,6 +25,10 @@ nw = (cnt[0] + 31) // 32 + (cnt[1] + 31) // 32
 names = {0: "pass A", 1: "scalars", 2: "pass B fwd", 3: "pass C bwd", 4: "single profile", 5: "output pass"} if os.environ.get("TILED", "1") == "1" else {0: "cumsum s", 1: "2x s_coord on path", 2: "ego brake", 3: "glob_rl match", 4: "opp brake+stop idx+vctrl",
          5: "control profile", 6: "complete profile", 7: "min", 8: "non-follow fb / red", 9: "ax+sqrt", 10: "follow total tail"}
 print("queue counts", cnt[:2], "warps", nw)
-tot = sum(out)
+pn = {16: "plan: defaults+object filter", 17: "plan: planning range", 18: "plan: blocked edges+closest", 19: "plan: const-seg objects",
+      20: "plan: glob match", 21: "plan: DP", 22: "plan: goal+backtrack"}
+for k in range(16, 23):
+    print("%-30s %10.0f cycles/scenario" % (pn[k], out[k] / 10000.0))
+tot = sum(out[:16])
 for k in range(11):
     print("%-28s %12.0f cycles/warp-with-phase(avg over all warps) %5.1f%%" % (names.get(k, k), out[k] / nw, 100.0 * out[k] / max(tot, 1)))
