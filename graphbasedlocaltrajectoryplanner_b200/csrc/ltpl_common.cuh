@@ -92,6 +92,33 @@ __device__ __forceinline__ double angle3pt(double ax, double ay, double bx, doub
     return ang;
 }
 
+// |angle3pt(pn, P, p1)| against |angle3pt(pn, P, p2)| (get_s_coord.py:60-77: which neighbour segment holds P).  The
+// unsigned angle at P between (pn - P) and (p_i - P) is strictly decreasing in its cosine, so the comparison is decided
+// on the two cosines whenever they differ by more than 1e-9 (orders of magnitude above the rounding of either
+// formulation); only near-ties evaluate the reference's atan2 expression.  gt: ang1 > ang2, ge: ang1 >= ang2.
+struct AngCmp {
+    bool gt, ge;
+};
+__device__ __forceinline__ AngCmp angle_cmp(double2 pn, double px, double py, double2 p1, double2 p2) {
+    const double ux = pn.x - px, uy = pn.y - py;
+    const double v1x = p1.x - px, v1y = p1.y - py, v2x = p2.x - px, v2y = p2.y - py;
+    const double un = ux * ux + uy * uy, n1 = v1x * v1x + v1y * v1y, n2 = v2x * v2x + v2y * v2y;
+    AngCmp r;
+    if (un > 0.0 && n1 > 0.0 && n2 > 0.0) {
+        const double c1 = (ux * v1x + uy * v1y) * rsqrt(n1), c2 = (ux * v2x + uy * v2y) * rsqrt(n2);
+        const double d = c1 - c2;
+        if (d * d > 1e-18 * un) {
+            r.gt = r.ge = (c1 < c2);
+            return r;
+        }
+    }
+    const double a1 = fabs(angle3pt(pn.x, pn.y, px, py, p1.x, p1.y));
+    const double a2 = fabs(angle3pt(pn.x, pn.y, px, py, p2.x, p2.y));
+    r.gt = a1 > a2;
+    r.ge = a1 >= a2;
+    return r;
+}
+
 // tph.normalize_psi
 __device__ __forceinline__ double normalize_psi(double psi) {
     double a = fmod(fabs(psi), 2 * LTPL_PI);
@@ -109,19 +136,17 @@ struct ArgMinD {
 };
 
 // first-minimum argmin over the warp (ties -> lower index), every lane gets the result
+// v >= 0 (squared distances): the bit pattern of a non-negative double orders like the value, so the minimum is three
+// 32-bit warp reductions (REDUX): high word, low word among the high-word winners, index among the value winners.
 __device__ __forceinline__ ArgMinD warp_argmin(double v, int i) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(LTPL_FULL, v, o);
-        int oi = __shfl_xor_sync(LTPL_FULL, i, o);
-        if (ov < v || (ov == v && oi < i)) {
-            v = ov;
-            i = oi;
-        }
-    }
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    const unsigned hi = (unsigned)(u >> 32), lo = (unsigned)u;
+    const unsigned mh = __reduce_min_sync(LTPL_FULL, hi);
+    const unsigned ml = __reduce_min_sync(LTPL_FULL, (hi == mh) ? lo : 0xffffffffu);
+    const unsigned mi = __reduce_min_sync(LTPL_FULL, (hi == mh && lo == ml) ? (unsigned)i : 0xffffffffu);
     ArgMinD r;
-    r.v = v;
-    r.i = i;
+    r.v = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+    r.i = (int)mi;
     return r;
 }
 
@@ -153,11 +178,10 @@ __device__ __noinline__ double s_coord_closed(const double2* __restrict__ pts, c
     if (idx2 > n - 1) idx2 = 0;
     int a1 = (idx1 < 0) ? idx1 + n : idx1;
     double2 pn = pts[nb], p1 = pts[a1], p2 = pts[idx2];
-    double ang1 = fabs(angle3pt(pn.x, pn.y, px, py, p1.x, p1.y));
-    double ang2 = fabs(angle3pt(pn.x, pn.y, px, py, p2.x, p2.y));
+    const AngCmp ac = angle_cmp(pn, px, py, p1, p2);
     double2 a, b;
     double sbase;
-    if (ang1 > ang2) {
+    if (ac.gt) {
         a = p1;
         b = pn;
         sbase = s_arr[a1];
@@ -172,7 +196,7 @@ __device__ __noinline__ double s_coord_closed(const double2* __restrict__ pts, c
     double sy = __dadd_rn(a.y, __dmul_rn(t, bay));
     double ds = sqrt(__dadd_rn(sq_rn(a.x - sx), sq_rn(a.y - sy)));
     if (i0_out) {
-        if (ang1 >= ang2) {
+        if (ac.ge) {
             *i0_out = idx1;
             *i1_out = nb;
         } else {
@@ -194,9 +218,7 @@ __device__ __noinline__ bool inside_bounds(const LatDev& lt, double px, double p
         if (idx2 > n - 1) idx2 = 0;
         int a1 = (idx1 < 0) ? idx1 + n : idx1;
         double2 pn = lt.center[nb], p1 = lt.center[a1], p2 = lt.center[idx2];
-        double ang1 = fabs(angle3pt(pn.x, pn.y, px, py, p1.x, p1.y));
-        double ang2 = fabs(angle3pt(pn.x, pn.y, px, py, p2.x, p2.y));
-        if (ang1 >= ang2) {
+        if (angle_cmp(pn, px, py, p1, p2).ge) {
             i0 = a1;
             i1 = nb;
         } else {

@@ -295,20 +295,22 @@ __device__ __forceinline__ int dp_goal(const LatDev& lt, int lane, const DpCtx& 
             tie = 1;
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double oa = __shfl_xor_sync(LTPL_FULL, best, o);
-        const double od = __shfl_xor_sync(LTPL_FULL, best_ds, o);
-        const int oj = __shfl_xor_sync(LTPL_FULL, best_j, o);
-        if (oa < LTPL_INF && oa == best && od == best_ds && oj != best_j) tie = 1;
-        if (oa < best || (oa == best && (od < best_ds || (od == best_ds && oj < best_j)))) {
-            best = oa;
-            best_ds = od;
-            best_j = oj;
-        }
-    }
-    if (__any_sync(LTPL_FULL, tie)) *tie_out = 1;
-    return best_j;
+    // lexicographic minimum of (alt, dist, j) over the lanes; costs are >= 0, so their bit patterns order like the values
+    // and every key is two 32-bit warp reductions
+    const unsigned long long ua = (unsigned long long)__double_as_longlong(best);
+    const unsigned long long ud = (unsigned long long)__double_as_longlong(best_ds);
+    const unsigned ah = __reduce_min_sync(LTPL_FULL, (unsigned)(ua >> 32));
+    bool in = ((unsigned)(ua >> 32) == ah);
+    const unsigned al = __reduce_min_sync(LTPL_FULL, in ? (unsigned)ua : 0xffffffffu);
+    in = in && ((unsigned)ua == al);
+    const unsigned dh = __reduce_min_sync(LTPL_FULL, in ? (unsigned)(ud >> 32) : 0xffffffffu);
+    in = in && ((unsigned)(ud >> 32) == dh);
+    const unsigned dl = __reduce_min_sync(LTPL_FULL, in ? (unsigned)ud : 0xffffffffu);
+    in = in && ((unsigned)ud == dl) && (best < LTPL_INF);
+    const unsigned win = __ballot_sync(LTPL_FULL, in);
+    const unsigned gj = __reduce_min_sync(LTPL_FULL, in ? (unsigned)best_j : 0x7fffffffu);
+    if (__popc(win) > 1 || __any_sync(LTPL_FULL, tie && in)) *tie_out = 1;
+    return (int)gj;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -572,9 +574,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         const int i1 = (nb - 1 < 0) ? ng - 1 : nb - 1;
         const int i2 = (nb + 1 > ng - 1) ? 0 : nb + 1;
         const double2 gn = lt.glob_xy[nb], g1 = lt.glob_xy[i1], g2 = lt.glob_xy[i2];
-        const double a1 = fabs(angle3pt(gn.x, gn.y, ox, oy, g1.x, g1.y));
-        const double a2 = fabs(angle3pt(gn.x, gn.y, ox, oy, g2.x, g2.y));
-        if (lane == 0) bf.cobj_start[b] = (a1 >= a2) ? i1 : nb;
+        if (lane == 0) bf.cobj_start[b] = angle_cmp(gn, ox, oy, g1, g2).ge ? i1 : nb;
     }
     LTPL_PH(20)
     if (lane == 0) {

@@ -214,10 +214,8 @@ __device__ __forceinline__ double s_coord_from_nb(const double* x, const double*
                                                   int ntc, int n, int nb, double px, double py) {
     const int idx1 = max(nb - 1, 0), idx2 = min(nb + 1, n - 1);
     const double xn = x[nb], yn = y[nb];
-    const double ang1 = fabs(angle3pt(xn, yn, px, py, x[idx1], y[idx1]));
-    const double ang2 = fabs(angle3pt(xn, yn, px, py, x[idx2], y[idx2]));
     int ia, ib;
-    if (ang1 > ang2) {
+    if (angle_cmp(make_double2(xn, yn), px, py, make_double2(x[idx1], y[idx1]), make_double2(x[idx2], y[idx2])).gt) {
         ia = idx1;
         ib = nb;
     } else {
