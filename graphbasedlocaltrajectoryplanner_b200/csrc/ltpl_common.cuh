@@ -156,12 +156,18 @@ __device__ __noinline__ ArgMinD warp_closest_point(const double2* __restrict__ p
     double bv = LTPL_INF;
     int bi = 0x7fffffff;
     #pragma unroll 1
-    for (int i = lane; i < n; i += 32) {
-        double2 p = pts[i];
-        double d = dist2_rn(p.x, p.y, px, py);
-        if (d < bv) {
-            bv = d;
-            bi = i;
+    for (int i0 = lane; i0 < n; i0 += 128) {  // four loads in flight per lane; candidates still visited in index order
+        double2 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) p[u] = pts[min(i0 + 32 * u, n - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            const double d = dist2_rn(p[u].x, p[u].y, px, py);
+            if (i < n && d < bv) {
+                bv = d;
+                bi = i;
+            }
         }
     }
     return warp_argmin(bv, bi);

@@ -112,36 +112,56 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     // ---- C2 spline through the nodes: tridiagonal system in the knot tangents m_k (== tph.calc_splines) ----
     const double psi_s = cs[2 * cplane + p0 - 1];           // MOPG:300-301: heading at the end of the constant segment
     const double psi_e = lt.edge_psi1[eid[nseg - 1]];       // MOPG:307: psi of the last sample
-    if (lane < 2) {
-        const double* kp = (lane == 0) ? kx : ky;
-        double* m = (lane == 0) ? mx : my;
-        double* dp = (lane == 0) ? dxp : dyp;
-        m[0] = (lane == 0) ? cos(psi_s + LTPL_PI / 2) : sin(psi_s + LTPL_PI / 2);
-        m[nseg] = (lane == 0) ? cos(psi_e + LTPL_PI / 2) : sin(psi_e + LTPL_PI / 2);
-        if (nseg > 1) {
-            // rows k = 1 .. nseg-1:  (2/el[k-1]) m[k-1] + 4 (1/el[k-1] + 1/el[k]) m[k] + (2/el[k]) m[k+1] = r[k]
-            // forward sweep (both lanes keep their own c' copy: lane 0 -> cp, lane 1 recomputes into registers)
-            double cprev = 0.0, dprev = 0.0;
-            for (int k = 1; k < nseg; ++k) {
-                const double e0 = kel[k - 1], e1 = kel[k];
-                const double lo = 2.0 / e0, di = 4.0 * (1.0 / e0 + 1.0 / e1), up = 2.0 / e1;
-                double r = 6.0 * ((kp[k] - kp[k - 1]) / (e0 * e0) + (kp[k + 1] - kp[k]) / (e1 * e1));
-                if (k == 1) r -= lo * m[0];
-                if (k == nseg - 1) r -= up * m[nseg];
-                const double den = (k == 1) ? di : (di - lo * cprev);
-                const double cc = (k == nseg - 1) ? 0.0 : up / den;
-                const double dd = (k == 1) ? r / den : (r - lo * dprev) / den;
-                if (lane == 0) cp[k] = cc;
-                dp[k] = dd;
-                cprev = cc;
-                dprev = dd;
-            }
+    // rows k = 1 .. nseg-1:  (2/el[k-1]) m[k-1] + 4 (1/el[k-1] + 1/el[k]) m[k] + (2/el[k]) m[k+1] = r[k]
+    // The rows themselves (lo, r_x, r_y; di and up follow from lo) do not depend on the elimination: all lanes build
+    // them in parallel, so that the serial Thomas sweep on lanes 0 / 1 is left with one reciprocal per row.
+    const double m0x = cos(psi_s + LTPL_PI / 2), m0y = sin(psi_s + LTPL_PI / 2);
+    const double mex = cos(psi_e + LTPL_PI / 2), mey = sin(psi_e + LTPL_PI / 2);
+    for (int k = 1 + lane; k < nseg; k += 32) {
+        const double i0 = 1.0 / kel[k - 1], i1 = 1.0 / kel[k];
+        const double lo = 2.0 * i0, up = 2.0 * i1;
+        double rx = 6.0 * ((kx[k] - kx[k - 1]) * (i0 * i0) + (kx[k + 1] - kx[k]) * (i1 * i1));
+        double ry = 6.0 * ((ky[k] - ky[k - 1]) * (i0 * i0) + (ky[k + 1] - ky[k]) * (i1 * i1));
+        if (k == 1) {
+            rx -= lo * m0x;
+            ry -= lo * m0y;
         }
+        if (k == nseg - 1) {
+            rx -= up * mex;
+            ry -= up * mey;
+        }
+        cp[k] = lo;   // lower diagonal of row k (== upper diagonal of row k - 1); replaced by c' in the sweep
+        dxp[k] = rx;
+        dyp[k] = ry;
+    }
+    if (lane == 0) {
+        mx[0] = m0x;
+        my[0] = m0y;
+        mx[nseg] = mex;
+        my[nseg] = mey;
     }
     __syncwarp();
     if (lane < 2 && nseg > 1) {
         double* m = (lane == 0) ? mx : my;
-        const double* dp = (lane == 0) ? dxp : dyp;
+        double* dp = (lane == 0) ? dxp : dyp;
+        // forward sweep; lo[k] is read before lane 0 overwrites cp[k] with c'[k] (both lanes run in lock step and the
+        // value is taken into a register first), up[k] = lo[k + 1]
+        double cprev = 0.0, dprev = 0.0;
+        double lo = cp[1];
+        for (int k = 1; k < nseg; ++k) {
+            const double up = (k + 1 < nseg) ? cp[k + 1] : 2.0 / kel[k];
+            const double di = 2.0 * (lo + up);
+            const double inv = 1.0 / ((k == 1) ? di : (di - lo * cprev));
+            const double cc = (k == nseg - 1) ? 0.0 : up * inv;
+            const double dd = ((k == 1) ? dp[k] : (dp[k] - lo * dprev)) * inv;
+            __syncwarp(0x3);
+            if (lane == 0) cp[k] = cc;
+            dp[k] = dd;
+            cprev = cc;
+            dprev = dd;
+            lo = up;
+        }
+        __syncwarp(0x3);
         m[nseg - 1] = dp[nseg - 1];
         for (int k = nseg - 2; k >= 1; --k) m[k] = dp[k] - cp[k] * m[k + 1];
     }

@@ -245,6 +245,7 @@ __device__ __forceinline__ double profile_sweeps(const WarpCtx& w, double* tiles
     double* t_w0 = tiles + 2 * VT_TILE;
     double* t_w1 = tiles + 3 * VT_TILE;
     double* t_w = tsel ? t_w1 : t_w0;
+    double* t_o = tiles + 4 * VT_TILE;
     const int ntile = (np + 31) >> 5;
     FwdSt f;
     f.cur = 0.0;
@@ -255,6 +256,14 @@ __device__ __forceinline__ double profile_sweeps(const WarpCtx& w, double* tiles
         tile_load_rows(w, t_e, el_pl, p0);
         cp_async_wait_all();
         __syncwarp();
+        // curvature speed limit w <= ay_max / |kappa| of the whole tile: element-wise, so all 32 lanes share the
+        // divisions instead of the 2 VT_P recurrence lanes paying one per step
+#pragma unroll
+        for (int it = 0; it < VT_P; ++it) {
+            const int e = it * 32 + w.lane, k = e / VT_P, cc = e % VT_P;
+            t_o[k * VT_W + cc] = c.ay_max / fabs(t_k[k * VT_W + cc]);
+        }
+        __syncwarp();
         if (compute) {
 #pragma unroll 1
             for (int k = 0; k < 32; ++k) {
@@ -262,7 +271,7 @@ __device__ __forceinline__ double profile_sweeps(const WarpCtx& w, double* tiles
                 if (p >= lo && p <= hi) {
                     const double kabs = fabs(t_k[k * VT_W + pl]);
                     const double e = t_e[k * VT_W + pl];
-                    const double oraw = c.ay_max / kabs;
+                    const double oraw = t_o[k * VT_W + pl];
                     double v = (p == lo) ? fwd_init(f, oraw, kabs, e, wcap, wmax) : fwd_step(f, oraw, kabs, e, wmax, c);
                     if (p == hi && we >= 0.0 && v > we) v = we;
                     t_w[k * VT_W + pl] = v;
@@ -395,6 +404,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     // pass A (forward).  role 0: s = [0, cumsum(el[:-1])] (OTH:743), ego brake profile (CVPF:152-165);
     //                    role 1: nearest path point to the object and to the ego position (OTH:774-782)
     // ------------------------------------------------------------------------------------------------------------------
+    LTPL_PH_INIT
     const double ox = live ? bf.cobj[4 * b] : 0.0, oy = live ? bf.cobj[4 * b + 1] : 0.0;
     const double ov = live ? bf.cobj[4 * b + 2] : 0.0;
     const double epx = live ? bf.pos[2 * b] : 0.0, epy = live ? bf.pos[2 * b + 1] : 0.0;
@@ -473,6 +483,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         if (follow_cls) tile_store_t(w, t5, T_B, p0, np);
         __syncwarp();
     }
+    LTPL_PH(0)
     __threadfence_block();
     const double* scol = T_S + mycol;
     // role exchange: both role lanes of a path continue with identical scalars
@@ -573,6 +584,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         }
     }
 
+    LTPL_PH(1)
     // ------------------------------------------------------------------------------------------------------------------
     // follow: pass B / C.  role 0: complete profile on [0, n-1] -> T_M;  role 1: control profile on [idx_c, stop_idx]
     // (or the single value vcs^2 when stop_idx == idx_c) -> T_C                                        (CVPF:263-310)
@@ -598,6 +610,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         }
         const double w_first = profile_sweeps(w, tiles, k_pl, e_pl, np, pl, compute && n > 0, role, lo, hi, n, wcap, we,
                                               wmx, false, c, T_M, T_C, true);
+        LTPL_PH(2)
         const double v0c = (role == 1 && use_prof && has_ctrl) ? sqrt(w_first) : vcs;
         const double v0c_r1 = __shfl_sync(LTPL_FULL, v0c, partner);
         // parameters of the intersection out = min(src, complete) for the fused final pass
@@ -645,6 +658,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         vel_bound = !(flags & 2);
     }
 
+    LTPL_PH(3)
     // ------------------------------------------------------------------------------------------------------------------
     // all actions but follow, and follow with a reduced horizon: v_end rule + one profile on role 0 (OTH:834-923)
     // ------------------------------------------------------------------------------------------------------------------
@@ -711,6 +725,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         }
     }
 
+    LTPL_PH(4)
     // ------------------------------------------------------------------------------------------------------------------
     // pass D (backward): role 0: vx = sqrt(w), s;  role 1: ax = (w1 - w0) / (2 ds) with the standstill fix-up
     // (OTH:926-941); row-major output planes
@@ -786,6 +801,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         }
     }
 
+    LTPL_PH(5)
     // acceptance (OTH:943-1025; no backup plan exists on the first tick)
     if (live && !prefix && n > 0 && role == 0) {
         if (!vel_bound) st |= LTPL_ST_VEL_BOUND_VIOL;

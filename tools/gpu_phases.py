@@ -21,8 +21,8 @@ pl.lib.ltpl_debug_phases(None, 1)
 pl.tick(); torch.cuda.synchronize()
 pl.lib.ltpl_debug_phases(out, 0)
 cnt = pl.t["queue_cnt"].cpu().numpy()
-nw = (cnt[0] + 31) // 32 + (cnt[1] + 31) // 32
-names = {0: "pass A", 1: "scalars", 2: "pass B fwd", 3: "pass C bwd", 4: "single profile", 5: "output pass"} if os.environ.get("TILED", "1") == "1" else {0: "cumsum s", 1: "2x s_coord on path", 2: "ego brake", 3: "glob_rl match", 4: "opp brake+stop idx+vctrl",
+nw = (cnt[0] + 7) // 8 + (cnt[1] + 7) // 8
+names = {0: "pass A (s, ego brake, nearest)", 1: "follow scalars", 2: "follow sweeps (fwd+bwd)", 3: "reduced merge", 4: "single profile (fwd+bwd)", 5: "output pass"} if os.environ.get("TILED", "1") == "1" else {0: "cumsum s", 1: "2x s_coord on path", 2: "ego brake", 3: "glob_rl match", 4: "opp brake+stop idx+vctrl",
          5: "control profile", 6: "complete profile", 7: "min", 8: "non-follow fb / red", 9: "ax+sqrt", 10: "follow total tail"}
 print("queue counts", cnt[:2], "warps", nw)
 pn = {16: "plan: defaults+object filter", 17: "plan: planning range", 18: "plan: blocked edges+closest", 19: "plan: const-seg objects",
@@ -30,5 +30,5 @@ pn = {16: "plan: defaults+object filter", 17: "plan: planning range", 18: "plan:
 for k in range(16, 23):
     print("%-30s %10.0f cycles/scenario" % (pn[k], out[k] / 10000.0))
 tot = sum(out[:16])
-for k in range(11):
+for k in range(6):
     print("%-28s %12.0f cycles/warp-with-phase(avg over all warps) %5.1f%%" % (names.get(k, k), out[k] / nw, 100.0 * out[k] / max(tot, 1)))
