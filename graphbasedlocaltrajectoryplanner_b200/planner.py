@@ -52,6 +52,8 @@ DEFAULT_ONLINE = dict(max_heading_offset=0.8, nmbr_export_points=115, v_max_offs
 
 
 class BatchPlanner(object):
+    N_SETS = 3   # host staging / export buffer sets of the pipelined path (plan_stream)
+
     def __init__(self, lattice: Lattice = None, online: dict = None, device=None, veh_param_dyn_model_exp: float = 1.0,
                  veh_param_dragcoeff: float = 0.85, veh_param_mass: float = 1000.0, packed: tuple = None,
                  blob_tensor: torch.Tensor = None):
@@ -181,12 +183,12 @@ class BatchPlanner(object):
         for name in capi.BUFFER_FIELDS:
             setattr(buf, name, t[name].data_ptr())
         self.t, self.buf, self.dims = t, buf, d
-        # second compact export buffer: the pipelined stream planner lets the D2H of step i overlap step i + 1
-        self.traj_bufs = [t["traj"], z((NSLOT * B, NE, 7), f32)]
-        # pinned host staging for the per-tick host <-> device copies (two sets for the pipelined path)
+        # further compact export buffers: the pipelined stream planner lets the D2H of step i overlap step i + 1
+        self.traj_bufs = [t["traj"]] + [z((NSLOT * B, NE, 7), f32) for _ in range(self.N_SETS - 1)]
+        # pinned host staging for the per-tick host <-> device copies (N_SETS sets for the pipelined path)
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()   # noqa: E731
         self.h_in_raw, self.h_in_sets, self.h_meta_raw, self.h_out_sets = [], [], [], []
-        for _ in range(2):
+        for _ in range(self.N_SETS):
             raw, views = packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
             self.h_in_raw.append(raw)
             self.h_in_sets.append(views)
@@ -253,17 +255,19 @@ class BatchPlanner(object):
 
         Per step: host staging (pinned) -> H2D -> k_startpos -> tick kernels -> D2H of the per-path arrays on the compute
         stream; the large D2H of the compact trajectory rows runs on a second stream and overlaps the kernels of the
-        next step (two export buffers, CUDA events for the hand-over).  Results are views of pinned host memory that
-        stay valid until two further steps have been submitted."""
+        next step (CUDA events for the hand-over).  With N_SETS = 3 staging / export buffer sets the host stages step
+        i + 1 while the GPU runs step i and the copy engine drains step i - 1, so the GPU never waits for the host.
+        Results are views of pinned host memory; a result stays valid until N_SETS - 1 further results were taken."""
         dev = self.device
+        ns = self.N_SETS
         compute = torch.cuda.current_stream(dev)
         copy_stream = getattr(self, "_copy_stream", None)
         if copy_stream is None:
             copy_stream = self._copy_stream = torch.cuda.Stream(device=dev)
-        ev_meta = [torch.cuda.Event(), torch.cuda.Event()]
-        ev_d2h = [None, None]
-        pending = []          # [(index, set)] submitted, trajectory copy not yet issued
-        inflight = []         # [(index, set, n_rows)] trajectory copy issued
+        ev_meta = [torch.cuda.Event() for _ in range(ns)]
+        ev_d2h = [None] * ns
+        pending = []          # sets submitted, trajectory copy not yet issued
+        inflight = []         # sets whose trajectory copy is issued, oldest first
 
         def issue_copy(k):
             ev_meta[k].synchronize()
@@ -276,16 +280,16 @@ class BatchPlanner(object):
                 ev.record(copy_stream)
             ev_d2h[k] = ev
             out["n_rows"] = n
-            return n
+            inflight.append(k)
 
         i = 0
         for sc in batches:
-            k = i & 1
-            if ev_d2h[k] is not None:
-                # results of step i - 2 (same buffers) must have left the device; hand them out before reuse
-                ev_d2h[k].synchronize()
-                yield self.h_out_sets[k]
-                inflight.pop(0)
+            k = i % ns
+            while inflight and (inflight[0] == k or ev_d2h[inflight[0]].query()):
+                # hand out finished results in order; the set about to be reused must have left the device first
+                j = inflight.pop(0)
+                ev_d2h[j].synchronize()
+                yield self.h_out_sets[j]
             self.stage_scenarios(sc, vel_est=vel_est, which=k)
             self.buf.traj = self.traj_bufs[k].data_ptr()
             self.upload(which=k)
@@ -297,15 +301,13 @@ class BatchPlanner(object):
             ev_meta[k].record(compute)
             pending.append(k)
             if len(pending) > 1:            # issue the trajectory copy of the previous step; it overlaps this step
-                pk = pending.pop(0)
-                inflight.append((pk, issue_copy(pk)))
+                issue_copy(pending.pop(0))
             i += 1
         while pending:
-            pk = pending.pop(0)
-            inflight.append((pk, issue_copy(pk)))
-        for pk, _ in inflight:
-            ev_d2h[pk].synchronize()
-            yield self.h_out_sets[pk]
+            issue_copy(pending.pop(0))
+        for j in inflight:
+            ev_d2h[j].synchronize()
+            yield self.h_out_sets[j]
         self.buf.traj = self.traj_bufs[0].data_ptr()
 
     # -- kernels ---------------------------------------------------------------------------------------------------------------
