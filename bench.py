@@ -9,8 +9,9 @@ A "step" = one planning tick (calc_paths + calc_vel_profile, 4 kernels) over one
 (SURVEY 8(d) config 2: Monteblanco lattice with lat_resolution=1.0, lon_straight_step=12.0 -> 216 layers x 7..12 nodes;
 random ego arc length + 1..3 dynamic obstacles, seed 20260924).  set_startpos is setup.
   value : device-timed (CUDA events on the launching stream), inputs resident in HBM, L2 flushed between steps
-  e2e   : same metric through the public API Graph_LTPL.plan_batch with HOST buffers: H2D of the scenario arrays,
-          set_startpos + tick kernels, D2H of the exported action sets, all inside the timed region
+  e2e   : same metric through the public API Graph_LTPL.plan_stream with HOST buffers: per step host staging + H2D of
+          the scenario arrays, set_startpos + tick kernels, D2H of the per-path arrays and of the kept trajectory rows,
+          all inside the timed region (the D2H of step i overlaps the kernels of step i + 1)
   roofline / cpu_baseline : see DESIGN.md "Measurement"
 Multi-GPU: scenarios are independent -> every rank plans its own 10 000-scenario batch ("weak" scaling), no data-path
 collective; the lattice blob is NCCL-broadcast from rank 0 at init and the e2e leg all-gathers the action sets.
@@ -27,8 +28,19 @@ import time
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug output (printed to stdout by default) goes to stderr
+# stdout carries exactly ONE JSON line.  NCCL prints its version banner (and any NCCL_DEBUG output) to the process's
+# stdout, so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a duplicate of the
+# original stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 import numpy as np  # noqa: E402
 
@@ -232,7 +244,7 @@ def main():
         total = float(np.sum(t))
         value = sample * args.steps / total
         desc = "first %d scenarios of the seeded batch per step" % sample
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": METRIC, "value": value, "unit": "ticks/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -352,9 +364,6 @@ def main():
         for _ in range(3):
             one()
         ktime[name] = timed_loop(one, args.steps) / args.steps
-    if rank == 0:
-        stop_evt.set()
-        th.join(timeout=3)
 
     # ------------------------------------------------------------------------------------------------------------------
     # e2e: public API with host buffers (pinned): H2D scenario arrays + set_startpos + tick + D2H action sets per step
@@ -383,6 +392,9 @@ def main():
     e2e_value = world * args.batch * args.steps / t_e2e
     assert rows > 0 and rows <= cap_rows * args.steps * 3
     rows_per_step = rows / args.steps
+    if rank == 0:
+        stop_evt.set()
+        th.join(timeout=3)
 
     if rank != 0:
         if world > 1:
@@ -470,7 +482,7 @@ def main():
             extra["velprofile_error"] = str(e)[:200]
         result["extra"] = extra
 
-    print(json.dumps(result))
+    emit(result)
     if world > 1:
         dist.destroy_process_group()
 
