@@ -40,6 +40,10 @@ def load_reference():
         np.object = object
     if not hasattr(np, 'Inf'):
         np.Inf = np.inf
+    # The reference addresses graph vertices by str((layer, node)) (GB:163, 742); with its pinned NumPy 1.x a NumPy
+    # integer prints as '41', with NumPy 2 as 'np.int64(41)' -- which silently disables remove_nodes_filter once GLNT:74
+    # has turned the zone lists into NumPy integers.  Restore the NumPy 1.x scalar repr the reference was written for.
+    np.set_printoptions(legacy="1.25")
     import graph_ltpl  # noqa
     import graph_ltpl.Graph_LTPL as gl
     gl.FORCE_RECALC = False
@@ -76,7 +80,7 @@ def ax_max_machines_table():
     return np.vstack((tab, [100.0, tab[-1, 1]]))
 
 
-def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False):
+def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False, blocked_zones=None):
     """one stateless planning tick through the reference's public API (main_min_example.py:69-104 flow)."""
     name = '_Graph_LTPL__nmbr_export_points'
     keep = getattr(ltpl, name)
@@ -88,7 +92,10 @@ def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False):
         if out_of_track:
             return rec
         oth = ltpl._Graph_LTPL__oth
-        path_dict = ltpl.calc_paths(prev_action_id="straight", object_list=object_list)
+        # zone objects persist inside the reference instance: every tick here is a FIRST tick, so start without zones
+        ltpl._Graph_LTPL__obj_zone = []
+        ltpl._Graph_LTPL__obj_list_handler._ObjectListInterface__object_zones = []
+        path_dict = ltpl.calc_paths(prev_action_id="straight", object_list=object_list, blocked_zones=blocked_zones)
         rec['paths'] = {k: [np.array(a) for a in v] for k, v in path_dict.items()}
         rec['nodes'] = {k: [list(map(list, n)) for n in v]
                         for k, v in oth._OnlineTrajectoryHandler__last_action_set_nodes.items()}
@@ -152,6 +159,66 @@ def pack_ticks(recs, pmax=None):
     return out
 
 
+def make_zone(lat, rng, pos):
+    """random blocked zone ('nodes' type: [layer ids, node ids, left bound, right bound], LTPL:311-312) ahead of /
+    around the ego position: 3-12 layers, the left or the right part of every layer (10 %: one fully blocked layer)."""
+    near = int(np.argmin(np.sum(np.power(lat.refline - np.asarray(pos), 2), axis=1)))
+    first = (near + int(rng.integers(0, 11))) % lat.num_layers
+    length = int(rng.integers(3, 13))
+    full_width = rng.random() < 0.1
+    left = rng.random() < 0.5
+    layers, nodes = [], []
+    for k in range(1 if full_width else length):
+        l = (first + k) % lat.num_layers
+        n_l = lat.nodes_in_layer(l)
+        m = int(rng.integers(1, n_l))
+        ids = range(n_l) if full_width else (range(0, m) if left else range(m, n_l))
+        for j in ids:
+            layers.append(l)
+            nodes.append(j)
+    return [layers, nodes, np.zeros((2, 2)), np.zeros((2, 2))]
+
+
+def ext_fixture(ltpl, lat, track, n, vel_kwargs):
+    """zones (GLNT:43-99) + emergency trajectory (OTH:1027-1034): stateless first ticks through the reference."""
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import make_scenarios
+    sc = make_scenarios(track, n, seed=777, n_obj_min=0, n_obj_max=3)
+    rng = np.random.default_rng(778)
+    vk = dict(vel_kwargs, incl_emerg_traj=True)
+    recs, zones = [], []
+    for b in range(sc.size):
+        zone = make_zone(lat, rng, sc.pos[b]) if b % 4 != 3 else None
+        zones.append(zone)
+        bz = None if zone is None else {'zone_%d' % b: zone}
+        recs.append(run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], sc.object_list(b), vk, full=True,
+                             blocked_zones=bz))
+    pk = pack_ticks(recs)
+    pmax = pk['path'].shape[2]
+    zmax = max([len(z[0]) for z in zones if z is not None] + [1])
+    em = np.zeros((n, pmax, 7))
+    em_len = np.zeros(n, dtype=np.int32)
+    em_id = np.full(n, -1, dtype=np.int32)
+    z_layers = np.full((n, zmax), -1, dtype=np.int32)
+    z_nodes = np.full((n, zmax), -1, dtype=np.int32)
+    for i, r in enumerate(recs):
+        if zones[i] is not None:
+            z_layers[i, :len(zones[i][0])] = zones[i][0]
+            z_nodes[i, :len(zones[i][1])] = zones[i][1]
+        if 'traj' in r and 'emergency' in r['traj']:
+            t = r['traj']['emergency'][0]
+            em[i, :t.shape[0]] = t
+            em_len[i] = t.shape[0]
+            em_id[i] = r['ids']['emergency']
+    pk.update(em_traj=em, em_len=em_len, em_id=em_id, zone_layers=z_layers, zone_nodes=z_nodes, sc_pos=sc.pos,
+              sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj, sc_obj=sc.obj,
+              ax_max_machines=vel_kwargs['ax_max_machines'])
+    acts = {a: int((pk['path_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)}
+    print("[ext] zones: %d of %d scenarios; action paths %s; emergency trajectories %d; reduced %d; out of track %d" %
+          (sum(z is not None for z in zones), n, acts, int((em_len > 0).sum()), int(pk['red_len'].sum()),
+           int(pk['out_of_track'].sum())))
+    return pk
+
+
 def lattice_fixture(graph_ltpl, ltpl, n_edge_samples=300, seed=7):
     """compact description of the reference-built GraphBase (validates the product's lattice builder)."""
     from graphbasedlocaltrajectoryplanner_b200.lattice import Lattice
@@ -180,6 +247,8 @@ def main():
     ap.add_argument('--quick', action='store_true', help='default lattice only')
     ap.add_argument('--n-default', type=int, default=96)
     ap.add_argument('--n-other', type=int, default=32)
+    ap.add_argument('--ext-only', action='store_true', help='only the zone / emergency fixture (default lattice)')
+    ap.add_argument('--n-ext', type=int, default=64)
     args = ap.parse_args()
 
     graph_ltpl = load_reference()
@@ -198,6 +267,11 @@ def main():
     for tag, overrides, n, omin, omax in configs:
         ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
         fx, lat = lattice_fixture(graph_ltpl, ltpl)
+        if tag == "default":
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_ext_default.npz'),
+                                **ext_fixture(ltpl, lat, track, args.n_ext, vel_kwargs))
+            if args.ext_only:
+                return
         np.savez_compressed(os.path.join(GOLDEN, 'lattice_%s.npz' % tag), **fx)
         print("[%s] lattice: %s" % (tag, lat.summary()))
 

@@ -276,8 +276,35 @@ class OracleLTPL(object):
         return edges, obj_layer
 
     # ----------------------------------------------------------------------------------------------------------------------
-    # gen_local_node_template  (GLNT:13-222, without zones)
+    # gen_local_node_template  (GLNT:13-222)
     # ----------------------------------------------------------------------------------------------------------------------
+    def zone_removed_nodes(self, start_node, blocked_zones):
+        """GLNT:43-99 for the first tick after set_startpos: every zone is new (not processed, not disabled, not fixed).
+        Returns the set {(layer, node)} removed by the 'overtaking_zones' filter.
+
+        Graph_LTPL.calc_paths (LTPL:324-329) calls update_zone once per dict key, and update_zone (OLI:155-237) flags
+        every zone that is not the one passed in as removed -- with more than one key the reference then fails in
+        GLNT:69-83 (boolean index of the wrong length), so only a single zone per scenario is a defined input."""
+        lt = self.lat
+        if not blocked_zones:
+            return set()
+        if len(blocked_zones) != 1:
+            raise NotImplementedError("more than one blocked zone per tick is not a defined input of the reference")
+        zone = list(blocked_zones.values())[0]
+        layer_ids = np.array(zone[0], dtype=np.int64)
+        node_ids = np.array(zone[1], dtype=np.int64)
+        n = 4                                                 # UNBLOCK_N_LAYERS_WHEN_IN_ZONE (GLNT:9)
+        s0 = start_node[0]
+        if (s0 + n) <= lt.num_layers:                         # GLNT:58-66 (quirk q6 in the wrap branch)
+            u_l = np.logical_and(layer_ids >= s0, layer_ids < (s0 + n))
+        else:
+            u_l = np.logical_or(np.logical_and(layer_ids >= s0, layer_ids < lt.num_layers),
+                                np.logical_and(layer_ids >= 0, layer_ids < ((s0 + n) % (lt.num_layers - 1) - 1)))
+        if np.any(u_l):                                       # vehicle within the zone -> unblock (GLNT:70-77)
+            layer_ids = layer_ids[~u_l]
+            node_ids = node_ids[~u_l]
+        return set(zip(layer_ids.tolist(), node_ids.tolist()))
+
     def gen_local_node_template(self, start_node, obj_veh):
         lt = self.lat
         start_layer = start_node[0]
@@ -314,7 +341,7 @@ class OracleLTPL(object):
     # graph search  (GB:854-929 search_graph_layer with virtual goal node; igraph Dijkstra semantics as a layered DP)
     # ----------------------------------------------------------------------------------------------------------------------
     def search(self, start_node, goal_layer, range_layers, blocked, removed_layer=None, removed_lo=0, removed_hi=0,
-               cost_factor=None):
+               cost_factor=None, zone=None):
         """returns (node list [[layer, node], ...] or None, tie_flag).
 
         nodes [removed_lo, removed_hi) of `removed_layer` are absent (MOPG:148-159); `blocked` = edge ids removed from
@@ -324,6 +351,8 @@ class OracleLTPL(object):
         sl, sn = start_node
         if removed_layer is not None and sl == removed_layer and removed_lo <= sn < removed_hi:
             return None, False                               # GB:882-885 start node filtered
+        if zone and (sl, sn) in zone:
+            return None, False
         layers = [sl]
         l = sl
         while l != goal_layer:
@@ -341,6 +370,8 @@ class OracleLTPL(object):
             par = {}
             for j in range(lt.nodes_in_layer(b)):
                 if removed_layer is not None and b == removed_layer and removed_lo <= j < removed_hi:
+                    continue
+                if zone and (b, j) in zone:                   # 'overtaking_zones' is the base of every other filter
                     continue
                 g = lt.node_off[b] + j
                 e0, cnt = lt.in_off[g]
@@ -387,7 +418,7 @@ class OracleLTPL(object):
     # ----------------------------------------------------------------------------------------------------------------------
     # main_online_path_gen  (MOPG:11-334)
     # ----------------------------------------------------------------------------------------------------------------------
-    def main_online_path_gen(self, start_node, obj_veh, last_action_id, const_path_seg, pos_est):
+    def main_online_path_gen(self, start_node, obj_veh, last_action_id, const_path_seg, pos_est, zone=None):
         lt = self.lat
         end_layer, closest_obj_index, closest_obj_node, blocked, range_layers = \
             self.gen_local_node_template(start_node, obj_veh)
@@ -452,7 +483,7 @@ class OracleLTPL(object):
             while True:                                       # MOPG:203-220
                 if mod_goal == start_node[0]:
                     break
-                nodes, tie = self.search(start_node, mod_goal, range_layers, blk, **kw)
+                nodes, tie = self.search(start_node, mod_goal, range_layers, blk, zone=zone, **kw)
                 if nodes is not None or not (name == "follow" or name == "straight"):
                     break
                 mod_goal -= 1
@@ -509,7 +540,7 @@ class OracleLTPL(object):
     # ----------------------------------------------------------------------------------------------------------------------
     # OTH.calc_paths, first tick after set_initial_pose  (OTH:289-516)
     # ----------------------------------------------------------------------------------------------------------------------
-    def calc_paths(self, st, obj_veh):
+    def calc_paths(self, st, obj_veh, blocked_zones=None):
         action_id_sel = "straight"                            # forced action id (OTH:262-263, 313-315)
         last_pp = st['path_param']
         start_node = st['start_node']
@@ -518,7 +549,9 @@ class OracleLTPL(object):
         start_node_idx = st['nodes'].index(start_node)
         const_path_seg = last_pp[:loc + 1, :]
 
-        res, closest_obj_index = self.main_online_path_gen(start_node, obj_veh, action_id_sel, const_path_seg, None)
+        zone = self.zone_removed_nodes(start_node, blocked_zones)
+        res, closest_obj_index = self.main_online_path_gen(start_node, obj_veh, action_id_sel, const_path_seg, None,
+                                                           zone=zone)
 
         for name in list(res['nodes'].keys()):                # OTH:433-472
             pp = res['path_param'][name][0]
@@ -675,7 +708,7 @@ class OracleLTPL(object):
     # OTH.get_ref_idx + OTH.calc_vel_profile, first tick  (OTH:518-601, 603-1040)
     # ----------------------------------------------------------------------------------------------------------------------
     def calc_vel_profile(self, st, res, obj_veh, pos_est, vel_est, vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0),
-                         ax_max_machines=np.atleast_2d([100.0, 5.0]), safety_d=30.0):
+                         ax_max_machines=np.atleast_2d([100.0, 5.0]), safety_d=30.0, incl_emerg_traj=False):
         lt = self.lat
         vk = dict(vel_max=vel_max, gg_scale=gg_scale, ax_max_machines=np.asarray(ax_max_machines, dtype=np.float64))
         # get_ref_idx, never planned before (OTH:590-599)
@@ -767,6 +800,17 @@ class OracleLTPL(object):
                 out_traj[action_id] = [bp_out]
             # else: action set removed (vel constraints broken)
 
+        if incl_emerg_traj and out_traj:                       # OTH:1027-1034 + calc_brake_emergency.py:9-47
+            em_base = list(out_traj.keys())[0]
+            traj = out_traj[em_base][0]
+            el = np.diff(traj[:, 0])
+            v_brake = tph.calc_vel_profile_brake(kappa=traj[:, 4], el_lengths=el, v_start=traj[0, 5], drag_coeff=0.854,
+                                                 m_veh=1160.0, loc_gg=np.ones((traj.shape[0], 2)) * tuple(local_gg))
+            idx_em = len(v_brake)
+            a_brake = tph.calc_ax_profile(vx_profile=v_brake, el_lengths=el[:idx_em], eq_length_output=True)
+            out_traj['emergency'] = [np.column_stack((traj[:idx_em, 0:5], v_brake, a_brake))]
+            out_ids['emergency'] = out_ids[em_base]
+
         n_exp = self.p['nmbr_export_points']
         cut = {k: [v[0][:n_exp, :]] for k, v in out_traj.items()}       # LTPL:401-406
         return dict(traj_full=out_traj, traj=cut, ids={k: out_ids[k] for k in out_traj}, vel_bound=vel_bound_flags)
@@ -774,15 +818,14 @@ class OracleLTPL(object):
     # ----------------------------------------------------------------------------------------------------------------------
     # one stateless tick = set_startpos -> calc_paths -> calc_vel_profile  (main_min_example.py:69-104)
     # ----------------------------------------------------------------------------------------------------------------------
-    def tick(self, pos, heading, vel, object_list, vel_kwargs=None):
+    def tick(self, pos, heading, vel, object_list, vel_kwargs=None, blocked_zones=None):
         vel_kwargs = dict(vel_kwargs or {})
-        vel_kwargs.pop('incl_emerg_traj', None)
         self.old_gg_scale = None
         st = self.set_startpos(np.asarray(pos, dtype=np.float64), float(heading), float(vel))
         if not (st['in_track'] and st['cor_heading']):
             return dict(out_of_track=True)
         obj_veh = self.process_object_list(object_list)
-        res = self.calc_paths(st, obj_veh)
+        res = self.calc_paths(st, obj_veh, blocked_zones)
         vp = self.calc_vel_profile(st, res, obj_veh, np.asarray(pos, dtype=np.float64), float(vel), **vel_kwargs)
         return dict(out_of_track=False, start_node=st['start_node'], paths=res['path_param'], nodes=res['nodes'],
                     node_idx=res['node_idx'], coeff=res['coeff'], red_len=res['red_len'], tie=res.get('tie', {}),

@@ -121,3 +121,23 @@ def compare_records(got, want, ctx=""):
         assert got["traj"][act][0].shape[0] == n_cut, ctx + " exported rows " + act
         assert_close("export[%s]" % act, got["traj"][act][0], want["traj"][act][0][:n_cut],
                      ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+
+
+def zone_of(g, b):
+    """blocked_zones dict of scenario b of the zone / emergency fixture (None: no zone)."""
+    n = int((g["zone_layers"][b] >= 0).sum())
+    if n == 0:
+        return None
+    return {"zone_%d" % b: [g["zone_layers"][b, :n].tolist(), g["zone_nodes"][b, :n].tolist(), np.zeros((2, 2)),
+                            np.zeros((2, 2))]}
+
+
+def compare_emergency(rec, g, b, ctx=""):
+    """'emergency' entry (OTH:1027-1034) of a tick record against the zone / emergency fixture."""
+    n = int(g["em_len"][b])
+    has = "emergency" in rec.get("traj_full", {})
+    assert has == (n > 0), "%s scenario %d: emergency present=%s, golden len %d" % (ctx, b, has, n)
+    if has:
+        assert int(rec["ids"]["emergency"]) % 10 == int(g["em_id"][b]) % 10, "%s scenario %d emergency id" % (ctx, b)
+        assert_close("traj[emergency]", rec["traj_full"]["emergency"][0], g["em_traj"][b, :n],
+                     ("s", "x", "y", "psi", "kappa", "vx", "ax"), "%s scenario %d" % (ctx, b))

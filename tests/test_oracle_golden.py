@@ -35,3 +35,19 @@ def test_oracle_config1_min_example():
         rec = orc.tick(g["sc_pos"][b], g["sc_heading"][b], g["sc_vel"][b], obj, {})
         H.compare_record(rec, g, b, prefix="", ctx="config1")
     assert int(g["path_len"][0, 0]) > 0 and int(g["path_len"][1, 1]) > 0   # straight / follow exercised
+
+
+def test_oracle_zones_and_emergency():
+    """blocked zones (GLNT:43-99, 'nodes' type, first tick) and the emergency trajectory (OTH:1027-1034)."""
+    from oracle.ltpl_oracle import OracleLTPL
+    g = H.golden("ticks_ext_default.npz")
+    orc = OracleLTPL(H.lattice_for("default"))
+    vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0,
+              incl_emerg_traj=True)
+    n = g["sc_pos"].shape[0]
+    assert int((g["zone_layers"][:, 0] >= 0).sum()) >= n // 2 and int((g["em_len"] > 0).sum()) >= n // 2
+    for b in range(n):
+        rec = orc.tick(g["sc_pos"][b], g["sc_heading"][b], g["sc_vel"][b], H.object_list(g, b), vk,
+                       blocked_zones=H.zone_of(g, b))
+        H.compare_record(rec, g, b, prefix="", ctx="ext")
+        H.compare_emergency(rec, g, b, ctx="ext")
