@@ -16,8 +16,9 @@ plus the batched variants ``set_startpos_batch`` / ``calc_paths_batch`` / ``calc
 over a ``ScenarioBatch`` (thousands of independent ego-start x obstacle scenarios per call).
 
 Scope: ticks are stateless -- ``calc_paths`` plans the first tick after ``set_startpos``; the reference's
-iterative memory across ticks depends on the wall clock (OTH:353-378) and is a listed next row, as are blocked zones,
-location dependent ``local_gg`` dicts and the emergency trajectory.  Offline graph generation is replaced by the flat
+iterative memory across ticks depends on the wall clock (OTH:353-378) and is a listed next row, as are location
+dependent ``local_gg`` dicts.  ``blocked_zones`` takes one zone per scenario ('nodes' type, GLNT:43-99 first-tick
+semantics); ``incl_emerg_traj=True`` adds the 'emergency' entry (OTH:1027-1034).  Offline graph generation is replaced by the flat
 lattice blob (lattice.py); logging and visualisation of the reference are out of scope.
 """
 
@@ -109,13 +110,12 @@ class Graph_LTPL(object):
 
     def calc_paths(self, prev_action_id: str, prev_traj_idx: int = 0, object_list: list = None,
                    blocked_zones: dict = None) -> dict:
-        if blocked_zones:
-            raise NotImplementedError("blocked zones are not part of the batched planning path yet (SURVEY 8(f) rank 3)")
         if self.__state is None:
             raise NotImplementedError("calc_paths() plans the first tick after set_startpos(); the reference's "
                                       "wall-clock dependent multi-tick memory (OTH:346-414) is SURVEY 8(f) rank 1")
         sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel],
-                                             [[o for o in (object_list or []) if o.get('type') == 'physical']])
+                                             [[o for o in (object_list or []) if o.get('type') == 'physical']],
+                                             blocked_zones=[blocked_zones] if blocked_zones else None)
         for o in (object_list or []):
             if o.get('type') != 'physical':   # OLI:140-141
                 self.__log.warning("Found non-supported object of type '%s' in object list!" % o.get('type'))
@@ -136,13 +136,11 @@ class Graph_LTPL(object):
                          safety_d: float = 30.0, incl_emerg_traj: bool = False) -> tuple:
         if self.__state != "paths":
             raise ValueError("calc_paths() must be called before calc_vel_profile()")
-        if incl_emerg_traj:
-            raise NotImplementedError("the optional emergency trajectory is SURVEY 8(f) rank 4")
         if type(local_gg) is dict:
             raise NotImplementedError("location dependent friction (local_gg dict) is not batched yet; pass a tuple")
         pl = self.__planner
         pl.set_vel_params(vel_max=vel_max, gg_scale=gg_scale, local_gg=local_gg, ax_max_machines=ax_max_machines,
-                          safety_d=safety_d)
+                          safety_d=safety_d, incl_emerg_traj=incl_emerg_traj)
         pl.t["vel_est"].fill_(float(vel_est))
         pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
         if not np.array_equal(pos, self.__pos):

@@ -12,7 +12,7 @@ import os
 import subprocess
 import sys
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 NSLOT = 3
 KMAX = 16
 MAX_AXM = 32
@@ -56,17 +56,19 @@ class Params(C.Structure):
                 ("dyn_model_exp", C.c_double), ("drag_coeff", C.c_double), ("m_veh", C.c_double),
                 ("vel_max", C.c_double), ("gg_scale", C.c_double), ("gg_ax", C.c_double), ("gg_ay", C.c_double),
                 ("safety_d", C.c_double), ("n_axm", C.c_int32), ("traj_base_id", C.c_int32),
+                ("incl_emerg_traj", C.c_int32), ("pad0", C.c_int32),
                 ("axm_v", C.c_double * MAX_AXM), ("axm_a", C.c_double * MAX_AXM), ("axm_s", C.c_double * MAX_AXM)]
 
 
 class Dims(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("batch", "k_obj", "p0_max", "p_max", "h_max", "n_export", "pad0", "pad1")]
+    _fields_ = [(n, C.c_int32) for n in ("batch", "k_obj", "p0_max", "p_max", "h_max", "n_export", "n_zone_words",
+                                            "n_zones")]
 
 
 BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
                  "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj", "cobj_start",
                  "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "vel_scratch", "s_vx_ax",
-                 "vel_t", "traj", "traj_len", "traj_id")
+                 "vel_t", "traj", "traj_len", "traj_id", "zone_bits", "zone_sel", "em_info")
 
 
 class Buffers(C.Structure):

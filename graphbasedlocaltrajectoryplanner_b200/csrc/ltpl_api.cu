@@ -19,6 +19,7 @@
 #include "ltpl_plan.cuh"
 #include "ltpl_vel.cuh"
 #include "ltpl_vel_tiled.cuh"
+#include "ltpl_emerg.cuh"
 
 #ifndef LTPL_VEL_TILED
 #define LTPL_VEL_TILED 1   // 1: tile-streamed velocity kernel (ltpl_vel_tiled.cuh), 0: thread-per-path k_vel
@@ -179,6 +180,8 @@ static int check_common(const LtplLattice* lat, const LtplParams* prm, const Ltp
     if (dm->k_obj < 1 || dm->k_obj > LTPL_KMAX) return fail("dims.k_obj must be in [1, 16]");
     if (dm->p_max % 4 != 0 || dm->p_max < dm->p0_max) return fail("dims.p_max must be a multiple of 4 and >= p0_max");
     if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");
+    if (dm->n_zones < 0 || (dm->n_zones > 0 && (!bf->zone_bits || !bf->zone_sel || dm->n_zone_words < 1)))
+        return fail("dims.n_zones > 0 needs buffers.zone_bits, buffers.zone_sel and dims.n_zone_words");
     if (prm->axm_v[prm->n_axm - 1] < prm->vel_max)  // tph.calc_vel_profile input check
         return fail("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!");
     return 0;
@@ -203,7 +206,9 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
     if (smem_plan > 200 * 1024 || smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
     static thread_local size_t attr_plan = 0, attr_path = 0;
     if (smem_plan > 48 * 1024 && smem_plan > attr_plan) {
-        if (cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
+                cudaSuccess ||
+            cudaFuncSetAttribute(k_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) != cudaSuccess)
             return fail("cudaFuncSetAttribute(k_plan) failed");
         attr_plan = smem_plan;
     }
@@ -214,7 +219,10 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
     }
     if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
     const int grid_plan = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    k_plan<<<grid_plan, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    if (dm->n_zones > 0)
+        k_plan<true><<<grid_plan, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    else
+        k_plan<false><<<grid_plan, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
     if (int r = check_launch("k_plan")) return r;
     const int nq = LTPL_NSLOT * dm->batch;
     const int grid_path = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
@@ -230,7 +238,16 @@ static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplD
     if (int r = check_launch("k_vel")) return r;
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
         *dm, *bf);
-    return check_launch("k_export");
+    if (int r = check_launch("k_export")) return r;
+    if (prm->incl_emerg_traj) {
+        if (!bf->em_info) return fail("params.incl_emerg_traj needs buffers.em_info");
+        const size_t smem = emerg_smem_bytes_per_warp(dm->n_export) * LTPL_WARPS_PER_CTA;
+        if (smem > 48 * 1024) return fail("n_export too large for k_emergency");
+        k_emergency<<<(dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem, st>>>(
+            *prm, *dm, *bf);
+        return check_launch("k_emergency");
+    }
+    return 0;
 }
 
 int ltpl_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
@@ -266,10 +283,17 @@ int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, 
             const size_t smem_plan = plan_smem_bytes_per_warp(maxn, dm->h_max, mask_words) * LTPL_WARPS_PER_CTA;
             const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
             if (stage == 1) {
-                if (smem_plan > 48 * 1024)
-                    cudaFuncSetAttribute(k_plan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
-                k_plan<<<(dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem_plan,
-                         st>>>(lat->d, *prm, *dm, *bf, maxn, dm->h_max, mask_words);
+                if (smem_plan > 48 * 1024) {
+                    cudaFuncSetAttribute(k_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
+                    cudaFuncSetAttribute(k_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
+                }
+                const int grid = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+                if (dm->n_zones > 0)
+                    k_plan<true><<<grid, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn,
+                                                                                   dm->h_max, mask_words);
+                else
+                    k_plan<false><<<grid, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn,
+                                                                                    dm->h_max, mask_words);
                 return check_launch("k_plan");
             }
             if (smem_path > 48 * 1024)

@@ -191,14 +191,23 @@ __device__ __forceinline__ void dp_fill_meta(const LatDev& lt, int lane, int4* m
     __syncwarp();
 }
 
+// blocked zones, first tick (GLNT:43-99): a new zone that overlaps the next UNBLOCK_N_LAYERS_WHEN_IN_ZONE = 4 layers from
+// the start layer is unblocked on those layers (GLNT:58-77; the wrap branch keeps the reference's arithmetic, quirk q6)
+__device__ __forceinline__ bool zone_unblocked(int l, int s0, int L) {
+    const int n = 4;
+    if (s0 + n <= L) return l >= s0 && l < s0 + n;
+    return (l >= s0 && l < L) || (l >= 0 && l < ((s0 + n) % (L - 1) - 1));
+}
+
 // Runs the layer transitions li_begin .. n_steps; returns the number of completed steps (last layer with a reachable
 // node).  li_begin == 1 starts at start_node; li_begin > 1 resumes from the snapshot in c.dsave (the pred rows below
 // li_begin are those of the run that took the snapshot).  After step snap_at the state is saved to c.dsave.
 // Each lane owns one node of the next layer and scans its in-edges IN CSC ORDER, which keeps igraph's relaxation order
 // and tie rule (strict <, then smaller dist[src]) bit for bit.
+template <bool ZONE>
 __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int start_layer, int start_node, int n_steps,
                                       const unsigned* mask, int e_base, int rem_layer, int rem_lo, int rem_hi,
-                                      int li_begin, int snap_at) {
+                                      int li_begin, int snap_at, const unsigned* zone) {
     const int maxn = c.maxn;
     int tie = 0;
     if (li_begin == 1) {
@@ -220,6 +229,8 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
         const int4 mt = c.meta[li];
         const int nbase = mt.x, nl = mt.y;
         const int moff = (mt.z >= e_base) ? -e_base : lt.E - e_base;  // edge id -> bit of the window mask
+        // 'overtaking_zones' is the base of every other filter (GLNT:96-99, 144-147): zone nodes are absent everywhere
+        const unsigned* zs = (ZONE && zone && !zone_unblocked(nxt, start_layer, lt.L)) ? zone : nullptr;
         const double* dcur = c.dist + cur * maxn;
         double* dnxt = c.dist + (cur ^ 1) * maxn;
         int any = 0;
@@ -227,7 +238,9 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
         for (int j = lane; j < maxn; j += 32) {
             double best = LTPL_INF, best_ds = LTPL_INF;
             int best_k = 255;
-            if (j < nl && !(nxt == rem_layer && j >= rem_lo && j < rem_hi)) {
+            bool present = j < nl && !(nxt == rem_layer && j >= rem_lo && j < rem_hi);
+            if (ZONE && present && zs) present = !((zs[(nbase + j) >> 5] >> ((nbase + j) & 31)) & 1u);
+            if (present) {
                 const int2 io = lt.in_off[nbase + j];
                 #pragma unroll 1
                 for (int k = 0; k < io.y; ++k) {
@@ -399,6 +412,7 @@ __device__ __forceinline__ int disc_pairs(const LatDev& lt, int lane, double ox,
 #ifndef LTPL_PLAN_MINB
 #define LTPL_PLAN_MINB 10  // resident CTAs per SM the register allocation is held to (occupancy hides the L1/L2 latency)
 #endif
+template <bool ZONE>
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32, LTPL_PLAN_MINB)
 k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf, const int maxn, const int hl,
        const int mask_words) {
@@ -616,6 +630,11 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     //  * two consecutive actions with the same filter ('left' and 'right' on 'default') are the same search;
     //  * 'overtake_left' and 'overtake_right' differ only from the object's layer onwards -> the second one resumes
     //    from a snapshot of the first one's state one layer before it.
+    const unsigned* zone = nullptr;   // k_plan<false> is launched when the batch carries no zones (dims.n_zones == 0)
+    if (ZONE) {
+        const int zsel = bf.zone_sel[b];
+        if (zsel >= 0 && zsel < dm.n_zones) zone = bf.zone_bits + (size_t)zsel * dm.n_zone_words;
+    }
     unsigned mask_any = 0;
     #pragma unroll 1
     for (int i = lane; i < mask_words; i += 32) mask_any |= mask[i];
@@ -651,6 +670,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         int src = (f == 0 || (f == 1 && !mask_any)) ? 0 : ((f == 1 && prev_f == 1) ? 2 : 1);
         const int tr = lt.tab_reach[tab_row];
         if (src == 0 && (tr & 0xff) > mod_steps) src = 1;  // table rows end at their own goal layer (open track only)
+        if (ZONE && src == 0 && zone) src = 1;              // the table holds searches on the zone-free lattice
         int st = 0, tie = 0, found = 0, reach = 0;
         if (mod_steps > 0) {
             const bool start_removed = (rem_layer == start_layer && start_node >= rem_lo && start_node < rem_hi);
@@ -664,8 +684,8 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             } else {
                 const int li_begin = (f == 3 && c.snap_li >= 1) ? c.snap_li + 1 : 1;
                 const int snap_at = (f == 2 && a + 1 < n_act && filt[a + 1] == 3) ? closest_dist - 1 : 0;
-                reach = dp_run(lt, lane, c, start_layer, start_node, mod_steps, mask, e_base, rem_layer, rem_lo, rem_hi,
-                               li_begin, snap_at);
+                reach = dp_run<ZONE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
+                               rem_layer, rem_lo, rem_hi, li_begin, snap_at, zone);
                 tie = c.tie;
             }
             LTPL_PH(21)
@@ -807,7 +827,7 @@ k_follow_table(const LatDev lt, const int maxn, int* tab_reach, unsigned char* t
     c.maxn = maxn;
     c.snap_li = 0;
     c.tie_save = 0;
-    const int reach = dp_run(lt, lane, c, start_layer, start_node, planning_dist, nullptr, 0, -1, 0, 0, 1, 0);
+    const int reach = dp_run<false>(lt, lane, c, start_layer, start_node, planning_dist, nullptr, 0, -1, 0, 0, 1, 0, nullptr);
     int tie = c.tie;
     int gj = 0;
     if (reach >= 1) gj = dp_goal(lt, lane, c, &tie);

@@ -84,6 +84,11 @@ class BatchPlanner(object):
         capi.check(self.lib, self.lib.ltpl_lattice_create(C.byref(self.header), C.c_void_p(self.blob.data_ptr()),
                                                           C.byref(handle)), "ltpl_lattice_create")
         self.handle = handle
+        # node offsets per layer (zone bitmasks address nodes as node_off[layer] + node), read back from the blob
+        off = int(self.header.off_node_off)
+        self.node_off = self.blob[off: off + 4 * (int(self.header.num_layers) + 1)].cpu().numpy().view(np.int32) \
+            .astype(np.int64)
+        self.lattice_nodes = int(self.header.num_nodes)
         self.dims = None
         self.buf = None
         self.t = {}
@@ -101,7 +106,8 @@ class BatchPlanner(object):
 
     # -- parameters ------------------------------------------------------------------------------------------------------
     def set_vel_params(self, vel_max: float = 100.0, gg_scale: float = 1.0, local_gg=(5.0, 5.0),
-                       ax_max_machines=np.atleast_2d([100.0, 5.0]), safety_d: float = 30.0) -> None:
+                       ax_max_machines=np.atleast_2d([100.0, 5.0]), safety_d: float = 30.0,
+                       incl_emerg_traj: bool = False) -> None:
         """per-call arguments of Graph_LTPL.calc_vel_profile (LTPL:344-352)."""
         if type(local_gg) is not tuple or len(local_gg) != 2:   # OTH:651-653 (location dependent dicts: not batched)
             raise ValueError("Provided local_gg does not satisfy requested format! Read parameter documentation.")
@@ -126,6 +132,7 @@ class BatchPlanner(object):
         p.dyn_model_exp, p.drag_coeff, p.m_veh = self.veh["dyn_model_exp"], self.veh["drag_coeff"], self.veh["m_veh"]
         p.vel_max, p.gg_scale, p.gg_ax, p.gg_ay, p.safety_d = vel_max, gg_scale, local_gg[0], local_gg[1], safety_d
         p.n_axm = axm.shape[0]
+        p.incl_emerg_traj = 1 if incl_emerg_traj else 0
         for i in range(axm.shape[0]):
             p.axm_v[i] = axm[i, 0]
             p.axm_a[i] = axm[i, 1]
@@ -161,10 +168,10 @@ class BatchPlanner(object):
             return raw, views
 
         in_spec = [("pos", (B, 2), f64), ("heading", (B,), f64), ("vel", (B,), f64), ("vel_est", (B,), f64),
-                   ("n_obj", (B,), i32), ("obj", (B, K, 5), f64)]
+                   ("n_obj", (B,), i32), ("obj", (B, K, 5), f64), ("zone_sel", (B,), i32)]
         meta_spec = [("exp_q", (NSLOT * B,), i32), ("traj_row", (NSLOT, B), i32), ("traj_len", (NSLOT, B), i32),
                      ("traj_id", (NSLOT, B), i32), ("action_id", (NSLOT, B), i32), ("status", (NSLOT, B), i32),
-                     ("sc_flags", (B,), i32), ("queue_cnt", (4,), i32)]
+                     ("sc_flags", (B,), i32), ("queue_cnt", (4,), i32), ("em_info", (B, 3), i32)]
         self.d_in_raw, t_in = packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
         self.d_meta_raw, t_meta = packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
         t = dict(
@@ -176,15 +183,17 @@ class BatchPlanner(object):
             path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), queue=z((2, NSLOT * B), i32),
             vel_scratch=z((3, NSLOT * B, P), f64),
             s_vx_ax=z((3, NSLOT * B, P), f64), vel_t=z((5, P, NSLOT * B + 64), f64),
-            traj=z((NSLOT * B, NE, 7), f32))
+            traj=z(((NSLOT + 1) * B, NE, 7), f32))
         t.update(t_in)
         t.update(t_meta)
         buf = capi.Buffers()
+        t["zone_bits"] = torch.zeros((1, 1), dtype=torch.int32, device=dev)   # replaced by _upload_zones()
+        d.n_zones, d.n_zone_words = 0, (self.lattice_nodes + 31) // 32
         for name in capi.BUFFER_FIELDS:
             setattr(buf, name, t[name].data_ptr())
         self.t, self.buf, self.dims = t, buf, d
         # further compact export buffers: the pipelined stream planner lets the D2H of step i overlap step i + 1
-        self.traj_bufs = [t["traj"]] + [z((NSLOT * B, NE, 7), f32) for _ in range(self.N_SETS - 1)]
+        self.traj_bufs = [t["traj"]] + [z(((NSLOT + 1) * B, NE, 7), f32) for _ in range(self.N_SETS - 1)]
         # pinned host staging for the per-tick host <-> device copies (N_SETS sets for the pipelined path)
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()   # noqa: E731
         self.h_in_raw, self.h_in_sets, self.h_meta_raw, self.h_out_sets = [], [], [], []
@@ -193,7 +202,7 @@ class BatchPlanner(object):
             self.h_in_raw.append(raw)
             self.h_in_sets.append(views)
             raw, views = packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
-            views["traj"] = pin((NSLOT * B, NE, 7), f32)
+            views["traj"] = pin(((NSLOT + 1) * B, NE, 7), f32)
             self.h_meta_raw.append(raw)
             self.h_out_sets.append(views)
         self.h_in, self.h_out = self.h_in_sets[0], self.h_out_sets[0]
@@ -231,6 +240,26 @@ class BatchPlanner(object):
         if k < h["obj"].shape[1]:
             h["obj"].numpy()[:, k:, :] = 0.0
         h["obj"].numpy()[:, :k, :] = sc.obj
+        h["zone_sel"].numpy()[...] = -1 if sc.zone_sel is None else sc.zone_sel
+        self._upload_zones(sc.zones)
+
+    def _upload_zones(self, zones) -> None:
+        """zone bitmasks: bit (node_off[layer] + node) of mask z = that node is blocked by zone z (GLNT:46, 96-99)."""
+        if not zones:
+            self.dims.n_zones = 0
+            return
+        w = int(self.dims.n_zone_words)
+        bits = np.zeros((len(zones), w), dtype=np.uint32)
+        for z, (lay, nod) in enumerate(zones):
+            if lay.size and (lay.min() < 0 or lay.max() >= self.node_off.size - 1):
+                raise ValueError("zone layer id outside the lattice")
+            g = self.node_off[lay] + nod
+            if lay.size and (np.any(nod < 0) or np.any(g >= self.node_off[lay + 1])):
+                raise ValueError("zone node id outside its layer")
+            np.bitwise_or.at(bits[z], g >> 5, (np.uint32(1) << (g & 31).astype(np.uint32)))
+        self.t["zone_bits"] = torch.from_numpy(bits.view(np.int32)).to(self.device)
+        self.buf.zone_bits = self.t["zone_bits"].data_ptr()
+        self.dims.n_zones = len(zones)
 
     def upload(self, which: int = 0) -> None:
         self.d_in_raw.copy_(self.h_in_raw[which], non_blocking=True)      # one packed H2D copy
@@ -345,7 +374,7 @@ class BatchPlanner(object):
         single-scenario facade.  Copies every result buffer to the host."""
         f = self.fetch("sc_flags", "start_node", "action_id", "status", "n_nodes", "nodes", "node_idx", "closest_obj",
                        "path_len", "path", "coeff", "s_vx_ax", "traj", "traj_row", "traj_len", "traj_id", "const_seg",
-                       "const_len")
+                       "const_len", "em_info")
         B = self.dims.batch
         out = []
         for b in (range(B) if indices is None else indices):
@@ -387,5 +416,9 @@ class BatchPlanner(object):
                     tl = int(f["traj_len"][s, b])
                     rec["traj"][name] = [f["traj"][int(f["traj_row"][s, b]), :tl].astype(np.float64)]
                     rec["ids"][name] = int(f["traj_id"][s, b])
+            if self.params.incl_emerg_traj and rec["traj"] and int(f["em_info"][b, 0]) >= 0:   # OTH:1027-1034
+                row, n_em, em_id = (int(v) for v in f["em_info"][b])
+                rec["traj"]["emergency"] = [f["traj"][row, :n_em].astype(np.float64)]
+                rec["ids"]["emergency"] = em_id
             out.append(rec)
         return out

@@ -29,6 +29,10 @@ class ScenarioBatch:
     vel: np.ndarray        # (B,)   float64
     n_obj: np.ndarray      # (B,)   int32
     obj: np.ndarray        # (B, K, 5) float64
+    # blocked zones (calc_paths(blocked_zones=...), LTPL:311-312, 'nodes' type): distinct zones as (layer ids, node ids)
+    # pairs and, per scenario, the index of its zone or -1.  None: no zones in this batch.
+    zones: list = None
+    zone_sel: np.ndarray = None   # (B,) int32
 
     @property
     def size(self) -> int:
@@ -46,14 +50,37 @@ class ScenarioBatch:
     def subset(self, idx) -> "ScenarioBatch":
         idx = np.asarray(idx)
         return ScenarioBatch(self.pos[idx].copy(), self.heading[idx].copy(), self.vel[idx].copy(),
-                             self.n_obj[idx].copy(), self.obj[idx].copy())
+                             self.n_obj[idx].copy(), self.obj[idx].copy(), self.zones,
+                             None if self.zone_sel is None else self.zone_sel[idx].copy())
+
+    def set_zones(self, blocked_zones) -> None:
+        """blocked_zones: one entry per scenario, each None or a dict {zone id: [layer ids, node ids, left bound, right
+        bound]} exactly as Graph_LTPL.calc_paths takes it (LTPL:311-312).  A scenario may carry ONE zone: with several
+        keys the reference's update_zone (OLI:155-237, called once per key at LTPL:326-329) flags all but the last as
+        removed and GLNT:69-83 then fails on them."""
+        zones, index, sel = [], {}, np.full(self.size, -1, dtype=np.int32)
+        for i, bz in enumerate(blocked_zones):
+            if not bz:
+                continue
+            if len(bz) != 1:
+                raise NotImplementedError("more than one blocked zone per scenario is not a defined input of the reference")
+            zid, z = next(iter(bz.items()))
+            lay, nod = np.asarray(z[0], dtype=np.int64), np.asarray(z[1], dtype=np.int64)
+            if lay.shape != nod.shape or lay.ndim != 1:
+                raise ValueError("zone '%s': layer ids and node ids must be two lists of equal length" % zid)
+            key = (lay.tobytes(), nod.tobytes())
+            if key not in index:
+                index[key] = len(zones)
+                zones.append((lay, nod))
+            sel[i] = index[key]
+        self.zones, self.zone_sel = (zones, sel) if zones else (None, None)
 
     def shard(self, rank: int, world: int) -> "ScenarioBatch":
         """scenario i goes to rank i % world."""
         return self.subset(np.arange(rank, self.size, world))
 
     @staticmethod
-    def from_object_lists(pos, heading, vel, object_lists, k_max=None) -> "ScenarioBatch":
+    def from_object_lists(pos, heading, vel, object_lists, k_max=None, blocked_zones=None) -> "ScenarioBatch":
         b = len(object_lists)
         n_obj = np.array([len(o) if o is not None else 0 for o in object_lists], dtype=np.int32)
         k = int(max(1, n_obj.max() if b else 1)) if k_max is None else int(k_max)
@@ -64,9 +91,12 @@ class ScenarioBatch:
                     raise NotImplementedError("batched scenarios use the reference's built-in 0.2 s constant-velocity "
                                               "prediction (OLI:121-127); explicit 'prediction' arrays are not batched")
                 obj[i, j] = [o['X'], o['Y'], o['theta'], o['v'], o['length']]
-        return ScenarioBatch(np.asarray(pos, dtype=np.float64).reshape(b, 2),
-                             np.asarray(heading, dtype=np.float64).reshape(b),
-                             np.asarray(vel, dtype=np.float64).reshape(b), n_obj, obj)
+        sc = ScenarioBatch(np.asarray(pos, dtype=np.float64).reshape(b, 2),
+                           np.asarray(heading, dtype=np.float64).reshape(b),
+                           np.asarray(vel, dtype=np.float64).reshape(b), n_obj, obj)
+        if blocked_zones is not None:
+            sc.set_zones(blocked_zones)
+        return sc
 
 
 class Track(object):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 4
+#define LTPL_ABI_VERSION 5
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -134,6 +134,9 @@ typedef struct LtplParams {
     double vel_max, gg_scale, gg_ax, gg_ay, safety_d;
     int32_t n_axm;               /* rows of ax_max_machines (<= LTPL_MAX_AXM)         */
     int32_t traj_base_id;        /* OTH:669 (+10 per calc_vel_profile call)           */
+    int32_t incl_emerg_traj;     /* calc_vel_profile(incl_emerg_traj=True): append the brake-to-stop profile on the   */
+                                 /* first kept trajectory of every scenario (OTH:1027-1034, calc_brake_emergency.py)   */
+    int32_t pad0;
     double axm_v[LTPL_MAX_AXM];
     double axm_a[LTPL_MAX_AXM];
     double axm_s[LTPL_MAX_AXM];  /* slopes (a[i+1] - a[i]) / (v[i+1] - v[i]) exactly as np.interp forms them  */
@@ -147,7 +150,8 @@ typedef struct LtplDims {
     int32_t p_max;     /* points of a full path (constant segment + new plan), % 4 == 0 */
     int32_t h_max;     /* nodes of a node sequence incl. the leading [None, None] entry */
     int32_t n_export;  /* rows of an exported trajectory (nmbr_export_points)          */
-    int32_t pad0, pad1;
+    int32_t n_zone_words; /* 32-bit words of one zone bitmask = ceil(num_nodes / 32)   */
+    int32_t n_zones;      /* zone bitmasks in LtplBuffers.zone_bits (0: no zones)      */
 } LtplDims;
 
 /* Caller-owned device buffers.  q = slot * B + b indexes a path ("action major").                                      */
@@ -191,6 +195,13 @@ typedef struct LtplBuffers {
                               /* the first queue_cnt[2] rows are filled (one per kept trajectory, row -> path via exp_q)   */
     int32_t* traj_len;        /* [NSLOT][B]                                                                              */
     int32_t* traj_id;         /* [NSLOT][B] traj_base_id + action id (OTH:696-697)                                       */
+    /* blocked zones (calc_paths(blocked_zones=...), LTPL:324-329; 'nodes' type, GLNT:43-99): bit (node_off[l] + n) of    */
+    /* a mask = node n of layer l is blocked.  A scenario selects one mask or none; may be NULL when n_zones == 0.        */
+    const uint32_t* zone_bits; /* [n_zones][n_zone_words]                                                                */
+    const int32_t* zone_sel;  /* [B] index into zone_bits or -1                                                          */
+    /* emergency trajectory (params.incl_emerg_traj): row in `traj` (or -1), rows, id -- key 'emergency' of the           */
+    /* reference's trajectory dict (OTH:1030-1034); `traj` needs (NSLOT + 1) * B rows then                                */
+    int32_t* em_info;         /* [B][3]                                                                                  */
 } LtplBuffers;
 
 /* stand-alone forward/backward ggv velocity profile over dense path arrays (BASELINE.json config 5).                   */

@@ -38,7 +38,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
         pl.set_vel_params(vel_max=60.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=bench.ax_max_machines(), safety_d=30.0)
         vp = lambda: velprofile_batch_device(pl, d["kappa"], d["el"], d["v_start"], d["v_end"], vx, ax)
         vp(); res["velprofile_ms"] = timed(vp, 5)
-    print(json.dumps(res))
+    bench.emit(res)
     sys.exit(0)
 from graphbasedlocaltrajectoryplanner_b200 import capi
 tag = sys.argv[1]
