@@ -55,15 +55,25 @@ def broadcast_lattice(lattice, device, src: int = 0) -> tuple:
     return header, cap, blob_t
 
 
-def gather_action_sets(traj: torch.Tensor, traj_len: torch.Tensor, traj_id: torch.Tensor) -> tuple:
-    """all-gather the fixed-stride exported trajectories ([NSLOT][B_local][n_export][7] fp32 + lengths + ids).
-    Every rank must hold the same local batch size.  Returns tensors with a leading world dimension."""
+def gather_action_sets(traj: torch.Tensor, traj_len: torch.Tensor, traj_id: torch.Tensor, out: list = None) -> tuple:
+    """all-gather the fixed-stride exported trajectories ([rows][n_export][7] fp32 + lengths + ids) on the current
+    stream.  Every rank must hold the same local sizes.  Returns tensors with a leading world dimension; ``out`` (a list,
+    filled on first use) keeps the receive buffers across calls."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return traj.unsqueeze(0), traj_len.unsqueeze(0), traj_id.unsqueeze(0)
     world = dist.get_world_size()
     outs = []
-    for t in (traj, traj_len, traj_id):
-        out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(out, t.contiguous())   # concatenated along dim 0 (valid for nccl and gloo)
-        outs.append(out.view((world,) + tuple(t.shape)))
+    for i, t in enumerate((traj, traj_len, traj_id)):
+        shape = (world * t.shape[0],) + tuple(t.shape[1:])
+        if out is not None and len(out) > i and tuple(out[i].shape) == shape and out[i].dtype == t.dtype:
+            buf = out[i]
+        else:
+            buf = torch.empty(shape, dtype=t.dtype, device=t.device)
+            if out is not None:
+                if len(out) > i:
+                    out[i] = buf
+                else:
+                    out.append(buf)
+        dist.all_gather_into_tensor(buf, t.contiguous())   # concatenated along dim 0 (valid for nccl and gloo)
+        outs.append(buf.view((world,) + tuple(t.shape)))
     return tuple(outs)

@@ -319,6 +319,8 @@ class BatchPlanner(object):
                 j = inflight.pop(0)
                 ev_d2h[j].synchronize()
                 yield self.h_out_sets[j]
+            if device_hook is not None and hasattr(device_hook, "before"):
+                device_hook.before(k)   # e.g. wait until a collective that still reads buffer set k has finished
             self.stage_scenarios(sc, vel_est=vel_est, which=k)
             self.buf.traj = self.traj_bufs[k].data_ptr()
             self.upload(which=k)
