@@ -61,16 +61,22 @@ def write_offline_ini(path, overrides):
         cfg.write(fh)
 
 
-def make_ltpl(graph_ltpl, tag, overrides=None):
+def make_ltpl(graph_ltpl, tag, overrides=None, controller_type=None, veh=None):
     ini = '/tmp/golden_offline_%s.ini' % tag
     write_offline_ini(ini, overrides)
+    online = REF + "/params/ltpl_config_online.ini"
+    if controller_type is not None:                       # same file, other follow-mode controller (ini line 35)
+        txt = open(online).read()
+        assert txt.count("controller_type=PD\n") == 1
+        online = '/tmp/golden_online_%s_%s.ini' % (tag, controller_type)
+        open(online, 'w').write(txt.replace("controller_type=PD\n", "controller_type=%s\n" % controller_type))
     path_dict = {'globtraj_input_path': REF + "/inputs/traj_ltpl_cl/traj_ltpl_cl_monteblanco.csv",
                  'graph_store_path': "/tmp/golden_graph_%s.pckl" % tag,
                  'ltpl_offline_param_path': ini,
-                 'ltpl_online_param_path': REF + "/params/ltpl_config_online.ini"}
+                 'ltpl_online_param_path': online}
     ltpl = graph_ltpl.Graph_LTPL.Graph_LTPL(path_dict=path_dict, visual_mode=False, log_to_file=False)
     t0 = time.time()
-    ltpl.graph_init()
+    ltpl.graph_init(**(veh or {}))
     print("[%s] reference graph_init: %.1f s" % (tag, time.time() - t0))
     return ltpl, path_dict
 
@@ -80,7 +86,7 @@ def ax_max_machines_table():
     return np.vstack((tab, [100.0, tab[-1, 1]]))
 
 
-def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False, blocked_zones=None):
+def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False, blocked_zones=None, vel_est=None):
     """one stateless planning tick through the reference's public API (main_min_example.py:69-104 flow)."""
     name = '_Graph_LTPL__nmbr_export_points'
     keep = getattr(ltpl, name)
@@ -106,7 +112,8 @@ def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False, block
         rec['red_len'] = {k: list(v) for k, v in oth._OnlineTrajectoryHandler__last_action_set_red_len.items()}
         rec['closest_obj_index'] = oth._OnlineTrajectoryHandler__closest_obj_index
         rec['start_node'] = list(oth._OnlineTrajectoryHandler__start_node)
-        traj, ids, _ = ltpl.calc_vel_profile(pos_est=np.array(pos), vel_est=float(vel), **vel_kwargs)
+        traj, ids, _ = ltpl.calc_vel_profile(pos_est=np.array(pos), vel_est=float(vel if vel_est is None else vel_est),
+                                             **vel_kwargs)
         rec['traj'] = {k: [np.array(a) for a in v] for k, v in traj.items()}
         rec['ids'] = dict(ids)
         return rec
@@ -219,6 +226,38 @@ def ext_fixture(ltpl, lat, track, n, vel_kwargs):
     return pk
 
 
+VARIANTS = (
+    # follow-mode controller with tan activation (CVPF:65-71), friction-ellipse exponent != 1 (tph.calc_ax_poss), other
+    # vehicle mass / drag (LTPL:189-192), reduced gg scale, asymmetric gg, lower v_max, ego estimate != planned velocity
+    dict(name="pdtan_exp15", controller_type="PDtan", veh=dict(veh_param_dyn_model_exp=1.5, veh_param_dragcoeff=0.9,
+                                                               veh_param_mass=1200.0),
+         vel=dict(vel_max=85.0, gg_scale=0.9, local_gg=(4.5, 5.5), safety_d=20.0), vel_est_offset=-2.0),
+    dict(name="pd_exp20", controller_type=None, veh=dict(veh_param_dyn_model_exp=2.0, veh_param_dragcoeff=0.7,
+                                                         veh_param_mass=900.0),
+         vel=dict(vel_max=90.0, gg_scale=1.0, local_gg=(6.0, 4.0), safety_d=40.0), vel_est_offset=3.0),
+)
+
+
+def variants_fixture(graph_ltpl, track, n):
+    """parameter variants of the velocity planner / follow controller, default lattice, first ticks."""
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import make_scenarios
+    out = {}
+    for vi, var in enumerate(VARIANTS):
+        ltpl, _ = make_ltpl(graph_ltpl, "default", {}, controller_type=var["controller_type"], veh=var["veh"])
+        sc = make_scenarios(track, n, seed=9000 + vi, n_obj_min=1, n_obj_max=3)
+        vk = dict(var["vel"], ax_max_machines=ax_max_machines_table(), incl_emerg_traj=False)
+        recs = [run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], sc.object_list(b), vk, full=True,
+                         vel_est=sc.vel[b] + var["vel_est_offset"]) for b in range(sc.size)]
+        pk = pack_ticks(recs)
+        pk.update(sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj, sc_obj=sc.obj)
+        for k, v in pk.items():
+            out["%s__%s" % (var["name"], k)] = v
+        acts = {a: int((pk['traj_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)}
+        print("[variant %s] trajectories %s" % (var["name"], acts))
+    out["ax_max_machines"] = ax_max_machines_table()
+    return out
+
+
 def lattice_fixture(graph_ltpl, ltpl, n_edge_samples=300, seed=7):
     """compact description of the reference-built GraphBase (validates the product's lattice builder)."""
     from graphbasedlocaltrajectoryplanner_b200.lattice import Lattice
@@ -249,6 +288,8 @@ def main():
     ap.add_argument('--n-other', type=int, default=32)
     ap.add_argument('--ext-only', action='store_true', help='only the zone / emergency fixture (default lattice)')
     ap.add_argument('--n-ext', type=int, default=64)
+    ap.add_argument('--variants-only', action='store_true', help='only the parameter-variant fixture')
+    ap.add_argument('--n-variant', type=int, default=24)
     args = ap.parse_args()
 
     graph_ltpl = load_reference()
@@ -258,6 +299,10 @@ def main():
     vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
                       safety_d=30.0, incl_emerg_traj=False)
 
+    if args.variants_only:
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_variants_default.npz'),
+                            **variants_fixture(graph_ltpl, track, args.n_variant))
+        return
     configs = [("default", {}, args.n_default, 0, 3)]
     if not args.quick:
         configs.append(("l216", {"lat_resolution": 1.0, "lon_straight_step": 12.0}, args.n_other, 1, 3))
@@ -315,6 +360,9 @@ def main():
                       sc_vel=np.array([0.0, 20.0]), obj=np.array([127.0, 82.0, 0.0, 0.0, 5.0]))
             np.savez_compressed(os.path.join(GOLDEN, 'config1_min_example.npz'), **pk)
             print("[config1] actions:", {a: pk['path_len'][:, i].tolist() for i, a in enumerate(ACTIONS)})
+    if not args.quick:
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_variants_default.npz'),
+                            **variants_fixture(graph_ltpl, track, args.n_variant))
 
 
 if __name__ == "__main__":

@@ -818,7 +818,7 @@ class OracleLTPL(object):
     # ----------------------------------------------------------------------------------------------------------------------
     # one stateless tick = set_startpos -> calc_paths -> calc_vel_profile  (main_min_example.py:69-104)
     # ----------------------------------------------------------------------------------------------------------------------
-    def tick(self, pos, heading, vel, object_list, vel_kwargs=None, blocked_zones=None):
+    def tick(self, pos, heading, vel, object_list, vel_kwargs=None, blocked_zones=None, vel_est=None):
         vel_kwargs = dict(vel_kwargs or {})
         self.old_gg_scale = None
         st = self.set_startpos(np.asarray(pos, dtype=np.float64), float(heading), float(vel))
@@ -826,7 +826,8 @@ class OracleLTPL(object):
             return dict(out_of_track=True)
         obj_veh = self.process_object_list(object_list)
         res = self.calc_paths(st, obj_veh, blocked_zones)
-        vp = self.calc_vel_profile(st, res, obj_veh, np.asarray(pos, dtype=np.float64), float(vel), **vel_kwargs)
+        vp = self.calc_vel_profile(st, res, obj_veh, np.asarray(pos, dtype=np.float64),
+                                   float(vel if vel_est is None else vel_est), **vel_kwargs)
         return dict(out_of_track=False, start_node=st['start_node'], paths=res['path_param'], nodes=res['nodes'],
                     node_idx=res['node_idx'], coeff=res['coeff'], red_len=res['red_len'], tie=res.get('tie', {}),
                     closest_obj_index=res['closest_obj_index'], const_path_seg=res['const_path_seg'],

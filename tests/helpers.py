@@ -141,3 +141,23 @@ def compare_emergency(rec, g, b, ctx=""):
         assert int(rec["ids"]["emergency"]) % 10 == int(g["em_id"][b]) % 10, "%s scenario %d emergency id" % (ctx, b)
         assert_close("traj[emergency]", rec["traj_full"]["emergency"][0], g["em_traj"][b, :n],
                      ("s", "x", "y", "psi", "kappa", "vx", "ax"), "%s scenario %d" % (ctx, b))
+
+
+VARIANTS = {   # oracle/gen_golden.py VARIANTS: online overrides, vehicle parameters, velocity arguments, vel_est offset
+    "pdtan_exp15": (dict(controller_type="PDtan", control_params={"c_p": 1.15, "k_d": 0.025, "k_p": 0.2, "tan_w": 15.0}),
+                    dict(veh_param_dyn_model_exp=1.5, veh_param_dragcoeff=0.9, veh_param_mass=1200.0),
+                    dict(vel_max=85.0, gg_scale=0.9, local_gg=(4.5, 5.5), safety_d=20.0), -2.0),
+    "pd_exp20": (dict(), dict(veh_param_dyn_model_exp=2.0, veh_param_dragcoeff=0.7, veh_param_mass=900.0),
+                 dict(vel_max=90.0, gg_scale=1.0, local_gg=(6.0, 4.0), safety_d=40.0), 3.0),
+}
+
+
+class _Sub(object):
+    """view of the arrays of one variant inside ticks_variants_default.npz (keys '<variant>__<name>')."""
+
+    def __init__(self, g, name):
+        self.g, self.p = g, name + "__"
+        self.files = [k[len(self.p):] for k in g.files if k.startswith(self.p)]
+
+    def __getitem__(self, k):
+        return self.g[self.p + k]

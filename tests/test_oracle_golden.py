@@ -51,3 +51,20 @@ def test_oracle_zones_and_emergency():
                        blocked_zones=H.zone_of(g, b))
         H.compare_record(rec, g, b, prefix="", ctx="ext")
         H.compare_emergency(rec, g, b, ctx="ext")
+
+
+@pytest.mark.parametrize("name", sorted(H.VARIANTS))
+def test_oracle_parameter_variants(name):
+    """PDtan follow controller, friction-ellipse exponents 1.5 / 2.0, other mass / drag, gg scale, asymmetric gg, ego
+    velocity estimate != planned velocity -- all against the unmodified reference."""
+    from oracle.ltpl_oracle import OracleLTPL
+    g = H.golden("ticks_variants_default.npz")
+    sub = H._Sub(g, name)
+    online, veh, vel, dv = H.VARIANTS[name]
+    orc = OracleLTPL(H.lattice_for("default"), online=online, **veh)
+    vk = dict(vel, ax_max_machines=g["ax_max_machines"])
+    n = sub["sc_pos"].shape[0]
+    for b in range(n):
+        rec = orc.tick(sub["sc_pos"][b], sub["sc_heading"][b], sub["sc_vel"][b], H.object_list(sub, b), vk,
+                       vel_est=sub["sc_vel"][b] + dv)
+        H.compare_record(rec, sub, b, prefix="", ctx=name)
