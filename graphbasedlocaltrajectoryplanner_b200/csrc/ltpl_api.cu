@@ -19,16 +19,32 @@
 #include "ltpl_plan.cuh"
 #include "ltpl_vel.cuh"
 #include "ltpl_vel_tiled.cuh"
+#include "ltpl_vel_split.cuh"
 #include "ltpl_emerg.cuh"
 
 #ifndef LTPL_VEL_TILED
 #define LTPL_VEL_TILED 1   // 1: tile-streamed velocity kernel (ltpl_vel_tiled.cuh), 0: thread-per-path k_vel
 #endif
+#ifndef LTPL_VEL_SPLIT
+// 1: k_vel_sweeps + k_vel_out (ltpl_vel_split.cuh: the independent recurrences of a follow path in concurrent CTAs),
+// 0: the single k_vel_tiled kernel.  Measured on B200 (10 k scenarios): the split shortens the chain per warp from ~3 n to
+// ~2 n steps but doubles the resident warps and adds ~25 % instructions (second prologue, kappa / el tiles loaded twice):
+// 0.35 ms against 0.28 ms -- the stage is bound by issue slots as much as by latency, so the single kernel stays default.
+#define LTPL_VEL_SPLIT 0
+#endif
+
+static std::atomic<unsigned long long> g_launches{0};
 
 static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                                 cudaStream_t st) {
     const int nq = LTPL_NSLOT * dm->batch;
-#if LTPL_VEL_TILED
+#if LTPL_VEL_TILED && LTPL_VEL_SPLIT
+    // follow groups get three CTAs each (<= B follow paths: slot 0 only), every other group one
+    const int g_follow = dm->batch / VT_P + 1, g_all = nq / VT_P + 2;
+    k_vel_sweeps<<<3 * g_follow + g_all, 32, VS_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    k_vel_out<<<g_all, 32, VO_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
+#elif LTPL_VEL_TILED
     static thread_local bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_vel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
@@ -43,7 +59,6 @@ static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, c
 }
 
 static thread_local std::string g_err;
-static std::atomic<unsigned long long> g_launches{0};
 
 static int fail(const char* what) {
     g_err = what;
