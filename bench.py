@@ -458,7 +458,7 @@ def main():
                 "kept_trajectories_per_step": rows_per_step,
                 "api": "Graph_LTPL.plan_stream: per step host staging + H2D + set_startpos + calc_paths + "
                        "calc_vel_profile + D2H of the compact action sets; D2H of step i overlaps the kernels of step "
-                       "i+1 (2 streams)" + ("; + all_gather of action sets" if world > 1 else "")},
+                       "i+1 (copy stream, 3 buffer sets)" + ("; + all_gather of the action sets on a communication stream" if world > 1 else "")},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
     if cpu is not None:
         result["cpu_baseline"] = cpu
@@ -480,6 +480,20 @@ def main():
             del pl_d
         except Exception as e:   # noqa: BLE001
             extra["default_lattice_error"] = str(e)[:200]
+        try:   # 430 layers x 13-25 nodes (lon steps 6 m, lat_resolution 0.5), 5 objects each
+            pl_4 = BatchPlanner(get_lattice("l430"), online=read_online_config(ONLINE_INI), device=device)
+            pl_4.set_vel_params(**vel_kwargs())
+            pl_4.stage_scenarios(make_batch("l430", args.batch))
+            pl_4.upload()
+            pl_4.set_startpos()
+            for _ in range(args.warmup):
+                pl_4.tick()
+            t4 = timed_loop(pl_4.tick, args.steps)
+            extra["config4_l430_ticks_per_s"] = args.batch * args.steps / t4
+            extra["config4_l430_ms_per_step"] = 1e3 * t4 / args.steps
+            del pl_4
+        except Exception as e:   # noqa: BLE001
+            extra["config4_l430_error"] = str(e)[:200]
         try:   # 100 k paths x 500 points forward/backward solver
             from graphbasedlocaltrajectoryplanner_b200.scenarios import make_velocity_microbench
             from graphbasedlocaltrajectoryplanner_b200.velprofile import velprofile_batch_device
