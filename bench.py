@@ -417,6 +417,12 @@ def main():
         stop_evt.set()
         th.join(timeout=3)
 
+    # third timing of SURVEY 8(d): the optional per-scenario Python view of one result (reference-style dicts)
+    t0 = time.perf_counter()
+    unpacked = Graph_LTPL.unpack_batch(out)
+    t_unpack = time.perf_counter() - t0
+    assert len(unpacked) == args.batch
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -456,6 +462,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "ticks/s", "h2d_bytes_per_step": pl.h2d_bytes(),
                 "d2h_bytes_per_step": pl.d2h_bytes(int(rows_per_step)), "ms_per_step": 1e3 * t_e2e / args.steps,
                 "kept_trajectories_per_step": rows_per_step,
+                "facade_unpack_ms_per_batch": 1e3 * t_unpack,
                 "api": "Graph_LTPL.plan_stream: per step host staging + H2D + set_startpos + calc_paths + "
                        "calc_vel_profile + D2H of the compact action sets; D2H of step i overlaps the kernels of step "
                        "i+1 (copy stream, 3 buffer sets)" + ("; + all_gather of the action sets on a communication stream" if world > 1 else "")},

@@ -202,6 +202,30 @@ class Graph_LTPL(object):
             torch.cuda.current_stream(pl.device).synchronize()
         return out
 
+    @staticmethod
+    def unpack_batch(out: dict) -> list:
+        """per-scenario view of a plan_batch / plan_stream result in the reference's return structure of
+        calc_vel_profile (LTPL:344-408): a list of ({action: [ndarray(rows, 7)]}, {action: id}) -- the arrays are views of
+        the pinned host buffer (fp32), nothing is copied."""
+        names = capi.ACTION_NAMES
+        rows, lens, ids, acts = (out[k].numpy() for k in ("traj_row", "traj_len", "traj_id", "action_id"))
+        traj = out["traj"].numpy()
+        em = out["em_info"].numpy() if out.get("incl_emerg_traj") else None
+        res = []
+        for b in range(rows.shape[1]):
+            t, i = {}, {}
+            for s in range(rows.shape[0]):
+                r = rows[s, b]
+                if r >= 0:
+                    name = names[int(acts[s, b])]
+                    t[name] = [traj[r, :lens[s, b]]]
+                    i[name] = int(ids[s, b])
+            if em is not None and t and em[b, 0] >= 0:
+                t["emergency"] = [traj[em[b, 0], :em[b, 1]]]
+                i["emergency"] = int(em[b, 2])
+            res.append((t, i))
+        return res
+
     def plan_stream(self, batches, vel_est=None, device_hook=None):
         """Pipelined variant of ``plan_batch`` over an iterable of ScenarioBatch objects: yields one result dict per
         batch, in order; the device-to-host copy of step i overlaps the kernels of step i + 1

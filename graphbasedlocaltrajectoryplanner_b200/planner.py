@@ -277,6 +277,7 @@ class BatchPlanner(object):
         if n:
             out["traj"][:n].copy_(self.t["traj"][:n], non_blocking=True)
         out["n_rows"] = n
+        out["incl_emerg_traj"] = bool(self.params.incl_emerg_traj)
         return out
 
     def plan_stream(self, batches, vel_est=None, device_hook=None):
@@ -309,6 +310,7 @@ class BatchPlanner(object):
                 ev.record(copy_stream)
             ev_d2h[k] = ev
             out["n_rows"] = n
+            out["incl_emerg_traj"] = bool(self.params.incl_emerg_traj)
             inflight.append(k)
 
         i = 0

@@ -122,3 +122,32 @@ def test_facade_blocked_zones_and_emergency():
         if done == 4:
             break
     assert done == 4
+
+
+def test_unpack_batch_matches_records():
+    """Graph_LTPL.unpack_batch (views of the pinned host result) against BatchPlanner.records() incl. 'emergency'."""
+    from graphbasedlocaltrajectoryplanner_b200.Graph_LTPL import Graph_LTPL
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios
+    import torch
+    g = H.golden("ticks_ext_default.npz")
+    pl = _planner(g)
+    sc = make_scenarios(Track(H.TRACK_CSV), 96, seed=31, n_obj_min=0, n_obj_max=3)
+    pl.stage_scenarios(sc)
+    pl.upload()
+    pl.set_startpos()
+    pl.tick()
+    out = pl.download()
+    torch.cuda.synchronize()
+    recs = pl.records()
+    views = Graph_LTPL.unpack_batch(out)
+    assert len(views) == sc.size
+    n_em = 0
+    for b in range(sc.size):
+        traj, ids = views[b]
+        want = recs[b].get("traj", {})
+        assert sorted(traj) == sorted(want), "scenario %d: %s vs %s" % (b, sorted(traj), sorted(want))
+        for name in want:
+            assert np.array_equal(traj[name][0].astype(np.float64), want[name][0])
+            assert ids[name] == recs[b]["ids"][name]
+        n_em += int("emergency" in traj)
+    assert n_em > sc.size // 2
