@@ -61,7 +61,19 @@ def write_offline_ini(path, overrides):
         cfg.write(fh)
 
 
-def make_ltpl(graph_ltpl, tag, overrides=None, controller_type=None, veh=None):
+OPEN_ROWS = 560   # data rows of the Monteblanco file kept for the open-track fixture (~1.67 km, 88 layers)
+
+
+def write_open_track_csv(dst):
+    """an OPEN track: the first OPEN_ROWS points of the reference's Monteblanco trajectory file (header kept); the
+    reference detects it as unclosed (main_offline_callback.py:90-99)."""
+    lines = open(REF + "/inputs/traj_ltpl_cl/traj_ltpl_cl_monteblanco.csv").read().splitlines()
+    hdr = [ln for ln in lines if ln.startswith('#')]
+    rows = [ln for ln in lines if not ln.startswith('#')]
+    open(dst, 'w').write("\n".join(hdr + rows[:OPEN_ROWS]) + "\n")
+
+
+def make_ltpl(graph_ltpl, tag, overrides=None, controller_type=None, veh=None, csv=None):
     ini = '/tmp/golden_offline_%s.ini' % tag
     write_offline_ini(ini, overrides)
     online = REF + "/params/ltpl_config_online.ini"
@@ -70,7 +82,7 @@ def make_ltpl(graph_ltpl, tag, overrides=None, controller_type=None, veh=None):
         assert txt.count("controller_type=PD\n") == 1
         online = '/tmp/golden_online_%s_%s.ini' % (tag, controller_type)
         open(online, 'w').write(txt.replace("controller_type=PD\n", "controller_type=%s\n" % controller_type))
-    path_dict = {'globtraj_input_path': REF + "/inputs/traj_ltpl_cl/traj_ltpl_cl_monteblanco.csv",
+    path_dict = {'globtraj_input_path': csv or (REF + "/inputs/traj_ltpl_cl/traj_ltpl_cl_monteblanco.csv"),
                  'graph_store_path': "/tmp/golden_graph_%s.pckl" % tag,
                  'ltpl_offline_param_path': ini,
                  'ltpl_online_param_path': online}
@@ -288,6 +300,8 @@ def main():
     ap.add_argument('--n-other', type=int, default=32)
     ap.add_argument('--ext-only', action='store_true', help='only the zone / emergency fixture (default lattice)')
     ap.add_argument('--n-ext', type=int, default=64)
+    ap.add_argument('--open-only', action='store_true', help='only the open-track fixture')
+    ap.add_argument('--n-open', type=int, default=64)
     ap.add_argument('--variants-only', action='store_true', help='only the parameter-variant fixture')
     ap.add_argument('--n-variant', type=int, default=24)
     args = ap.parse_args()
@@ -299,6 +313,30 @@ def main():
     vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
                       safety_d=30.0, incl_emerg_traj=False)
 
+    if args.open_only or not (args.quick or args.variants_only or args.ext_only):
+        # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
+        # q7; MOPG:203-243; OTH:846-859)
+        open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
+        write_open_track_csv(open_csv)
+        ltpl, _ = make_ltpl(graph_ltpl, "open", {}, csv=open_csv)
+        fx, lat = lattice_fixture(graph_ltpl, ltpl)
+        np.savez_compressed(os.path.join(GOLDEN, 'lattice_open.npz'), **fx)
+        print("[open] lattice: %s" % lat.summary())
+        tr_open = Track(open_csv)
+        sc = make_scenarios(tr_open, args.n_open, seed=DEFAULT_SEED + 99, n_obj_min=0, n_obj_max=3,
+                            s_max=tr_open.length - 8.0)
+        recs = [run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], sc.object_list(b), vel_kwargs, full=True)
+                for b in range(sc.size)]
+        pk = pack_ticks(recs)
+        payload = {('full_' + k): v for k, v in pk.items()}
+        payload.update(sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj, sc_obj=sc.obj,
+                       ax_max_machines=vel_kwargs['ax_max_machines'], overrides=np.array(repr([])))
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_open.npz'), **payload)
+        print("[open] action paths %s; reduced %d; out of track %d" % (
+            {a: int((pk['path_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)}, int(pk['red_len'].sum()),
+            int(pk['out_of_track'].sum())))
+        if args.open_only:
+            return
     if args.variants_only:
         np.savez_compressed(os.path.join(GOLDEN, 'ticks_variants_default.npz'),
                             **variants_fixture(graph_ltpl, track, args.n_variant))

@@ -8,6 +8,7 @@ import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(REPO, "tests", "golden")
 TRACK_CSV = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco.csv")
+OPEN_TRACK_CSV = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")   # first 560 points
 OFFLINE_INI = os.path.join(REPO, "params", "ltpl_config_offline.ini")
 ONLINE_INI = os.path.join(REPO, "params", "ltpl_config_online.ini")
 ACTIONS = ("straight", "follow", "left", "right")
@@ -26,7 +27,11 @@ def golden(name):
 def lattice_for(tag):
     from graphbasedlocaltrajectoryplanner_b200.lattice import build_lattice
     ov = dict(ast.literal_eval(str(golden("ticks_%s.npz" % tag)["overrides"])))
-    return build_lattice(TRACK_CSV, OFFLINE_INI, overrides=ov)
+    return build_lattice(track_csv_for(tag), OFFLINE_INI, overrides=ov)
+
+
+def track_csv_for(tag):
+    return OPEN_TRACK_CSV if tag == "open" else TRACK_CSV
 
 
 def object_list(g, b):

@@ -37,7 +37,7 @@ def _collect(fn, n):
     return fails
 
 
-@pytest.mark.parametrize("tag", ["default", "l216", "l430"])
+@pytest.mark.parametrize("tag", ["default", "l216", "l430", "open"])
 def test_cuda_matches_reference_golden(tag):
     from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
     g = H.golden("ticks_%s.npz" % tag)
@@ -65,14 +65,16 @@ def test_cuda_config1_min_example():
         H.compare_record(recs[b], g, b, prefix="", ctx="config1")
 
 
-@pytest.mark.parametrize("tag,n,omin,omax", [("default", 384, 0, 3), ("l216", 256, 1, 3), ("l430", 128, 5, 5)])
+@pytest.mark.parametrize("tag,n,omin,omax", [("default", 384, 0, 3), ("l216", 256, 1, 3), ("l430", 128, 5, 5), ("open", 256, 0, 3)])
 def test_cuda_matches_oracle_seeded(tag, n, omin, omax):
     """fresh seeded batches (different seed than the golden files), oracle as the checker."""
     from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios
     from oracle.ltpl_oracle import OracleLTPL
     g = H.golden("ticks_%s.npz" % tag)
     axm = g["ax_max_machines"]
-    sc = make_scenarios(Track(H.TRACK_CSV), n, seed=4242 + n, n_obj_min=omin, n_obj_max=omax)
+    track = Track(H.track_csv_for(tag))
+    sc = make_scenarios(track, n, seed=4242 + n, n_obj_min=omin, n_obj_max=omax,
+                        s_max=(track.length - 8.0) if tag == "open" else None)
     recs = _run_batch(_planner(tag), sc, axm)
     orc = OracleLTPL(H.lattice_for(tag))
     vk = dict(ax_max_machines=axm, **VEL)

@@ -5,7 +5,7 @@ import pytest
 
 from tests import helpers as H
 
-TAGS = ("default", "l216", "l430")
+TAGS = ("default", "l216", "l430", "open")
 
 
 def _run(tag, idx=None):
