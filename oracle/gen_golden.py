@@ -300,6 +300,7 @@ def main():
     ap.add_argument('--n-other', type=int, default=32)
     ap.add_argument('--ext-only', action='store_true', help='only the zone / emergency fixture (default lattice)')
     ap.add_argument('--n-ext', type=int, default=64)
+    ap.add_argument('--only', default=None, help='only this lattice configuration of the main loop (e.g. layers14)')
     ap.add_argument('--open-only', action='store_true', help='only the open-track fixture')
     ap.add_argument('--n-open', type=int, default=64)
     ap.add_argument('--variants-only', action='store_true', help='only the parameter-variant fixture')
@@ -313,7 +314,7 @@ def main():
     vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
                       safety_d=30.0, incl_emerg_traj=False)
 
-    if args.open_only or not (args.quick or args.variants_only or args.ext_only):
+    if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -346,6 +347,10 @@ def main():
         configs.append(("l216", {"lat_resolution": 1.0, "lon_straight_step": 12.0}, args.n_other, 1, 3))
         configs.append(("l430", {"lon_curve_step": 6.0, "lon_straight_step": 6.0, "lat_resolution": 0.5},
                         args.n_other, 5, 5))
+        # planning horizon as a fixed number of layers (GLNT:126-136)
+        configs.append(("layers14", {"plan_horizon_mode": "layers", "min_plan_horizon": 14}, args.n_other, 0, 3))
+    if args.only:
+        configs = [c for c in configs if c[0] == args.only]
 
     for tag, overrides, n, omin, omax in configs:
         ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
@@ -398,7 +403,7 @@ def main():
                       sc_vel=np.array([0.0, 20.0]), obj=np.array([127.0, 82.0, 0.0, 0.0, 5.0]))
             np.savez_compressed(os.path.join(GOLDEN, 'config1_min_example.npz'), **pk)
             print("[config1] actions:", {a: pk['path_len'][:, i].tolist() for i, a in enumerate(ACTIONS)})
-    if not args.quick:
+    if not args.quick and not args.only:
         np.savez_compressed(os.path.join(GOLDEN, 'ticks_variants_default.npz'),
                             **variants_fixture(graph_ltpl, track, args.n_variant))
 

@@ -37,7 +37,7 @@ def _collect(fn, n):
     return fails
 
 
-@pytest.mark.parametrize("tag", ["default", "l216", "l430", "open"])
+@pytest.mark.parametrize("tag", ["default", "l216", "l430", "open", "layers14"])
 def test_cuda_matches_reference_golden(tag):
     from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
     g = H.golden("ticks_%s.npz" % tag)
@@ -65,7 +65,7 @@ def test_cuda_config1_min_example():
         H.compare_record(recs[b], g, b, prefix="", ctx="config1")
 
 
-@pytest.mark.parametrize("tag,n,omin,omax", [("default", 384, 0, 3), ("l216", 256, 1, 3), ("l430", 128, 5, 5), ("open", 256, 0, 3)])
+@pytest.mark.parametrize("tag,n,omin,omax", [("default", 384, 0, 3), ("l216", 256, 1, 3), ("l430", 128, 5, 5), ("open", 256, 0, 3), ("layers14", 128, 0, 3)])
 def test_cuda_matches_oracle_seeded(tag, n, omin, omax):
     """fresh seeded batches (different seed than the golden files), oracle as the checker."""
     from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios

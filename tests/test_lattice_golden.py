@@ -5,7 +5,7 @@ import pytest
 from tests import helpers as H
 
 
-@pytest.mark.parametrize("tag", ["default", "l216", "l430", "open"])
+@pytest.mark.parametrize("tag", ["default", "l216", "l430", "open", "layers14"])
 def test_lattice_builder_matches_reference_graph(tag):
     g = H.golden("lattice_%s.npz" % tag)
     lat = H.lattice_for(tag)

@@ -5,7 +5,7 @@ import pytest
 
 from tests import helpers as H
 
-TAGS = ("default", "l216", "l430", "open")
+TAGS = ("default", "l216", "l430", "open", "layers14")
 
 
 def _run(tag, idx=None):
