@@ -12,7 +12,7 @@ import os
 import subprocess
 import sys
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 NSLOT = 3
 KMAX = 16
 MAX_AXM = 32
@@ -62,13 +62,14 @@ class Params(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "k_obj", "p0_max", "p_max", "h_max", "n_export", "n_zone_words",
-                                            "n_zones")]
+                                            "n_zones", "k_pred", "pad0")]
 
 
 BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
                  "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj", "cobj_start",
                  "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "vel_scratch", "s_vx_ax",
-                 "vel_t", "traj", "traj_len", "traj_id", "zone_bits", "zone_sel", "em_info")
+                 "vel_t", "traj", "traj_len", "traj_id", "zone_bits", "zone_sel", "em_info", "obj_pred",
+                 "n_pred")
 
 
 class Buffers(C.Structure):

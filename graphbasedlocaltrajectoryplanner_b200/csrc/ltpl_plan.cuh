@@ -4,6 +4,7 @@
 #include "ltpl_common.cuh"
 
 #define LTPL_KMAX 16          // object slots per scenario held in shared memory
+#define LTPL_DMAX 32          // obstacle discs per scenario (one warp ballot): on-track vehicles + their prediction points
 #define LTPL_WARPS_PER_CTA 4
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -330,8 +331,10 @@ __device__ __forceinline__ int dp_goal(const LatDev& lt, int lane, const DpCtx& 
 // k_plan: OLI.process_object_list + gen_local_node_template + main_online_path_gen (action sets + graph search)
 // ---------------------------------------------------------------------------------------------------------------------
 struct PlanSmem {  // per warp, followed by dist / mask / pred (sizes depend on the lattice)
-    double vx[LTPL_KMAX], vy[LTPL_KMAX], vr[LTPL_KMAX], vv[LTPL_KMAX], pxp[LTPL_KMAX], pyp[LTPL_KMAX];
-    double dx[2 * LTPL_KMAX], dy[2 * LTPL_KMAX], dref[2 * LTPL_KMAX];  // obstacle discs: 2 v current, 2 v + 1 predicted
+    double vx[LTPL_KMAX], vy[LTPL_KMAX], vr[LTPL_KMAX], vv[LTPL_KMAX];
+    // obstacle discs (GLNT:169-189): per on-track vehicle its current position followed by its prediction points
+    double dx[LTPL_DMAX], dy[LTPL_DMAX], dref[LTPL_DMAX];
+    int vd0[LTPL_KMAX], vdn[LTPL_KMAX];   // first disc of a vehicle, number of prediction discs behind it
     int n_veh;
     int pad[3];
 };
@@ -452,27 +455,59 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     const size_t cplane = (size_t)B * dm.p0_max;
     const double* cs = bf.const_seg + (size_t)b * dm.p0_max;
 
-    // ---- OLI.process_object_list (OLI:96-141): drop off-track objects, radius = length / 2, 0.2 s CV prediction ----
-    int n_veh = 0;
+    // ---- OLI.process_object_list (OLI:96-141): drop off-track objects, radius = length / 2, prediction points: the
+    // caller's 'prediction' array (OLI:117-119) or one constant-velocity point at 0.2 s (OLI:121-127) ----
+    int n_veh = 0, n_disc = 0;
     {
         int n_in = bf.n_obj[b];
         if (n_in > dm.k_obj) n_in = dm.k_obj;
+        bool over = false;
         #pragma unroll 1
         for (int k = 0; k < n_in; ++k) {
             const double* o = bf.obj + ((size_t)b * dm.k_obj + k) * 5;
             const double ox = o[0], oy = o[1];
             if (inside_bounds(lt, ox, oy, lane)) {
+                int np_k = -1;   // -1: built-in prediction
+                if (dm.k_pred > 0 && bf.n_pred) np_k = min(bf.n_pred[(size_t)b * dm.k_obj + k], dm.k_pred);
+                const int n_pd = (np_k < 0) ? 1 : np_k;
+                if (n_disc + 1 + n_pd > LTPL_DMAX) {
+                    over = true;
+                    break;
+                }
                 if (lane == 0) {
-                    const double th = o[2], v = o[3];
+                    const double th = o[2], v = o[3], r = o[4] / 2.0;
                     ps->vx[n_veh] = ox;
                     ps->vy[n_veh] = oy;
-                    ps->vr[n_veh] = o[4] / 2.0;
+                    ps->vr[n_veh] = r;
                     ps->vv[n_veh] = v;
-                    ps->pxp[n_veh] = __dsub_rn(ox, __dmul_rn(__dmul_rn(sin(th), v), 0.2));
-                    ps->pyp[n_veh] = __dadd_rn(oy, __dmul_rn(__dmul_rn(cos(th), v), 0.2));
+                    ps->vd0[n_veh] = n_disc;
+                    ps->vdn[n_veh] = n_pd;
+                    // obstacle_ref = (r + veh_width / 2)^2 + stepsize^2 / 4  (GB:626-629)
+                    const double ref = __dadd_rn(sq_rn(__dadd_rn(r, __ddiv_rn(lt.veh_width, 2.0))),
+                                                 __ddiv_rn(sq_rn(lt.step), 4.0));
+                    ps->dx[n_disc] = ox;
+                    ps->dy[n_disc] = oy;
+                    ps->dref[n_disc] = ref;
+                    if (np_k < 0) {
+                        ps->dx[n_disc + 1] = __dsub_rn(ox, __dmul_rn(__dmul_rn(sin(th), v), 0.2));
+                        ps->dy[n_disc + 1] = __dadd_rn(oy, __dmul_rn(__dmul_rn(cos(th), v), 0.2));
+                        ps->dref[n_disc + 1] = ref;
+                    } else {
+                        const double* pp = bf.obj_pred + (((size_t)b * dm.k_obj + k) * dm.k_pred) * 2;
+                        for (int j = 0; j < np_k; ++j) {
+                            ps->dx[n_disc + 1 + j] = pp[2 * j];
+                            ps->dy[n_disc + 1 + j] = pp[2 * j + 1];
+                            ps->dref[n_disc + 1 + j] = ref;
+                        }
+                    }
                 }
+                n_disc += 1 + n_pd;
                 ++n_veh;
             }
+        }
+        if (over) {
+            if (lane == 0) bf.sc_flags[b] = LTPL_SC_CAPACITY;
+            return;
         }
     }
     #pragma unroll 1
@@ -496,24 +531,16 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     int my_pa = -1, my_pb = -1;  // lane d: layer pairs disc d can block
     #pragma unroll 1
     for (int v = 0; v < n_veh; ++v) {
-        int pa, pb;
-        disc_pairs(lt, lane, ps->vx[v], ps->vy[v], start_layer, end_layer, &pa, &pb);
-        if (lane == 2 * v) {
-            my_pa = pa;
-            my_pb = pb;
-        }
-        const int obj_layer = disc_pairs(lt, lane, ps->pxp[v], ps->pyp[v], start_layer, end_layer, &pa, &pb);  // q14
-        if (lane == 2 * v + 1) {
-            my_pa = pa;
-            my_pb = pb;
-        }
-        if (lane < 2) {
-            // obstacle_ref = (r + veh_width / 2)^2 + stepsize^2 / 4  (GB:626-629)
-            const int d = 2 * v + lane;
-            ps->dx[d] = lane ? ps->pxp[v] : ps->vx[v];
-            ps->dy[d] = lane ? ps->pyp[v] : ps->vy[v];
-            ps->dref[d] = __dadd_rn(sq_rn(__dadd_rn(ps->vr[v], __ddiv_rn(lt.veh_width, 2.0))),
-                                    __ddiv_rn(sq_rn(lt.step), 4.0));
+        const int d0 = ps->vd0[v], d1 = d0 + ps->vdn[v];
+        int obj_layer = -1;
+        #pragma unroll 1
+        for (int d = d0; d <= d1; ++d) {   // current position, then the prediction points: the LAST one sets obj_layer (q14)
+            int pa, pb;
+            obj_layer = disc_pairs(lt, lane, ps->dx[d], ps->dy[d], start_layer, end_layer, &pa, &pb);
+            if (lane == d) {
+                my_pa = pa;
+                my_pb = pb;
+            }
         }
         if (obj_layer >= 0) {
             int ld = obj_layer - start_layer;
@@ -527,7 +554,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     }
     __syncwarp();
     #pragma unroll 1
-    for (int d = 0; d < 2 * n_veh; ++d) {  // one sweep per distinct layer pair, shared by every disc that touches it
+    for (int d = 0; d < n_disc; ++d) {  // one sweep per distinct layer pair, shared by every disc that touches it
         #pragma unroll 1
         for (int slot = 0; slot < 2; ++slot) {
             const int a = __shfl_sync(LTPL_FULL, slot ? my_pb : my_pa, d);

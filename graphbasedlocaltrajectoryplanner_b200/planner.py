@@ -90,6 +90,7 @@ class BatchPlanner(object):
             .astype(np.int64)
         self.lattice_nodes = int(self.header.num_nodes)
         self.dims = None
+        self._k_pred_cap = 0
         self.buf = None
         self.t = {}
         self.params = capi.Params()
@@ -140,8 +141,9 @@ class BatchPlanner(object):
             p.axm_s[i] = (axm[i + 1, 1] - axm[i, 1]) / (axm[i + 1, 0] - axm[i, 0])
 
     # -- buffers -----------------------------------------------------------------------------------------------------------
-    def allocate(self, batch: int, k_obj: int = 3) -> None:
-        if self.dims is not None and self.dims.batch == batch and self.dims.k_obj == max(1, k_obj):
+    def allocate(self, batch: int, k_obj: int = 3, k_pred: int = 0) -> None:
+        if self.dims is not None and self.dims.batch == batch and self.dims.k_obj == max(1, k_obj) \
+                and self._k_pred_cap >= k_pred:
             return
         k_obj = max(1, int(k_obj))
         if k_obj > capi.KMAX:
@@ -168,7 +170,10 @@ class BatchPlanner(object):
             return raw, views
 
         in_spec = [("pos", (B, 2), f64), ("heading", (B,), f64), ("vel", (B,), f64), ("vel_est", (B,), f64),
-                   ("n_obj", (B,), i32), ("obj", (B, K, 5), f64), ("zone_sel", (B,), i32)]
+                   ("n_obj", (B,), i32), ("obj", (B, K, 5), f64), ("zone_sel", (B,), i32), ("n_pred", (B, K), i32)]
+        self._k_pred_cap = int(k_pred)
+        if k_pred > 0:
+            in_spec.append(("obj_pred", (B, K, int(k_pred), 2), f64))
         meta_spec = [("exp_q", (NSLOT * B,), i32), ("traj_row", (NSLOT, B), i32), ("traj_len", (NSLOT, B), i32),
                      ("traj_id", (NSLOT, B), i32), ("action_id", (NSLOT, B), i32), ("status", (NSLOT, B), i32),
                      ("sc_flags", (B,), i32), ("queue_cnt", (4,), i32), ("em_info", (B, 3), i32)]
@@ -188,6 +193,9 @@ class BatchPlanner(object):
         t.update(t_meta)
         buf = capi.Buffers()
         t["zone_bits"] = torch.zeros((1, 1), dtype=torch.int32, device=dev)   # replaced by _upload_zones()
+        if k_pred == 0:
+            t["obj_pred"] = torch.zeros((1,), dtype=f64, device=dev)
+        d.k_pred = 0
         d.n_zones, d.n_zone_words = 0, (self.lattice_nodes + 31) // 32
         for name in capi.BUFFER_FIELDS:
             setattr(buf, name, t[name].data_ptr())
@@ -228,8 +236,9 @@ class BatchPlanner(object):
 
     def stage_scenarios(self, sc: ScenarioBatch, vel_est=None, which: int = 0) -> None:
         """copy a scenario batch into the pinned staging buffers (host memcpy)."""
-        if self.dims is None or sc.size != self.dims.batch or sc.obj.shape[1] > self.dims.k_obj:
-            self.allocate(sc.size, sc.obj.shape[1])
+        kp = 0 if sc.pred is None else int(sc.pred.shape[2])
+        if self.dims is None or sc.size != self.dims.batch or sc.obj.shape[1] > self.dims.k_obj or kp > self._k_pred_cap:
+            self.allocate(sc.size, sc.obj.shape[1], kp)
         h = self.h_in_sets[which]
         k = sc.obj.shape[1]
         h["pos"].numpy()[...] = sc.pos
@@ -241,6 +250,13 @@ class BatchPlanner(object):
             h["obj"].numpy()[:, k:, :] = 0.0
         h["obj"].numpy()[:, :k, :] = sc.obj
         h["zone_sel"].numpy()[...] = -1 if sc.zone_sel is None else sc.zone_sel
+        h["n_pred"].numpy()[...] = -1
+        self.dims.k_pred = 0
+        if sc.n_pred is not None:     # kp >= 1 here, so allocate() above provided the obj_pred staging
+            h["n_pred"].numpy()[:, :k] = sc.n_pred
+            h["obj_pred"].numpy()[...] = 0.0
+            h["obj_pred"].numpy()[:, :k, :kp, :] = sc.pred
+            self.dims.k_pred = self._k_pred_cap
         self._upload_zones(sc.zones)
 
     def _upload_zones(self, zones) -> None:

@@ -33,6 +33,10 @@ class ScenarioBatch:
     # pairs and, per scenario, the index of its zone or -1.  None: no zones in this batch.
     zones: list = None
     zone_sel: np.ndarray = None   # (B,) int32
+    # explicit prediction arrays of the objects (dict key 'prediction', OLI:117-119): n_pred[b, k] points (-1: none
+    # given -> the built-in constant-velocity point at 0.2 s, OLI:121-127).  None: no object carries a prediction.
+    pred: np.ndarray = None       # (B, K, KP, 2) float64
+    n_pred: np.ndarray = None     # (B, K) int32
 
     @property
     def size(self) -> int:
@@ -45,13 +49,17 @@ class ScenarioBatch:
             x, y, th, v, ln = (float(a) for a in self.obj[b, k])
             out.append({'id': k + 1, 'type': 'physical', 'X': x, 'Y': y, 'theta': th, 'v': v, 'length': ln,
                         'width': 2.5})
+            if self.n_pred is not None and self.n_pred[b, k] >= 0:
+                out[-1]['prediction'] = self.pred[b, k, :int(self.n_pred[b, k])].copy()
         return out
 
     def subset(self, idx) -> "ScenarioBatch":
         idx = np.asarray(idx)
         return ScenarioBatch(self.pos[idx].copy(), self.heading[idx].copy(), self.vel[idx].copy(),
                              self.n_obj[idx].copy(), self.obj[idx].copy(), self.zones,
-                             None if self.zone_sel is None else self.zone_sel[idx].copy())
+                             None if self.zone_sel is None else self.zone_sel[idx].copy(),
+                             None if self.pred is None else self.pred[idx].copy(),
+                             None if self.n_pred is None else self.n_pred[idx].copy())
 
     def set_zones(self, blocked_zones) -> None:
         """blocked_zones: one entry per scenario, each None or a dict {zone id: [layer ids, node ids, left bound, right
@@ -85,15 +93,21 @@ class ScenarioBatch:
         n_obj = np.array([len(o) if o is not None else 0 for o in object_lists], dtype=np.int32)
         k = int(max(1, n_obj.max() if b else 1)) if k_max is None else int(k_max)
         obj = np.zeros((b, k, 5))
+        kp = max([np.atleast_2d(o['prediction']).shape[0] for ol in object_lists for o in (ol or [])
+                  if 'prediction' in o and np.size(o['prediction'])] + [0])
+        has_pred = any('prediction' in o for ol in object_lists for o in (ol or []))
+        pred = np.zeros((b, k, max(kp, 1), 2)) if has_pred else None
+        n_pred = np.full((b, k), -1, dtype=np.int32) if has_pred else None
         for i, ol in enumerate(object_lists):
             for j, o in enumerate(ol or []):
-                if 'prediction' in o:
-                    raise NotImplementedError("batched scenarios use the reference's built-in 0.2 s constant-velocity "
-                                              "prediction (OLI:121-127); explicit 'prediction' arrays are not batched")
                 obj[i, j] = [o['X'], o['Y'], o['theta'], o['v'], o['length']]
+                if 'prediction' in o:
+                    pr = np.asarray(o['prediction'], dtype=np.float64).reshape(-1, 2)
+                    n_pred[i, j] = pr.shape[0]
+                    pred[i, j, :pr.shape[0]] = pr
         sc = ScenarioBatch(np.asarray(pos, dtype=np.float64).reshape(b, 2),
                            np.asarray(heading, dtype=np.float64).reshape(b),
-                           np.asarray(vel, dtype=np.float64).reshape(b), n_obj, obj)
+                           np.asarray(vel, dtype=np.float64).reshape(b), n_obj, obj, pred=pred, n_pred=n_pred)
         if blocked_zones is not None:
             sc.set_zones(blocked_zones)
         return sc

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 5
+#define LTPL_ABI_VERSION 6
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -152,6 +152,8 @@ typedef struct LtplDims {
     int32_t n_export;  /* rows of an exported trajectory (nmbr_export_points)          */
     int32_t n_zone_words; /* 32-bit words of one zone bitmask = ceil(num_nodes / 32)   */
     int32_t n_zones;      /* zone bitmasks in LtplBuffers.zone_bits (0: no zones)      */
+    int32_t k_pred;       /* prediction points per object slot in obj_pred (0: built-in 0.2 s prediction only) */
+    int32_t pad0;
 } LtplDims;
 
 /* Caller-owned device buffers.  q = slot * B + b indexes a path ("action major").                                      */
@@ -202,6 +204,11 @@ typedef struct LtplBuffers {
     /* emergency trajectory (params.incl_emerg_traj): row in `traj` (or -1), rows, id -- key 'emergency' of the           */
     /* reference's trajectory dict (OTH:1030-1034); `traj` needs (NSLOT + 1) * B rows then                                */
     int32_t* em_info;         /* [B][3]                                                                                  */
+    /* explicit prediction arrays of the objects (object dict key 'prediction', OLI:117-119); may be NULL when k_pred == 0 */
+    const double* obj_pred;   /* [B][K][k_pred][2] x, y                                                                  */
+    const int32_t* n_pred;    /* [B][K] number of prediction points of the object, -1: none given -> one constant-        */
+                              /*        velocity point at 0.2 s (OLI:121-127).  At most 32 discs (on-track objects +     */
+                              /*        their prediction points) per scenario, else LTPL_SC_CAPACITY                     */
 } LtplBuffers;
 
 /* stand-alone forward/backward ggv velocity profile over dense path arrays (BASELINE.json config 5).                   */

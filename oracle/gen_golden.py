@@ -238,6 +238,39 @@ def ext_fixture(ltpl, lat, track, n, vel_kwargs):
     return pk
 
 
+def pred_fixture(ltpl, track, n, vel_kwargs):
+    """objects that carry an explicit 'prediction' array (OLI:117-119; GLNT:180-189 blocks the edges under every
+    prediction point, the LAST one decides the object's layer -- quirk q14): 0-4 points per object, some objects without
+    the key in the same list."""
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import make_scenarios
+    sc = make_scenarios(track, n, seed=5150, n_obj_min=1, n_obj_max=3)
+    rng = np.random.default_rng(5151)
+    kp = 4
+    sc.pred = np.zeros((n, sc.obj.shape[1], kp, 2))
+    sc.n_pred = np.full((n, sc.obj.shape[1]), -1, dtype=np.int32)
+    for b in range(n):
+        for k in range(int(sc.n_obj[b])):
+            if rng.random() < 0.25:
+                continue                                   # no 'prediction' key -> built-in 0.2 s point
+            m = int(rng.integers(0, kp + 1))
+            x, y, th, v, _ = sc.obj[b, k]
+            drift = rng.uniform(-0.4, 0.4)
+            for j in range(m):
+                t = 0.3 * (j + 1)
+                sc.pred[b, k, j] = [x - np.sin(th) * v * t + np.cos(th) * drift * t * 3.0,
+                                    y + np.cos(th) * v * t + np.sin(th) * drift * t * 3.0]
+            sc.n_pred[b, k] = m
+    recs = [run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], sc.object_list(b), vel_kwargs, full=True)
+            for b in range(n)]
+    pk = pack_ticks(recs)
+    pk.update(sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj, sc_obj=sc.obj, sc_pred=sc.pred,
+              sc_n_pred=sc.n_pred, ax_max_machines=vel_kwargs['ax_max_machines'])
+    print("[pred] %d objects with explicit predictions (%d points); action paths %s" % (
+        int((sc.n_pred >= 0).sum()), int(np.maximum(sc.n_pred, 0).sum()),
+        {a: int((pk['path_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)}))
+    return pk
+
+
 VARIANTS = (
     # follow-mode controller with tan activation (CVPF:65-71), friction-ellipse exponent != 1 (tph.calc_ax_poss), other
     # vehicle mass / drag (LTPL:189-192), reduced gg scale, asymmetric gg, lower v_max, ego estimate != planned velocity
@@ -300,6 +333,7 @@ def main():
     ap.add_argument('--n-other', type=int, default=32)
     ap.add_argument('--ext-only', action='store_true', help='only the zone / emergency fixture (default lattice)')
     ap.add_argument('--n-ext', type=int, default=64)
+    ap.add_argument('--pred-only', action='store_true', help="only the explicit-'prediction' fixture (default lattice)")
     ap.add_argument('--only', default=None, help='only this lattice configuration of the main loop (e.g. layers14)')
     ap.add_argument('--open-only', action='store_true', help='only the open-track fixture')
     ap.add_argument('--n-open', type=int, default=64)
@@ -314,7 +348,7 @@ def main():
     vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
                       safety_d=30.0, incl_emerg_traj=False)
 
-    if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only):
+    if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -356,6 +390,10 @@ def main():
         ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
         fx, lat = lattice_fixture(graph_ltpl, ltpl)
         if tag == "default":
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_pred_default.npz'),
+                                **pred_fixture(ltpl, track, args.n_other, vel_kwargs))
+            if args.pred_only:
+                return
             np.savez_compressed(os.path.join(GOLDEN, 'ticks_ext_default.npz'),
                                 **ext_fixture(ltpl, lat, track, args.n_ext, vel_kwargs))
             if args.ext_only:

@@ -39,6 +39,8 @@ def object_list(g, b):
     for k in range(int(g["sc_n_obj"][b])):
         x, y, th, v, ln = (float(a) for a in g["sc_obj"][b, k])
         out.append({'id': k + 1, 'type': 'physical', 'X': x, 'Y': y, 'theta': th, 'v': v, 'length': ln, 'width': 2.5})
+        if "sc_n_pred" in g.files and int(g["sc_n_pred"][b, k]) >= 0:
+            out[-1]['prediction'] = g["sc_pred"][b, k, :int(g["sc_n_pred"][b, k])].copy()
     return out
 
 

@@ -151,3 +151,61 @@ def test_unpack_batch_matches_records():
             assert ids[name] == recs[b]["ids"][name]
         n_em += int("emergency" in traj)
     assert n_em > sc.size // 2
+
+
+def test_explicit_predictions_match_reference_golden_and_oracle():
+    """objects with an explicit 'prediction' array (OLI:117-119): up to 4 points per object, mixed with objects that use
+    the built-in 0.2 s point; golden vectors of the reference + a seeded batch against the oracle."""
+    from oracle.ltpl_oracle import OracleLTPL
+    from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch, Track, make_scenarios
+    g = H.golden("ticks_pred_default.npz")
+    n = g["sc_pos"].shape[0]
+    ols = [H.object_list(g, b) for b in range(n)]
+    sc = ScenarioBatch.from_object_lists(g["sc_pos"], g["sc_heading"], g["sc_vel"], ols, k_max=3)
+    assert sc.pred is not None and np.array_equal(sc.n_pred, g["sc_n_pred"])
+    vel = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    pl = BatchPlanner(H.lattice_for("default"), device="cuda:0")
+    pl.set_vel_params(**vel)
+    pl.stage_scenarios(sc)
+    pl.upload()
+    pl.set_startpos()
+    pl.tick()
+    recs = pl.records()
+    for b in range(n):
+        H.compare_record(recs[b], g, b, prefix="", ctx="pred gpu")
+    # seeded: many prediction points (up to 6) so that several scenarios hold > 10 discs
+    sc2 = make_scenarios(Track(H.TRACK_CSV), 128, seed=606, n_obj_min=1, n_obj_max=4)
+    rng = np.random.default_rng(607)
+    kp = 6
+    sc2.pred = np.zeros((sc2.size, sc2.obj.shape[1], kp, 2))
+    sc2.n_pred = np.full((sc2.size, sc2.obj.shape[1]), -1, dtype=np.int32)
+    for b in range(sc2.size):
+        for k in range(int(sc2.n_obj[b])):
+            if rng.random() < 0.2:
+                continue
+            m = int(rng.integers(0, kp + 1))
+            x, y, th, v, _ = sc2.obj[b, k]
+            for j in range(m):
+                t = 0.25 * (j + 1)
+                sc2.pred[b, k, j] = [x - np.sin(th) * v * t, y + np.cos(th) * v * t]
+            sc2.n_pred[b, k] = m
+    pl.stage_scenarios(sc2)
+    pl.upload()
+    pl.set_startpos()
+    pl.tick()
+    recs2 = pl.records()
+    orc = OracleLTPL(H.lattice_for("default"))
+    for b in range(sc2.size):
+        want = orc.tick(sc2.pos[b], sc2.heading[b], sc2.vel[b], sc2.object_list(b), vel)
+        H.compare_records(recs2[b], want, ctx="pred seeded %d" % b)
+    # a later batch WITHOUT predictions on the same planner goes back to the built-in rule
+    sc3 = make_scenarios(Track(H.TRACK_CSV), 128, seed=608, n_obj_min=1, n_obj_max=4)
+    pl.stage_scenarios(sc3)
+    pl.upload()
+    pl.set_startpos()
+    pl.tick()
+    recs3 = pl.records()
+    for b in range(0, sc3.size, 4):
+        want = orc.tick(sc3.pos[b], sc3.heading[b], sc3.vel[b], sc3.object_list(b), vel)
+        H.compare_records(recs3[b], want, ctx="no-pred after pred %d" % b)

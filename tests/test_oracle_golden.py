@@ -68,3 +68,15 @@ def test_oracle_parameter_variants(name):
         rec = orc.tick(sub["sc_pos"][b], sub["sc_heading"][b], sub["sc_vel"][b], H.object_list(sub, b), vk,
                        vel_est=sub["sc_vel"][b] + dv)
         H.compare_record(rec, sub, b, prefix="", ctx=name)
+
+
+def test_oracle_explicit_predictions():
+    """objects with an explicit 'prediction' array (OLI:117-119, GLNT:180-189, quirk q14) against the reference."""
+    from oracle.ltpl_oracle import OracleLTPL
+    g = H.golden("ticks_pred_default.npz")
+    orc = OracleLTPL(H.lattice_for("default"))
+    vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    assert int((g["sc_n_pred"] >= 0).sum()) > 20
+    for b in range(g["sc_pos"].shape[0]):
+        rec = orc.tick(g["sc_pos"][b], g["sc_heading"][b], g["sc_vel"][b], H.object_list(g, b), vk)
+        H.compare_record(rec, g, b, prefix="", ctx="pred")
