@@ -12,7 +12,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
     from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
     pl = BatchPlanner(bench.get_lattice(tag), device="cuda:0")
     pl.set_vel_params(**bench.vel_kwargs())
-    pl.stage_scenarios(bench.make_batch(tag, 10000)); pl.upload(); pl.set_startpos()
+    pl.stage_scenarios(bench.make_batch(tag, int(os.environ.get("TUNE_BATCH", "10000")))); pl.upload(); pl.set_startpos()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream()
     def timed(fn, steps=10):
