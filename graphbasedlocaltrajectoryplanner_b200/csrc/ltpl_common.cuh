@@ -99,6 +99,15 @@ __device__ __forceinline__ double angle3pt(double ax, double ay, double bx, doub
 struct AngCmp {
     bool gt, ge;
 };
+// the reference's own expression (four atan2): only reached on near-ties, kept out of line (instruction cache)
+__device__ __noinline__ AngCmp angle_cmp_exact(double2 pn, double px, double py, double2 p1, double2 p2) {
+    const double a1 = fabs(angle3pt(pn.x, pn.y, px, py, p1.x, p1.y));
+    const double a2 = fabs(angle3pt(pn.x, pn.y, px, py, p2.x, p2.y));
+    AngCmp r;
+    r.gt = a1 > a2;
+    r.ge = a1 >= a2;
+    return r;
+}
 __device__ __forceinline__ AngCmp angle_cmp(double2 pn, double px, double py, double2 p1, double2 p2) {
     const double ux = pn.x - px, uy = pn.y - py;
     const double v1x = p1.x - px, v1y = p1.y - py, v2x = p2.x - px, v2y = p2.y - py;
@@ -112,11 +121,7 @@ __device__ __forceinline__ AngCmp angle_cmp(double2 pn, double px, double py, do
             return r;
         }
     }
-    const double a1 = fabs(angle3pt(pn.x, pn.y, px, py, p1.x, p1.y));
-    const double a2 = fabs(angle3pt(pn.x, pn.y, px, py, p2.x, p2.y));
-    r.gt = a1 > a2;
-    r.ge = a1 >= a2;
-    return r;
+    return angle_cmp_exact(pn, px, py, p1, p2);
 }
 
 // tph.normalize_psi

@@ -54,14 +54,19 @@ __device__ __forceinline__ VelCfg make_velcfg(const LtplParams& prm, const doubl
 }
 
 // available longitudinal tyre acceleration at w = v^2 on curvature |kappa| (friction ellipse with exponent exp)
+// general friction-ellipse exponent: two pow() calls = ~1000 instructions; kept out of line so that the recurrence
+// loops of the common exponent 1.0 (LTPL:190 default) stay small in the instruction cache
+__device__ __noinline__ double acc_tire_pow(double ratio, double ax_max, double exp_) {
+    const double radicand = 1.0 - pow(ratio, exp_);
+    return (radicand > 0.0) ? ax_max * pow(radicand, 1.0 / exp_) : 0.0;
+}
 __device__ __forceinline__ double acc_tire(double w, double kabs, double ax_max, double inv_ay, double exp_) {
     const double ratio = w * kabs * inv_ay;  // ay_used / ay_max, ay_used = v^2 / radius
     if (exp_ == 1.0) {
         const double radicand = 1.0 - ratio;
         return (radicand > 0.0) ? ax_max * radicand : 0.0;
     }
-    const double radicand = 1.0 - pow(ratio, exp_);
-    return (radicand > 0.0) ? ax_max * pow(radicand, 1.0 / exp_) : 0.0;
+    return acc_tire_pow(ratio, ax_max, exp_);
 }
 
 // np.interp on the machine table with a moving hint (v changes slowly along a path)

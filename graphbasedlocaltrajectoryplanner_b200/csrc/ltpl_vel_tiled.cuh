@@ -22,6 +22,11 @@
 #define VT_P 8                       // paths per warp (power of two, 2 * VT_P <= 32)
 #endif
 #define VT_W (VT_P + 1)              // padded tile row (doubles)
+#ifndef VT_UNROLL
+#define VT_UNROLL 8                  // unroll factor of the tile move loops (VT_P iterations each, ~20 call sites)
+#endif
+#define VT_PRAGMA_(x) _Pragma(#x)
+#define VT_PRAGMA_UNROLL(n) VT_PRAGMA_(unroll n)
 #define VT_TILE (32 * VT_W)          // doubles per tile
 #define VT_NTILES 6                  // tiles per warp
 #define VT_SMEM_BYTES (VT_NTILES * VT_TILE * 8 + 2 * VT_P * 4)
@@ -46,7 +51,7 @@ struct WarpCtx {
 
 // tile[k][r] = row_r[p0 + k] for the warp's VT_P paths (row-major per-path array `plane`); lanes = 32 points
 __device__ __forceinline__ void tile_load_rows(const WarpCtx& w, double* tile, const double* plane, int p0) {
-#pragma unroll
+VT_PRAGMA_UNROLL(VT_UNROLL)
     for (int r = 0; r < VT_P; ++r) {
         if (p0 + w.lane < w.ns[r])
             cp_async8(&tile[w.lane * VT_W + r], plane + (size_t)w.qs[r] * w.p_max + p0 + w.lane);
@@ -54,21 +59,21 @@ __device__ __forceinline__ void tile_load_rows(const WarpCtx& w, double* tile, c
 }
 // row_r[p0 + k] = tile[k][r]
 __device__ __forceinline__ void tile_store_rows(const WarpCtx& w, const double* tile, double* plane, int p0) {
-#pragma unroll
+VT_PRAGMA_UNROLL(VT_UNROLL)
     for (int r = 0; r < VT_P; ++r) {
         if (p0 + w.lane < w.ns[r]) plane[(size_t)w.qs[r] * w.p_max + p0 + w.lane] = tile[w.lane * VT_W + r];
     }
 }
 // transposed scratch <-> tile: 32 rows x VT_P columns, element e = it * 32 + lane -> (row e / VT_P, column e % VT_P)
 __device__ __forceinline__ void tile_load_t(const WarpCtx& w, double* tile, const double* tarr, int p0, int np) {
-#pragma unroll
+VT_PRAGMA_UNROLL(VT_UNROLL)
     for (int it = 0; it < VT_P; ++it) {
         const int e = it * 32 + w.lane, k = e / VT_P, cc = e % VT_P;
         if (p0 + k < np) cp_async8(&tile[k * VT_W + cc], tarr + (size_t)(p0 + k) * w.ntc + w.col0 + cc);
     }
 }
 __device__ __forceinline__ void tile_store_t(const WarpCtx& w, const double* tile, double* tarr, int p0, int np) {
-#pragma unroll
+VT_PRAGMA_UNROLL(VT_UNROLL)
     for (int it = 0; it < VT_P; ++it) {
         const int e = it * 32 + w.lane, k = e / VT_P, cc = e % VT_P;
         if (p0 + k < np) tarr[(size_t)(p0 + k) * w.ntc + w.col0 + cc] = tile[k * VT_W + cc];
