@@ -271,6 +271,99 @@ def pred_fixture(ltpl, track, n, vel_kwargs):
     return pk
 
 
+class ScriptedClock(object):
+    """stands in for the `time` module inside OnlineTrajectoryHandler (OTH:353-354, 395, 672): the calculation time the
+    reference measures with the wall clock becomes an input of the fixture."""
+
+    def __init__(self):
+        self.t = 1000.0
+
+    def time(self):
+        return self.t
+
+
+def advance_on_traj(traj, dt):
+    """vehicle dummy: position / velocity after dt on a trajectory (s, x, y, psi, kappa, vx, ax), constant-acceleration
+    step with the first row's values (cf. testing_tools/src/vdc_dummy.py)."""
+    ds = max(traj[0, 5] * dt + 0.5 * traj[0, 6] * dt * dt, 0.0)
+    s = traj[0, 0] + ds
+    return (np.array([np.interp(s, traj[:, 0], traj[:, 1]), np.interp(s, traj[:, 0], traj[:, 2])]),
+            float(np.interp(s, traj[:, 0], traj[:, 5])))
+
+
+def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs):
+    """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
+    selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids)."""
+    import graph_ltpl.online_graph.src.OnlineTrajectoryHandler as oth_mod
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import make_scenarios
+    clock = ScriptedClock()
+    real_time = oth_mod.time
+    oth_mod.time = clock
+    try:
+        sc = make_scenarios(track, n_seq, seed=31337, n_obj_min=0, n_obj_max=2)
+        rng = np.random.default_rng(31338)
+        prefer = (("right", "left", "straight", "follow"), ("follow", "straight", "left", "right"),
+                  ("left", "straight", "follow", "right"))
+        hmax, pmax = 40, 115
+        out = dict(dt=np.zeros((n_seq, n_ticks)), sel=np.full((n_seq, n_ticks), -1, dtype=np.int32),
+                   pos_est=np.zeros((n_seq, n_ticks, 2)), vel_est=np.zeros((n_seq, n_ticks)),
+                   obj=np.zeros((n_seq, n_ticks, sc.obj.shape[1], 5)),
+                   traj=np.zeros((n_seq, n_ticks, 4, pmax, 7)), traj_len=np.zeros((n_seq, n_ticks, 4), dtype=np.int32),
+                   traj_id=np.full((n_seq, n_ticks, 4), -1, dtype=np.int32),
+                   nodes=np.full((n_seq, n_ticks, 4, hmax, 2), -1, dtype=np.int32),
+                   nodes_len=np.zeros((n_seq, n_ticks, 4), dtype=np.int32),
+                   path_len=np.zeros((n_seq, n_ticks, 4), dtype=np.int32), n_done=np.zeros(n_seq, dtype=np.int32))
+        for q in range(n_seq):
+            if ltpl.set_startpos(pos_est=np.array(sc.pos[q]), heading_est=float(sc.heading[q]), vel_est=float(sc.vel[q])):
+                continue
+            oth = ltpl._Graph_LTPL__oth
+            ltpl._Graph_LTPL__obj_zone = []
+            ltpl._Graph_LTPL__obj_list_handler._ObjectListInterface__object_zones = []
+            objs = sc.obj[q, :int(sc.n_obj[q])].copy()
+            pos_est, vel_est, sel, traj_set = np.array(sc.pos[q]), float(sc.vel[q]), "straight", None
+            order = prefer[q % len(prefer)]
+            for k in range(n_ticks):
+                dt = float(rng.uniform(0.04, 0.16))
+                clock.t += dt
+                for j in range(objs.shape[0]):            # opponents keep heading and speed
+                    objs[j, 0] -= np.sin(objs[j, 2]) * objs[j, 3] * dt
+                    objs[j, 1] += np.cos(objs[j, 2]) * objs[j, 3] * dt
+                ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
+                       'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(objs)]
+                if traj_set is not None:
+                    pos_est, vel_est = advance_on_traj(traj_set[sel][0], dt)
+                out['dt'][q, k], out['sel'][q, k] = dt, ACTIONS.index(sel)
+                out['pos_est'][q, k], out['vel_est'][q, k] = pos_est, vel_est
+                out['obj'][q, k, :objs.shape[0]] = objs
+                paths = ltpl.calc_paths(prev_action_id=sel, object_list=ol)
+                nodes = oth._OnlineTrajectoryHandler__last_action_set_nodes
+                for a, act in enumerate(ACTIONS):
+                    if act in paths and len(paths[act]) and np.size(paths[act][0]):
+                        out['path_len'][q, k, a] = paths[act][0].shape[0]
+                        nd = [[-1 if v is None else int(v) for v in pair] for pair in nodes[act][0]]
+                        out['nodes'][q, k, a, :len(nd)] = nd
+                        out['nodes_len'][q, k, a] = len(nd)
+                traj_set, ids, _ = ltpl.calc_vel_profile(pos_est=pos_est, vel_est=vel_est, **vel_kwargs)
+                for a, act in enumerate(ACTIONS):
+                    if act in traj_set and len(traj_set[act]):
+                        t = traj_set[act][0]
+                        out['traj'][q, k, a, :t.shape[0]] = t
+                        out['traj_len'][q, k, a] = t.shape[0]
+                        out['traj_id'][q, k, a] = ids[act]
+                out['n_done'][q] = k + 1
+                cand = [a for a in order if a in traj_set and len(traj_set[a])]
+                if not cand:
+                    break
+                sel = cand[0]
+        out.update(sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj,
+                   ax_max_machines=vel_kwargs['ax_max_machines'])
+        print("[multitick] %d sequences, %d ticks; selected actions %s" % (
+            n_seq, int(out['n_done'].sum()), {a: int((out['sel'] == i).sum()) for i, a in enumerate(ACTIONS)}))
+        return out
+    finally:
+        oth_mod.time = real_time
+
+
 VARIANTS = (
     # follow-mode controller with tan activation (CVPF:65-71), friction-ellipse exponent != 1 (tph.calc_ax_poss), other
     # vehicle mass / drag (LTPL:189-192), reduced gg scale, asymmetric gg, lower v_max, ego estimate != planned velocity
@@ -333,6 +426,7 @@ def main():
     ap.add_argument('--n-other', type=int, default=32)
     ap.add_argument('--ext-only', action='store_true', help='only the zone / emergency fixture (default lattice)')
     ap.add_argument('--n-ext', type=int, default=64)
+    ap.add_argument('--multitick-only', action='store_true', help='only the closed-loop (stateful) fixture')
     ap.add_argument('--pred-only', action='store_true', help="only the explicit-'prediction' fixture (default lattice)")
     ap.add_argument('--only', default=None, help='only this lattice configuration of the main loop (e.g. layers14)')
     ap.add_argument('--open-only', action='store_true', help='only the open-track fixture')
@@ -348,7 +442,8 @@ def main():
     vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
                       safety_d=30.0, incl_emerg_traj=False)
 
-    if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only):
+    if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
+                              or args.multitick_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -389,6 +484,11 @@ def main():
     for tag, overrides, n, omin, omax in configs:
         ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
         fx, lat = lattice_fixture(graph_ltpl, ltpl)
+        if tag == "default" and (args.multitick_only or not (args.pred_only or args.ext_only)):
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_default.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 16, 10, vel_kwargs))
+            if args.multitick_only:
+                return
         if tag == "default":
             np.savez_compressed(os.path.join(GOLDEN, 'ticks_pred_default.npz'),
                                 **pred_fixture(ltpl, track, args.n_other, vel_kwargs))

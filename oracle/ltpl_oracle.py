@@ -418,7 +418,8 @@ class OracleLTPL(object):
     # ----------------------------------------------------------------------------------------------------------------------
     # main_online_path_gen  (MOPG:11-334)
     # ----------------------------------------------------------------------------------------------------------------------
-    def main_online_path_gen(self, start_node, obj_veh, last_action_id, const_path_seg, pos_est, zone=None):
+    def main_online_path_gen(self, start_node, obj_veh, last_action_id, const_path_seg, pos_est, zone=None,
+                             cost_factor=None):
         lt = self.lat
         end_layer, closest_obj_index, closest_obj_node, blocked, range_layers = \
             self.gen_local_node_template(start_node, obj_veh)
@@ -483,7 +484,8 @@ class OracleLTPL(object):
             while True:                                       # MOPG:203-220
                 if mod_goal == start_node[0]:
                     break
-                nodes, tie = self.search(start_node, mod_goal, range_layers, blk, zone=zone, **kw)
+                nodes, tie = self.search(start_node, mod_goal, range_layers, blk, zone=zone, cost_factor=cost_factor,
+                                         **kw)
                 if nodes is not None or not (name == "follow" or name == "straight"):
                     break
                 mod_goal -= 1
@@ -704,6 +706,80 @@ class OracleLTPL(object):
                                         drag_coeff=self.drag_coeff, m_veh=self.m_veh, closed=False)
         return np.minimum(vx_profile, vx_compl), too_close, vel_bound_fulfilled
 
+    def vel_one(self, action_id, pp, gg, end_node_in, red_len, vel_plan, vel_course, vel_est, closest_obj_index, obj_veh,
+                pos_est, safety_d, vk):
+        """velocity profile of ONE action's path `pp` (already cut at the ego position), OTH:733-941; returns
+        (bp_out (P, 7) or [], vel_bound)."""
+        lt = self.lat
+        bp_out = []
+        vel_bound = True
+        if np.size(pp, axis=0) > 0:
+            vel_idx = vel_course.shape[0]
+            s = np.concatenate(([0], np.cumsum(pp[:-1, 4])))                      # OTH:743
+            vx_prefix, pref_idx_add, vel_start = self.vp_check_brake_prefix(
+                vel_plan, vel_course, pp[vel_idx:, 3], pp[vel_idx:-1, 4], gg[vel_idx:, :], vk)
+            pref_idx = vel_idx + pref_idx_add
+
+            if action_id == "follow":                     # OTH:763-830
+                if closest_obj_index is None:
+                    obj_dist = 0.0
+                    c_obj_vel = 0.0
+                    c_obj_pos = None
+                else:
+                    c_obj_pos = obj_veh[closest_obj_index].pos
+                    c_obj_vel = obj_veh[closest_obj_index].vel
+                    s_obj, _ = get_s_coord(pp[:, 0:2], c_obj_pos, np.cumsum(pp[:, 4]))
+                    s_start, _ = get_s_coord(pp[:, 0:2], pos_est, np.cumsum(pp[:, 4]))
+                    obj_dist = s_obj - s_start
+                vx, too_close, vel_bound = self.calc_vel_profile_follow(
+                    kappa=pp[pref_idx:, 3], el_lengths=pp[pref_idx:, 4], loc_gg=gg[pref_idx:, :],
+                    v_start=vel_start, v_ego=vel_est, v_obj=c_obj_vel, safety_d=safety_d, obj_dist=obj_dist,
+                    obj_pos=c_obj_pos, vk=vk)
+                vx = np.concatenate((vel_course, vx))
+                if vx.shape[0] > s.shape[0]:
+                    vx = vx[0:len(s)]
+                bp_out = np.column_stack((s, pp[:, 0:4], vx))
+
+            if action_id != "follow" or (action_id == "follow" and red_len):   # OTH:834-923
+                end_node = end_node_in
+                num_el = len(pp[:, 4])
+                raceline_index = lt.raceline_index[end_node[0]]
+                raceline_offset = abs(end_node[1] - raceline_index) * lt.lat_offset      # quirk q3
+                if red_len:
+                    v_end = 0.0
+                    spl_len = np.sum(pp[:-1, 4])
+                    v_idx = np.argmin(np.cumsum(pp[:-1, 4]) < (spl_len - 5.0)) + 1
+                    if v_idx == 1 and num_el > 1:
+                        v_idx = num_el
+                else:
+                    v_end = lt.vel_raceline[end_node[0]]
+                    v_end -= min(v_end * lt.vel_decrease_lat * raceline_offset, v_end)
+                    v_idx = num_el
+                if v_idx - pref_idx > 1:
+                    vx = self.vp_calc_vel_profile(kappa=pp[pref_idx:v_idx, 3], el_lengths=pp[pref_idx:v_idx - 1, 4],
+                                                  loc_gg=gg[pref_idx:v_idx, :], v_start=vel_start, v_end=v_end,
+                                                  vk=vk)
+                else:
+                    vx = [0.0]
+                if v_idx != num_el or v_idx <= 2:
+                    vx = np.append(vx, [0.0] * (num_el - v_idx))
+                vel_bound = True
+                if not abs(vx[0] - vel_plan) < self.p['v_max_offset']:
+                    vel_bound = False
+                vx = np.concatenate((vel_course, vx))[:num_el]
+                if action_id != "follow":
+                    bp_out = np.column_stack((s, pp[:, 0:4], vx))
+                else:
+                    bp_out2 = np.column_stack((s, pp[:, 0:4], vx))
+                    bp_out = np.where(bp_out[5, :] < bp_out2[5, :], bp_out, bp_out2)     # quirk q1
+
+            vx_f = tph.conv_filt(signal=bp_out[:, 5], filt_window=self.p['filt_window_width'], closed=False)
+            ax_f = tph.calc_ax_profile(vx_profile=vx_f, el_lengths=np.diff(bp_out[:, 0]))
+            ax_f[np.logical_and(np.isclose(vx_f[:-1], 0.0), np.isclose(ax_f, 0.0))] = -5.0      # OTH:939
+            bp_out = np.column_stack((bp_out[:, :-1], vx_f, np.append(ax_f, [0.0])))
+
+        return bp_out, vel_bound
+
     # ----------------------------------------------------------------------------------------------------------------------
     # OTH.get_ref_idx + OTH.calc_vel_profile, first tick  (OTH:518-601, 603-1040)
     # ----------------------------------------------------------------------------------------------------------------------
@@ -727,73 +803,8 @@ class OracleLTPL(object):
             gg = np.ones((pp.shape[0], 2)) * tuple(local_gg)  # OTH:665-666
             out_ids[action_id] = traj_base_id + ACTION_ID_MAP.get(action_id, 9)
             red_len = res['red_len'][action_id][0]
-            bp_out = []
-            vel_bound = True
-            if np.size(pp, axis=0) > 0:
-                vel_idx = vel_course.shape[0]
-                s = np.concatenate(([0], np.cumsum(pp[:-1, 4])))                      # OTH:743
-                vx_prefix, pref_idx_add, vel_start = self.vp_check_brake_prefix(
-                    vel_plan, vel_course, pp[vel_idx:, 3], pp[vel_idx:-1, 4], gg[vel_idx:, :], vk)
-                pref_idx = vel_idx + pref_idx_add
-
-                if action_id == "follow":                     # OTH:763-830
-                    if closest_obj_index is None:
-                        obj_dist = 0.0
-                        c_obj_vel = 0.0
-                        c_obj_pos = None
-                    else:
-                        c_obj_pos = obj_veh[closest_obj_index].pos
-                        c_obj_vel = obj_veh[closest_obj_index].vel
-                        s_obj, _ = get_s_coord(pp[:, 0:2], c_obj_pos, np.cumsum(pp[:, 4]))
-                        s_start, _ = get_s_coord(pp[:, 0:2], pos_est, np.cumsum(pp[:, 4]))
-                        obj_dist = s_obj - s_start
-                    vx, too_close, vel_bound = self.calc_vel_profile_follow(
-                        kappa=pp[pref_idx:, 3], el_lengths=pp[pref_idx:, 4], loc_gg=gg[pref_idx:, :],
-                        v_start=vel_start, v_ego=vel_est, v_obj=c_obj_vel, safety_d=safety_d, obj_dist=obj_dist,
-                        obj_pos=c_obj_pos, vk=vk)
-                    vx = np.concatenate((vel_course, vx))
-                    if vx.shape[0] > s.shape[0]:
-                        vx = vx[0:len(s)]
-                    bp_out = np.column_stack((s, pp[:, 0:4], vx))
-
-                if action_id != "follow" or (action_id == "follow" and red_len):   # OTH:834-923
-                    end_node = res['nodes'][action_id][0][-1]
-                    num_el = len(pp[:, 4])
-                    raceline_index = lt.raceline_index[end_node[0]]
-                    raceline_offset = abs(end_node[1] - raceline_index) * lt.lat_offset      # quirk q3
-                    if red_len:
-                        v_end = 0.0
-                        spl_len = np.sum(pp[:-1, 4])
-                        v_idx = np.argmin(np.cumsum(pp[:-1, 4]) < (spl_len - 5.0)) + 1
-                        if v_idx == 1 and num_el > 1:
-                            v_idx = num_el
-                    else:
-                        v_end = lt.vel_raceline[end_node[0]]
-                        v_end -= min(v_end * lt.vel_decrease_lat * raceline_offset, v_end)
-                        v_idx = num_el
-                    if v_idx - pref_idx > 1:
-                        vx = self.vp_calc_vel_profile(kappa=pp[pref_idx:v_idx, 3], el_lengths=pp[pref_idx:v_idx - 1, 4],
-                                                      loc_gg=gg[pref_idx:v_idx, :], v_start=vel_start, v_end=v_end,
-                                                      vk=vk)
-                    else:
-                        vx = [0.0]
-                    if v_idx != num_el or v_idx <= 2:
-                        vx = np.append(vx, [0.0] * (num_el - v_idx))
-                    vel_bound = True
-                    if not abs(vx[0] - vel_plan) < self.p['v_max_offset']:
-                        vel_bound = False
-                    vx = np.concatenate((vel_course, vx))[:num_el]
-                    if action_id != "follow":
-                        bp_out = np.column_stack((s, pp[:, 0:4], vx))
-                    else:
-                        bp_out2 = np.column_stack((s, pp[:, 0:4], vx))
-                        bp_out = np.where(bp_out[5, :] < bp_out2[5, :], bp_out, bp_out2)     # quirk q1
-
-                vx_f = tph.conv_filt(signal=bp_out[:, 5], filt_window=self.p['filt_window_width'], closed=False)
-                ax_f = tph.calc_ax_profile(vx_profile=vx_f, el_lengths=np.diff(bp_out[:, 0]))
-                ax_f[np.logical_and(np.isclose(vx_f[:-1], 0.0), np.isclose(ax_f, 0.0))] = -5.0      # OTH:939
-                bp_out = np.column_stack((bp_out[:, :-1], vx_f, np.append(ax_f, [0.0])))
-
+            bp_out, vel_bound = self.vel_one(action_id, pp, gg, res['nodes'][action_id][0][-1], red_len, vel_plan,
+                                             vel_course, vel_est, closest_obj_index, obj_veh, pos_est, safety_d, vk)
             vel_bound_flags[action_id] = vel_bound
             # first tick: no backup plan exists (OTH:339-344) -> OTH:945-948 / 1007-1015
             if vel_bound or action_id in ["follow", "straight"]:

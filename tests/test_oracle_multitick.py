@@ -1,0 +1,58 @@
+"""Stateful (multi-tick) oracle, oracle/ltpl_session.py, against closed-loop sequences of the unmodified reference driven
+with a scripted clock (tests/golden/ticks_multitick_default.npz, oracle/gen_golden.py:multitick_fixture).
+Groundwork of SURVEY 8(f) rank 1: the CUDA path plans first ticks only."""
+import numpy as np
+
+from tests import helpers as H
+
+
+class _Clock(object):
+    def __init__(self):
+        self.t = 1000.0
+
+    def __call__(self):
+        return self.t
+
+
+def test_session_oracle_matches_reference_sequences():
+    from oracle.ltpl_oracle import OracleLTPL
+    from oracle.ltpl_session import OracleSession
+    g = H.golden("ticks_multitick_default.npz")
+    lat = H.lattice_for("default")
+    vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    n_seq, n_ticks = g["dt"].shape
+    compared = 0
+    for q in range(n_seq):
+        if int(g["n_done"][q]) == 0:
+            continue
+        clock = _Clock()
+        ses = OracleSession(OracleLTPL(lat), clock=clock)
+        assert ses.set_startpos(g["sc_pos"][q], g["sc_heading"][q], g["sc_vel"][q]) is False
+        n_obj = int(g["sc_n_obj"][q])
+        for k in range(int(g["n_done"][q])):
+            ctx = "sequence %d tick %d" % (q, k)
+            clock.t += float(g["dt"][q, k])
+            ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
+                   'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(g["obj"][q, k, :n_obj])]
+            sel = H.ACTIONS[int(g["sel"][q, k])]
+            paths = ses.calc_paths(sel, ol)
+            for a, act in enumerate(H.ACTIONS):
+                n_want = int(g["path_len"][q, k, a])
+                assert (act in paths) == (n_want > 0), "%s: path %s present=%s, golden %d" % (ctx, act, act in paths,
+                                                                                            n_want)
+                if n_want:
+                    assert paths[act][0].shape[0] == n_want, ctx + " path length " + act
+                    nd = [[-1 if v is None else int(v) for v in p] for p in ses.m_nodes[act][0]]
+                    assert nd == g["nodes"][q, k, a, :int(g["nodes_len"][q, k, a])].tolist(), ctx + " nodes " + act
+            traj, ids = ses.calc_vel_profile(g["pos_est"][q, k], float(g["vel_est"][q, k]), **vk)
+            for a, act in enumerate(H.ACTIONS):
+                t_want = int(g["traj_len"][q, k, a])
+                assert (act in traj) == (t_want > 0), "%s: trajectory %s present=%s, golden %d" % (ctx, act, act in traj,
+                                                                                                 t_want)
+                if t_want:
+                    # the id base (+10 per calc_vel_profile call, OTH:669) is instance state of the reference
+                    assert ids[act] % 10 == int(g["traj_id"][q, k, a]) % 10, ctx + " id " + act
+                    H.assert_close("traj[%s]" % act, traj[act][0], g["traj"][q, k, a, :t_want],
+                                   ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+                    compared += 1
+    assert compared > 150
