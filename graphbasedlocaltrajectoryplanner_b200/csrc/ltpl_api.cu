@@ -3,6 +3,7 @@
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
 #include <atomic>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -192,6 +193,12 @@ int ltpl_lattice_destroy(LtplLattice* lat) {
 static int check_common(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf) {
     if (!lat || !prm || !dm || !bf) return fail("null argument");
     if (dm->batch <= 0) return fail("dims.batch must be > 0");
+    {   // every buffer in front of the optional block (zones, emergency, predictions) is required
+        const void* const* ptr = reinterpret_cast<const void* const*>(bf);
+        for (size_t i = 0; i < offsetof(LtplBuffers, zone_bits) / sizeof(void*); ++i)
+            if (!ptr[i]) return fail("buffers: a required device pointer is NULL");
+    }
+    if (dm->h_max < 3 || dm->p0_max < 2 || dm->n_export < 1) return fail("dims: h_max >= 3, p0_max >= 2, n_export >= 1");
     if (dm->k_obj < 1 || dm->k_obj > LTPL_KMAX) return fail("dims.k_obj must be in [1, 16]");
     if (dm->p_max % 4 != 0 || dm->p_max < dm->p0_max) return fail("dims.p_max must be a multiple of 4 and >= p0_max");
     if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");

@@ -123,3 +123,38 @@ def test_single_scenario_facade_matches_config1_and_errors():
         ltpl.calc_paths(prev_action_id="straight", object_list=[])
         ltpl.calc_vel_profile(pos_est=g["sc_pos"][0], vel_est=0.0, vel_max=120.0)
     assert ltpl.set_startpos(pos_est=np.array([1e4, 1e4]), heading_est=0.0) is True      # out of track
+
+
+def test_c_abi_error_convention():
+    """entry points return < 0 and ltpl_last_error() names the problem; nothing is launched."""
+    import ctypes as C
+    from graphbasedlocaltrajectoryplanner_b200 import capi
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios
+    pl = _planner("l216")
+    pl.set_vel_params(**VEL)
+    pl.stage_scenarios(make_scenarios(Track(H.TRACK_CSV), 8, seed=1))
+    pl.upload()
+    pl.set_startpos()
+    n0 = pl.launch_count()
+    keep = pl.dims.batch
+    pl.dims.batch = 0
+    with pytest.raises(RuntimeError, match="batch"):
+        pl.tick()
+    pl.dims.batch = keep
+    keep_ptr = pl.buf.path
+    pl.buf.path = None
+    with pytest.raises(RuntimeError, match="NULL"):
+        pl.tick()
+    pl.buf.path = keep_ptr
+    pl.dims.n_zones = 1                                   # zones announced without bitmasks
+    keep_z = pl.buf.zone_bits
+    pl.buf.zone_bits = None
+    with pytest.raises(RuntimeError, match="zone"):
+        pl.calc_paths()
+    pl.buf.zone_bits = keep_z
+    pl.dims.n_zones = 0
+    assert pl.launch_count() == n0
+    rc = pl.lib.ltpl_tick_batch(None, C.byref(pl.params), C.byref(pl.dims), C.byref(pl.buf), pl.stream)
+    assert rc < 0 and b"null" in pl.lib.ltpl_last_error()
+    pl.tick()                                             # still usable afterwards
+    assert pl.launch_count() > n0
