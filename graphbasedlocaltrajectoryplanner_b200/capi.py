@@ -12,7 +12,7 @@ import os
 import subprocess
 import sys
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 NSLOT = 3
 KMAX = 16
 MAX_AXM = 32
@@ -22,7 +22,7 @@ ACTION_NAMES = {ACT_STRAIGHT: "straight", ACT_FOLLOW: "follow", ACT_LEFT: "left"
 
 ST_FOUND, ST_REDUCED_HORIZON, ST_TIE_AMBIGUOUS, ST_START_BLOCKED = 1, 2, 4, 8
 ST_TRAJ_VALID, ST_VEL_BOUND_VIOL, ST_TOO_CLOSE, ST_CONST_ONLY, ST_RENAMED_STRAIGHT = 16, 32, 64, 128, 256
-SC_OUT_OF_TRACK, SC_HEADING_MISMATCH, SC_CAPACITY, SC_BRAKE_PREFIX = 1, 2, 4, 8
+SC_OUT_OF_TRACK, SC_HEADING_MISMATCH, SC_CAPACITY, SC_BRAKE_PREFIX, SC_STATE_FALLBACK = 1, 2, 4, 8, 16
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
@@ -56,7 +56,8 @@ class Params(C.Structure):
                 ("dyn_model_exp", C.c_double), ("drag_coeff", C.c_double), ("m_veh", C.c_double),
                 ("vel_max", C.c_double), ("gg_scale", C.c_double), ("gg_ax", C.c_double), ("gg_ay", C.c_double),
                 ("safety_d", C.c_double), ("n_axm", C.c_int32), ("traj_base_id", C.c_int32),
-                ("incl_emerg_traj", C.c_int32), ("pad0", C.c_int32),
+                ("incl_emerg_traj", C.c_int32), ("pad0", C.c_int32), ("delaycomp", C.c_double),
+                ("w_last_edges", C.c_double * 4),
                 ("axm_v", C.c_double * MAX_AXM), ("axm_a", C.c_double * MAX_AXM), ("axm_s", C.c_double * MAX_AXM)]
 
 
@@ -69,7 +70,10 @@ BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags",
                  "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj", "cobj_start",
                  "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "vel_scratch", "s_vx_ax",
                  "vel_t", "traj", "traj_len", "traj_id", "zone_bits", "zone_sel", "em_info", "obj_pred",
-                 "n_pred")
+                 "n_pred", "prev_path", "prev_path_len", "prev_node_idx", "prev_nodes", "prev_n_nodes", "prev_coeff",
+                 "prev_s_vx_ax", "prev_action_id", "prev_traj_len", "prev_trim", "sel_action", "pos_last", "t_const",
+                 "st_info", "trim", "vel_plan", "course", "obj_dist")
+STATE_FIELDS = BUFFER_FIELDS[BUFFER_FIELDS.index("prev_path"):]   # NULL unless a stateful tick is planned
 
 
 class Buffers(C.Structure):
@@ -83,7 +87,7 @@ class VelBatch(C.Structure):
 
 EXPORTS = ("ltpl_version", "ltpl_last_error", "ltpl_sizeof", "ltpl_lattice_create", "ltpl_lattice_destroy",
            "ltpl_set_startpos_batch", "ltpl_calc_paths_batch", "ltpl_calc_vel_profile_batch", "ltpl_tick_batch",
-           "ltpl_velprofile_batch", "ltpl_launch_count", "ltpl_launch_stage")
+           "ltpl_velprofile_batch", "ltpl_launch_count", "ltpl_launch_stage", "ltpl_next_tick_batch")
 
 
 def build_library(verbose: bool = False) -> str:
@@ -126,7 +130,7 @@ def load_library():
     lib.ltpl_lattice_create.argtypes = [C.POINTER(LatticeHeader), C.c_void_p, C.POINTER(C.c_void_p)]
     lib.ltpl_lattice_destroy.argtypes = [C.c_void_p]
     for fn in (lib.ltpl_set_startpos_batch, lib.ltpl_calc_paths_batch, lib.ltpl_calc_vel_profile_batch,
-               lib.ltpl_tick_batch):
+               lib.ltpl_tick_batch, lib.ltpl_next_tick_batch):
         fn.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Dims), C.POINTER(Buffers), C.c_void_p]
         fn.restype = C.c_int
     lib.ltpl_launch_stage.argtypes = [C.c_int, C.c_void_p, C.POINTER(Params), C.POINTER(Dims), C.POINTER(Buffers),

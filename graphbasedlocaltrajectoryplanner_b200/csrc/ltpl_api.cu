@@ -22,6 +22,7 @@
 #include "ltpl_vel_tiled.cuh"
 #include "ltpl_vel_split.cuh"
 #include "ltpl_emerg.cuh"
+#include "ltpl_state.cuh"
 
 #ifndef LTPL_VEL_TILED
 #define LTPL_VEL_TILED 1   // 1: tile-streamed velocity kernel (ltpl_vel_tiled.cuh), 0: thread-per-path k_vel
@@ -37,7 +38,7 @@
 static std::atomic<unsigned long long> g_launches{0};
 
 static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
-                                cudaStream_t st) {
+                                cudaStream_t st, bool stateful = false) {
     const int nq = LTPL_NSLOT * dm->batch;
 #if LTPL_VEL_TILED && LTPL_VEL_SPLIT
     // follow groups get three CTAs each (<= B follow paths: slot 0 only), every other group one
@@ -48,11 +49,16 @@ static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, c
 #elif LTPL_VEL_TILED
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_vel_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(k_vel_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_vel_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_vel_tiled<<<nq / VT_P + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
+    if (stateful)
+        k_vel_tiled<true><<<nq / VT_P + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
+    else
+        k_vel_tiled<false><<<nq / VT_P + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
 #else
     k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
 #endif
@@ -237,7 +243,7 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
         attr_plan = smem_plan;
     }
     if (smem_path > 48 * 1024 && smem_path > attr_path) {
-        if (cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
+        if (cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
             return fail("cudaFuncSetAttribute(k_path) failed");
         attr_path = smem_path;
     }
@@ -250,7 +256,7 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
     if (int r = check_launch("k_plan")) return r;
     const int nq = LTPL_NSLOT * dm->batch;
     const int grid_path = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    k_path<<<grid_path, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
+    k_path<false><<<grid_path, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
     return check_launch("k_path");
 }
 
@@ -293,6 +299,61 @@ int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDim
     return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
 }
 
+// stateful tick (EXPERIMENTAL, ltpl_state.cuh): k_state -> k_plan<.., true> -> k_path<true> -> k_ref -> k_vel_tiled<true>
+// -> k_prefix -> k_export
+int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                         void* stream) {
+    if (int r = check_common(lat, prm, dm, bf)) return r;
+    if (!bf->prev_path || !bf->prev_path_len || !bf->prev_node_idx || !bf->prev_nodes || !bf->prev_n_nodes ||
+        !bf->prev_coeff || !bf->prev_s_vx_ax || !bf->prev_action_id || !bf->prev_traj_len || !bf->prev_trim ||
+        !bf->sel_action || !bf->pos_last || !bf->t_const || !bf->st_info || !bf->trim || !bf->vel_plan || !bf->course ||
+        !bf->obj_dist)
+        return fail("ltpl_next_tick_batch: the stateful buffers (prev_*, sel_action, pos_last, t_const, st_info, trim, "
+                    "vel_plan, course, obj_dist) must be set");
+    if (bf->vel != bf->vel_plan) return fail("ltpl_next_tick_batch: buffers.vel must point at buffers.vel_plan");
+    if (dm->n_zones > 0 || prm->incl_emerg_traj)
+        return fail("ltpl_next_tick_batch: zones and the emergency trajectory are not part of the stateful tick yet");
+    if (prm->delaycomp <= 0.0) return fail("params.delaycomp must be > 0");
+#if !LTPL_VEL_TILED || LTPL_VEL_SPLIT
+    return fail("ltpl_next_tick_batch needs the default velocity kernel (LTPL_VEL_TILED=1, LTPL_VEL_SPLIT=0)");
+#else
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
+    const int hl = dm->h_max;
+    const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
+    const size_t smem_plan = plan_smem_bytes_per_warp(maxn, hl, mask_words) * LTPL_WARPS_PER_CTA;
+    const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
+    if (smem_plan > 200 * 1024 || smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
+    if (smem_plan > 48 * 1024 &&
+        cudaFuncSetAttribute(k_plan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
+            cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_plan) failed");
+    if (smem_path > 48 * 1024 &&
+        cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(k_path) failed");
+    if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
+    const int grid_b = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    const int nq = LTPL_NSLOT * dm->batch;
+    const int grid_q = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    k_state<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
+    if (int r = check_launch("k_state")) return r;
+    k_plan<false, true><<<grid_b, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    if (int r = check_launch("k_plan")) return r;
+    k_path<true><<<grid_q, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
+    if (int r = check_launch("k_path")) return r;
+    k_ref<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
+    if (int r = check_launch("k_ref")) return r;
+    if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
+    if (launch_k_vel(lat, prm, dm, bf, st, true) != cudaSuccess) return fail("k_vel: cudaFuncSetAttribute failed");
+    if (int r = check_launch("k_vel")) return r;
+    k_prefix<<<grid_q, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*dm, *bf);
+    if (int r = check_launch("k_prefix")) return r;
+    k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
+        *dm, *bf);
+    return check_launch("k_export");
+#endif
+}
+
 int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,
                       const LtplBuffers* bf, void* stream) {
     if (int r = check_common(lat, prm, dm, bf)) return r;
@@ -321,10 +382,10 @@ int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, 
                 return check_launch("k_plan");
             }
             if (smem_path > 48 * 1024)
-                cudaFuncSetAttribute(k_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path);
+                cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path);
             if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess)
                 return fail("memset(queue_cnt) failed");
-            k_path<<<(nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(
+            k_path<false><<<(nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(
                 lat->d, *prm, *dm, *bf);
             return check_launch("k_path");
         }

@@ -22,6 +22,8 @@ __device__ __forceinline__ void enqueue_path(const LtplBuffers& bf, const LtplDi
 #ifndef LTPL_PATH_MINB
 #define LTPL_PATH_MINB 8
 #endif
+// STATE: stateful tick (ltpl_state.cuh): the constant part and the list prefixes come from the previous tick's buffers
+template <bool STATE>
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32, LTPL_PATH_MINB)
 k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -48,23 +50,42 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     int* nsamp = eid + H;
 
     const int p0 = bf.const_len[b];
-    const size_t cplane = (size_t)B * dm.p0_max;
-    const double* cs = bf.const_seg + (size_t)b * dm.p0_max;
     const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
+    size_t cplane = (size_t)B * dm.p0_max;
+    const double* cs = bf.const_seg + (size_t)b * dm.p0_max;
+    int cnd = 1;                       // list entries in front of the start node
+    const int* mem_ni = nullptr;       // memory node index list (trimmed at L) and its offset m
+    const double* mem_cf = nullptr;
+    int mem_m = 0, mem_rows = 0;
+    if (STATE) {
+        const int* sinfo = bf.st_info + 8 * (size_t)b;
+        cplane = pplane;
+        cs = bf.prev_path + (size_t)sinfo[0] * dm.p_max + sinfo[1];
+        cnd = sinfo[3];
+        mem_m = sinfo[1];
+        mem_ni = bf.prev_node_idx + (size_t)sinfo[0] * dm.h_max + sinfo[2];
+        mem_cf = bf.prev_coeff + ((size_t)sinfo[0] * dm.h_max + sinfo[2]) * 8;
+        mem_rows = bf.prev_n_nodes[sinfo[0]] - sinfo[2] - 1;   // coefficient rows of the memory
+    }
     double* pp = bf.path + (size_t)q * dm.p_max;
     int* node_idx = bf.node_idx + (size_t)q * H;
     double* coeff = bf.coeff + (size_t)q * H * 8;
 
     const int n_nodes = bf.n_nodes[q];  // incl. the leading (-1, -1)
-    const int nseg = n_nodes - 2;       // segments of the new plan
+    const int nseg = n_nodes - 1 - cnd; // segments of the new plan
 
     if (st & LTPL_ST_CONST_ONLY) {  // OTH:481-506: constant segment incl. its last point
         for (int k = lane; k < p0; k += 32)
             for (int c = 0; c < 5; ++c) pp[c * pplane + k] = cs[c * cplane + k];
         if (lane == 0) {
-            node_idx[0] = 0;
-            node_idx[1] = p0 - 1;
-            for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
+            if (STATE) {   // OTH:486-501: memory lists up to and including the start node
+                for (int i = 0; i < cnd; ++i) node_idx[i] = mem_ni[i] - mem_m;
+                for (int i = 0; i < min(cnd + 1, mem_rows) * 8; ++i) coeff[i] = mem_cf[i];
+            } else {
+                node_idx[0] = 0;
+                for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
+            }
+            node_idx[cnd] = p0 - 1;
             bf.path_len[q] = p0;
             enqueue_path(bf, dm, q);
         }
@@ -168,10 +189,16 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     __syncwarp();
 
     // ---- stitched bookkeeping (OTH:458-472) ----
-    for (int i = lane; i <= nseg; i += 32) node_idx[1 + i] = nidx[i] + loc;
+    for (int i = lane; i <= nseg; i += 32) node_idx[cnd + i] = nidx[i] + loc;
+    if (STATE) {
+        for (int i = lane; i < cnd; i += 32) node_idx[i] = mem_ni[i] - mem_m;
+        for (int i = lane; i < cnd * 8; i += 32) coeff[i] = mem_cf[i];
+    }
     if (lane == 0) {
-        node_idx[0] = 0;
-        for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
+        if (!STATE) {
+            node_idx[0] = 0;
+            for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
+        }
         bf.path_len[q] = p_tot;
         enqueue_path(bf, dm, q);
     }
@@ -180,7 +207,7 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         const double dx = kx[i + 1] - kx[i], dy = ky[i + 1] - ky[i];
         const double a1x = e0 * mx[i], e1x = e0 * mx[i + 1];
         const double a1y = e0 * my[i], e1y = e0 * my[i + 1];
-        double* c = coeff + (size_t)(1 + i) * 8;
+        double* c = coeff + (size_t)(cnd + i) * 8;
         c[0] = kx[i]; c[1] = a1x; c[2] = 3 * dx - 2 * a1x - e1x; c[3] = -2 * dx + a1x + e1x;
         c[4] = ky[i]; c[5] = a1y; c[6] = 3 * dy - 2 * a1y - e1y; c[7] = -2 * dy + a1y + e1y;
     }

@@ -153,6 +153,8 @@ struct DpCtx {
     int tie;             // an equal-cost alternative was seen (igraph's pick then depends on heap order)
     int snap_li;         // step whose result dsave holds (0: no snapshot)
     int tie_save;        // tie flag at the snapshot
+    int fe0, fe1, fe2;   // stateful tick: edges of the last solution whose cost is scaled (GLNT:155-162), -1: none
+    double ff0, ff1, ff2;
 };
 
 // planning range (GLNT:104-142): layer the plan has to reach from start_layer
@@ -205,7 +207,7 @@ __device__ __forceinline__ bool zone_unblocked(int l, int s0, int L) {
 // li_begin are those of the run that took the snapshot).  After step snap_at the state is saved to c.dsave.
 // Each lane owns one node of the next layer and scans its in-edges IN CSC ORDER, which keeps igraph's relaxation order
 // and tie rule (strict <, then smaller dist[src]) bit for bit.
-template <bool ZONE>
+template <bool ZONE, bool COSTF = false>
 __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int start_layer, int start_node, int n_steps,
                                       const unsigned* mask, int e_base, int rem_layer, int rem_lo, int rem_hi,
                                       int li_begin, int snap_at, const unsigned* zone) {
@@ -253,7 +255,13 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
                         const int idx = e + moff;
                         if ((mask[idx >> 5] >> (idx & 31)) & 1u) continue;
                     }
-                    const double alt = __dadd_rn(ds, r.cost);
+                    double cost = r.cost;
+                    if (COSTF) {   // offline_cost *= factor on this tick's copy of the planning range (GB:505-508)
+                        if (e == c.fe0) cost = __dmul_rn(cost, c.ff0);
+                        else if (e == c.fe1) cost = __dmul_rn(cost, c.ff1);
+                        else if (e == c.fe2) cost = __dmul_rn(cost, c.ff2);
+                    }
+                    const double alt = __dadd_rn(ds, cost);
                     if (alt < best || (alt == best && ds < best_ds)) {
                         best = alt;
                         best_ds = ds;
@@ -415,7 +423,10 @@ __device__ __forceinline__ int disc_pairs(const LatDev& lt, int lane, double ox,
 #ifndef LTPL_PLAN_MINB
 #define LTPL_PLAN_MINB 10  // resident CTAs per SM the register allocation is held to (occupancy hides the L1/L2 latency)
 #endif
-template <bool ZONE>
+// STATE: stateful tick (ltpl_state.cuh): start node / constant segment come from k_state, the constant segment lives in
+// the previous tick's path planes, pos_est and the last action id enter the action-set logic, the first edges of the
+// last solution are cheaper
+template <bool ZONE, bool STATE = false>
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32, LTPL_PLAN_MINB)
 k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf, const int maxn, const int hl,
        const int mask_words) {
@@ -452,8 +463,15 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
 
     const int start_layer = bf.start_node[2 * b], start_node = bf.start_node[2 * b + 1];
     const int p0 = bf.const_len[b];
-    const size_t cplane = (size_t)B * dm.p0_max;
+    size_t cplane = (size_t)B * dm.p0_max;
     const double* cs = bf.const_seg + (size_t)b * dm.p0_max;
+    int cnd = 1;   // entries of the node / node-index / coefficient lists in front of the start node
+    if (STATE) {
+        const int* sinfo = bf.st_info + 8 * (size_t)b;
+        cplane = (size_t)LTPL_NSLOT * B * dm.p_max;
+        cs = bf.prev_path + (size_t)sinfo[0] * dm.p_max + sinfo[1];
+        cnd = sinfo[3];
+    }
 
     // ---- OLI.process_object_list (OLI:96-141): drop off-track objects, radius = length / 2, prediction points: the
     // caller's 'prediction' array (OLI:117-119) or one constant-velocity point at 0.2 s (OLI:121-127) ----
@@ -519,7 +537,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     const int end_layer = plan_end_layer(lt, start_layer, lane);
     int planning_dist = end_layer - start_layer;
     if (planning_dist < 0) planning_dist = lt.L - start_layer + end_layer;
-    if (end_layer >= lt.L || planning_dist + 1 > hl || planning_dist + 2 > dm.h_max) {
+    if (end_layer >= lt.L || planning_dist + 1 > hl || planning_dist + 1 + cnd > dm.h_max) {
         if (lane == 0) bf.sc_flags[b] = LTPL_SC_CAPACITY;
         return;
     }
@@ -576,7 +594,8 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     // ---- objects in / beside the constant path segment (MOPG:76-122) ----
     bool obj_in_const = false, obj_beside = false;
     if (p0 >= 2) {
-        const double sx0 = cs[0], sy0 = cs[cplane];                        // pos_est is None on the first tick
+        // MOPG:80-84: pos_est of the previous calc_vel_profile call; None on the first tick -> first point of the segment
+        const double sx0 = STATE ? bf.pos_last[2 * b] : cs[0], sy0 = STATE ? bf.pos_last[2 * b + 1] : cs[cplane];
         const double sxe = cs[p0 - 1], sye = cs[cplane + p0 - 1];
         const double s_start = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sx0, sy0, lane, nullptr, nullptr);
         const double s_end = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sxe, sye, lane, nullptr, nullptr);
@@ -634,7 +653,12 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         n_act = 1;
         names[0] = LTPL_ACT_FOLLOW;
         filt[0] = 0;
-        if (!obj_in_const) {  // last_action_id is the forced "straight" on the first tick -> offer left and right
+        const int last_act = STATE ? bf.sel_action[b] : LTPL_ACT_STRAIGHT;
+        if (!obj_in_const && (last_act == LTPL_ACT_LEFT || last_act == LTPL_ACT_RIGHT)) {   // MOPG:130-133: keep overtaking
+            names[1] = last_act;
+            filt[1] = 1;
+            n_act = 2;
+        } else if (!obj_in_const) {  // last_action_id is the forced "straight" on the first tick -> offer left and right
             names[1] = LTPL_ACT_LEFT;  filt[1] = 1;
             names[2] = LTPL_ACT_RIGHT; filt[2] = 1;
             n_act = 3;
@@ -675,6 +699,19 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     c.maxn = maxn;
     c.snap_li = 0;
     c.tie_save = 0;
+    c.fe0 = c.fe1 = c.fe2 = -1;
+    c.ff0 = c.ff1 = c.ff2 = 1.0;
+    int n_fe = 0;
+    if (STATE) {
+        const int* sinfo = bf.st_info + 8 * (size_t)b;
+        n_fe = sinfo[4];
+        c.fe0 = sinfo[5];
+        c.fe1 = sinfo[6];
+        c.fe2 = sinfo[7];
+        c.ff0 = prm.w_last_edges[0];
+        c.ff1 = prm.w_last_edges[1];
+        c.ff2 = prm.w_last_edges[2];
+    }
     const int goal_steps = planning_dist;
     const int tab_row = lt.node_off[start_layer] + start_node;
     int mod_steps = goal_steps;
@@ -698,6 +735,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         const int tr = lt.tab_reach[tab_row];
         if (src == 0 && (tr & 0xff) > mod_steps) src = 1;  // table rows end at their own goal layer (open track only)
         if (ZONE && src == 0 && zone) src = 1;              // the table holds searches on the zone-free lattice
+        if (STATE && src == 0 && n_fe > 0) src = 1;         // ... with the offline costs
         int st = 0, tie = 0, found = 0, reach = 0;
         if (mod_steps > 0) {
             const bool start_removed = (rem_layer == start_layer && start_node >= rem_lo && start_node < rem_hi);
@@ -711,7 +749,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             } else {
                 const int li_begin = (f == 3 && c.snap_li >= 1) ? c.snap_li + 1 : 1;
                 const int snap_at = (f == 2 && a + 1 < n_act && filt[a + 1] == 3) ? closest_dist - 1 : 0;
-                reach = dp_run<ZONE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
+                reach = dp_run<ZONE, STATE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
                                rem_layer, rem_lo, rem_hi, li_begin, snap_at, zone);
                 tie = c.tie;
             }
@@ -750,15 +788,15 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             for (int li = 1 + lane; li <= reach; li += 32) {
                 int layer = start_layer + li;
                 if (layer >= lt.L) layer -= lt.L;
-                nd[2 * (li + 1)] = layer;
-                nd[2 * (li + 1) + 1] = tn[li - 1];
+                nd[2 * (li + cnd)] = layer;
+                nd[2 * (li + cnd) + 1] = tn[li - 1];
                 es[li - 1] = te[li - 1];
             }
         } else if (found && src == 2) {  // copy of the previous action's plan
             const int* pn = bf.nodes + (size_t)prev_q * dm.h_max * 2;
             const int* pe = bf.edge_seq + (size_t)prev_q * dm.h_max;
             #pragma unroll 1
-            for (int i = lane; i < 2 * (reach + 2); i += 32) nd[i] = pn[i];
+            for (int i = lane; i < 2 * (reach + 1 + cnd); i += 32) nd[i] = pn[i];
             #pragma unroll 1
             for (int i = lane; i < reach; i += 32) es[i] = pe[i];
             st |= bf.status[prev_q] & LTPL_ST_TIE_AMBIGUOUS;
@@ -768,24 +806,31 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             if (src == 1) gj = dp_goal(lt, lane, c, &tie);
             if (tie) st |= LTPL_ST_TIE_AMBIGUOUS;
             st |= LTPL_ST_FOUND;
+            if (STATE && src != 2) {   // constant nodes in front of the start node: the memory of the last tick (OTH:462-466)
+                const int* sinfo = bf.st_info + 8 * (size_t)b;
+                const int* pn = bf.prev_nodes + ((size_t)sinfo[0] * dm.h_max + sinfo[2]) * 2;
+                for (int i = lane; i < 2 * cnd; i += 32) nd[i] = pn[i];
+            }
             if (lane == 0) {
-                nd[0] = -1;
-                nd[1] = -1;
-                nd[2] = start_layer;
-                nd[3] = start_node;
+                if (!STATE) {
+                    nd[0] = -1;
+                    nd[1] = -1;
+                }
+                nd[2 * cnd] = start_layer;
+                nd[2 * cnd + 1] = start_node;
                 if (src == 1) {
                     int j = gj, layer = c.layer;
                     #pragma unroll 1
                     for (int li = reach; li >= 1; --li) {
-                        nd[2 * (li + 1)] = layer;
-                        nd[2 * (li + 1) + 1] = j;
+                        nd[2 * (li + cnd)] = layer;
+                        nd[2 * (li + cnd) + 1] = j;
                         const int e = lt.in_off[lt.node_off[layer] + j].x + (int)pred[li * maxn + j];
                         es[li - 1] = e;
                         j = lt.edge_src[e];
                         layer = (layer == 0) ? lt.L - 1 : layer - 1;
                     }
                 }
-                bf.n_nodes[q] = reach + 2;
+                bf.n_nodes[q] = reach + 1 + cnd;
                 bf.action_id[q] = name;
                 bf.status[q] = st;
             }
@@ -806,8 +851,17 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         if (!any && p0 > 2) {
             const int q = b;
             int* nd = bf.nodes + (size_t)q * dm.h_max * 2;
-            nd[0] = -1; nd[1] = -1; nd[2] = start_layer; nd[3] = start_node;
-            bf.n_nodes[q] = 2;
+            if (STATE) {
+                const int* sinfo = bf.st_info + 8 * (size_t)b;
+                const int* pn = bf.prev_nodes + ((size_t)sinfo[0] * dm.h_max + sinfo[2]) * 2;
+                for (int i = 0; i < 2 * cnd; ++i) nd[i] = pn[i];
+            } else {
+                nd[0] = -1;
+                nd[1] = -1;
+            }
+            nd[2 * cnd] = start_layer;
+            nd[2 * cnd + 1] = start_node;
+            bf.n_nodes[q] = cnd + 1;
             bf.action_id[q] = LTPL_ACT_STRAIGHT;
             bf.status[q] = LTPL_ST_FOUND | LTPL_ST_CONST_ONLY | LTPL_ST_REDUCED_HORIZON;
         }

@@ -16,9 +16,9 @@
 #include "ltpl_vel_tiled.cuh"
 
 #define VS_NTILES 4                      // k_vel_sweeps: kappa, el, w, curvature limit (pass A: kappa, el, x -> s, y -> brake)
-#define VS_SMEM_BYTES (VS_NTILES * VT_TILE * 8 + 2 * VT_P * 4)
+#define VS_SMEM_BYTES (VS_NTILES * VT_TILE * 8 + 2 * VT_P * 4 + 2 * VT_P * 8)
 #define VO_NTILES 7                      // k_vel_out
-#define VO_SMEM_BYTES (VO_NTILES * VT_TILE * 8 + 2 * VT_P * 4)
+#define VO_SMEM_BYTES (VO_NTILES * VT_TILE * 8 + 2 * VT_P * 4 + 2 * VT_P * 8)
 #ifndef VS_MINB
 #define VS_MINB 20                      // resident one-warp CTAs per SM the register allocation of k_vel_sweeps is held to
 #endif
@@ -61,6 +61,8 @@ __device__ __forceinline__ bool vel_group_init(VelGroup& G, const LtplParams& pr
     if (G.role == 0) {
         qs[G.pl] = (G.n > 0) ? G.q : -1;
         ns[G.pl] = G.n;
+        long long* base = reinterpret_cast<long long*>(ns + VT_P);   // in_base | out_base (first ticks: q * p_max)
+        base[G.pl] = base[VT_P + G.pl] = (long long)max(G.q, 0) * dm.p_max;
     }
     __syncwarp();
     int np = G.n;
@@ -263,6 +265,8 @@ k_vel_sweeps(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltp
     w.col0 = g * VT_P;
     w.qs = qs;
     w.ns = ns;
+    w.in_base = reinterpret_cast<const long long*>(ns + VT_P);
+    w.out_base = w.in_base + VT_P;
     const size_t pplane = (size_t)G.nq * dm.p_max;
     const double* x_pl = bf.path;
     const double* y_pl = bf.path + pplane;
@@ -576,6 +580,8 @@ k_vel_out(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     w.col0 = g * VT_P;
     w.qs = qs;
     w.ns = ns;
+    w.in_base = reinterpret_cast<const long long*>(ns + VT_P);
+    w.out_base = w.in_base + VT_P;
     const size_t pplane = (size_t)G.nq * dm.p_max;
     const size_t tsz = (size_t)dm.p_max * w.ntc;
     const double* T_S = bf.vel_t;

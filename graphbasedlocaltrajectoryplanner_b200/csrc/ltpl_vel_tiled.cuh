@@ -29,7 +29,7 @@
 #define VT_PRAGMA_UNROLL(n) VT_PRAGMA_(unroll n)
 #define VT_TILE (32 * VT_W)          // doubles per tile
 #define VT_NTILES 6                  // tiles per warp
-#define VT_SMEM_BYTES (VT_NTILES * VT_TILE * 8 + 2 * VT_P * 4)
+#define VT_SMEM_BYTES (VT_NTILES * VT_TILE * 8 + 2 * VT_P * 4 + 2 * VT_P * 8)
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -47,6 +47,10 @@ struct WarpCtx {
     int col0;         // first column of this warp
     const int* qs;    // smem[VT_P] path id (-1 = idle slot)
     const int* ns;    // smem[VT_P] points per path (0 = idle slot)
+    // smem[VT_P] element offset of point 0 of a path inside a row-major plane: q * p_max (+ the cut index of a stateful
+    // tick, ltpl_state.cuh) for the INPUT planes, q * p_max (+ the vel_course rows) for the OUTPUT planes
+    const long long* in_base;
+    const long long* out_base;
 };
 
 // tile[k][r] = row_r[p0 + k] for the warp's VT_P paths (row-major per-path array `plane`); lanes = 32 points
@@ -54,14 +58,14 @@ __device__ __forceinline__ void tile_load_rows(const WarpCtx& w, double* tile, c
 VT_PRAGMA_UNROLL(VT_UNROLL)
     for (int r = 0; r < VT_P; ++r) {
         if (p0 + w.lane < w.ns[r])
-            cp_async8(&tile[w.lane * VT_W + r], plane + (size_t)w.qs[r] * w.p_max + p0 + w.lane);
+            cp_async8(&tile[w.lane * VT_W + r], plane + w.in_base[r] + p0 + w.lane);
     }
 }
 // row_r[p0 + k] = tile[k][r]
 __device__ __forceinline__ void tile_store_rows(const WarpCtx& w, const double* tile, double* plane, int p0) {
 VT_PRAGMA_UNROLL(VT_UNROLL)
     for (int r = 0; r < VT_P; ++r) {
-        if (p0 + w.lane < w.ns[r]) plane[(size_t)w.qs[r] * w.p_max + p0 + w.lane] = tile[w.lane * VT_W + r];
+        if (p0 + w.lane < w.ns[r]) plane[w.out_base[r] + p0 + w.lane] = tile[w.lane * VT_W + r];
     }
 }
 // transposed scratch <-> tile: 32 rows x VT_P columns, element e = it * 32 + lane -> (row e / VT_P, column e % VT_P)
@@ -326,12 +330,17 @@ __device__ __forceinline__ double profile_sweeps(const WarpCtx& w, double* tiles
     return first;
 }
 
+// STATE: stateful tick (ltpl_state.cuh) -- every path starts at its cut index + the vel_course rows (bf.trim), the planned
+// velocity comes from bf.vel (pointed at vel_plan by the host), the follow-mode object distance from bf.obj_dist (k_ref)
+template <bool STATE>
 __global__ void __launch_bounds__(32)
 k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     extern __shared__ __align__(16) unsigned char vt_smem[];
     double* tiles = reinterpret_cast<double*>(vt_smem);
     int* qs = reinterpret_cast<int*>(tiles + VT_NTILES * VT_TILE);
     int* ns = qs + VT_P;
+    long long* in_base = reinterpret_cast<long long*>(ns + VT_P);
+    long long* out_base = in_base + VT_P;
     __shared__ double s_axm[3 * LTPL_MAX_AXM];
     __shared__ double sp_wcapc[VT_P], sp_wnx[VT_P], sp_snx[VT_P];   // per path slot: final-pass parameters
     __shared__ int sp_idx_c[VT_P], sp_stop[VT_P], sp_mode[VT_P];
@@ -354,6 +363,12 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     int st = live ? bf.status[q] : 0;
     const int action = live ? bf.action_id[q] : LTPL_ACT_NONE;
     int n = live ? bf.path_len[q] : 0;
+    int off_in = 0, pref = 0;
+    if (STATE && live) {
+        pref = bf.trim[4 * q + 3];
+        off_in = bf.trim[4 * q + 2] + pref;
+        n = max(n - off_in, 0);
+    }
     const double vel_plan = live ? bf.vel[b] : 0.0;
     bool prefix = false;
     if (live && vel_plan > prm.vel_max + 0.1) {  // VPFB:106 brake prefix: the reference raises (see header)
@@ -364,6 +379,8 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     if (role == 0) {
         qs[pl] = (n > 0) ? q : -1;
         ns[pl] = n;
+        in_base[pl] = (long long)max(q, 0) * dm.p_max + off_in;
+        out_base[pl] = (long long)max(q, 0) * dm.p_max + pref;
     }
     __syncwarp();
     int np = n;
@@ -379,6 +396,8 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     w.col0 = wid * VT_P;
     w.qs = qs;
     w.ns = ns;
+    w.in_base = in_base;
+    w.out_base = out_base;
     const size_t pplane = (size_t)nq * dm.p_max;
     const double* x_pl = bf.path;
     const double* y_pl = bf.path + pplane;
@@ -464,7 +483,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
                     }
                 }
             }
-        } else if (role == 1 && follow_cls) {
+        } else if (role == 1 && follow_cls && !STATE) {
 #pragma unroll 1
             for (int k = 0; k < 32; ++k) {
                 const int p = p0 + k;
@@ -507,7 +526,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     const double v_start_f = vel_plan;
     {
         double s_mine = 0.0;
-        if (follow_cls && compute && n > 0) {   // role 0: s of the object, role 1: s of the ego position
+        if (!STATE && follow_cls && compute && n > 0) {   // role 0: s of the object, role 1: s of the ego position
             const double* xr = x_pl + (size_t)q * dm.p_max;
             const double* yr = y_pl + (size_t)q * dm.p_max;
             const double* er = e_pl + (size_t)q * dm.p_max;
@@ -516,7 +535,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         const double s_obj = __shfl_sync(LTPL_FULL, s_mine, pl);
         const double s_start = __shfl_sync(LTPL_FULL, s_mine, partner);
         if (follow_cls && compute && n > 0) {
-            const double obj_dist = s_obj - s_start;   // OTH:784
+            const double obj_dist = STATE ? bf.obj_dist[b] : (s_obj - s_start);   // OTH:784
             const double v_ego = bf.vel_est[b];
             const double control_d = prm.follow_c_p * prm.safety_d + lt.veh_length;
             const double safety_d = prm.safety_d + lt.veh_length;

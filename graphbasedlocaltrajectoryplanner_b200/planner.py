@@ -56,7 +56,7 @@ class BatchPlanner(object):
 
     def __init__(self, lattice: Lattice = None, online: dict = None, device=None, veh_param_dyn_model_exp: float = 1.0,
                  veh_param_dragcoeff: float = 0.85, veh_param_mass: float = 1000.0, packed: tuple = None,
-                 blob_tensor: torch.Tensor = None):
+                 blob_tensor: torch.Tensor = None, stateful: bool = False):
         """``packed`` = (LatticeHeader, capacities) + ``blob_tensor`` (device uint8) when the blob arrived through a
         collective instead of being uploaded from ``lattice`` (parallel.broadcast_lattice)."""
         self.lib = capi.load_library()
@@ -80,6 +80,8 @@ class BatchPlanner(object):
             if self.blob.device != self.device or self.blob.dtype != torch.uint8 \
                     or self.blob.numel() != self.header.blob_bytes:
                 raise ValueError("blob tensor does not match the lattice header")
+        if stateful:   # stateful ticks carry constant nodes / points of earlier ticks in front of the new plan
+            self.cap = dict(self.cap, h_max=self.cap["h_max"] + 8, p_max=self.cap["p_max"] + 96)
         handle = C.c_void_p()
         capi.check(self.lib, self.lib.ltpl_lattice_create(C.byref(self.header), C.c_void_p(self.blob.data_ptr()),
                                                           C.byref(handle)), "ltpl_lattice_create")
@@ -133,6 +135,9 @@ class BatchPlanner(object):
         p.dyn_model_exp, p.drag_coeff, p.m_veh = self.veh["dyn_model_exp"], self.veh["drag_coeff"], self.veh["m_veh"]
         p.vel_max, p.gg_scale, p.gg_ax, p.gg_ay, p.safety_d = vel_max, gg_scale, local_gg[0], local_gg[1], safety_d
         p.n_axm = axm.shape[0]
+        p.delaycomp = float(o.get("delaycomp", 0.1))
+        for i in range(3):
+            p.w_last_edges[i] = float(o["w_last_edges"][i]) if i < len(o["w_last_edges"]) else 1.0
         p.incl_emerg_traj = 1 if incl_emerg_traj else 0
         for i in range(axm.shape[0]):
             p.axm_v[i] = axm[i, 0]
@@ -198,8 +203,10 @@ class BatchPlanner(object):
         d.k_pred = 0
         d.n_zones, d.n_zone_words = 0, (self.lattice_nodes + 31) // 32
         for name in capi.BUFFER_FIELDS:
-            setattr(buf, name, t[name].data_ptr())
+            if name not in capi.STATE_FIELDS:
+                setattr(buf, name, t[name].data_ptr())
         self.t, self.buf, self.dims = t, buf, d
+        self._state = None   # buffers of the stateful tick, allocated by next_tick()
         # further compact export buffers: the pipelined stream planner lets the D2H of step i overlap step i + 1
         self.traj_bufs = [t["traj"]] + [z(((NSLOT + 1) * B, NE, 7), f32) for _ in range(self.N_SETS - 1)]
         # pinned host staging for the per-tick host <-> device copies (N_SETS sets for the pipelined path)
@@ -368,6 +375,8 @@ class BatchPlanner(object):
         self._call(self.lib.ltpl_set_startpos_batch, "ltpl_set_startpos_batch")
 
     def calc_paths(self) -> None:
+        if self._state is not None:
+            self.t["trim"].zero_()   # a first tick exports from point 0
         self._call(self.lib.ltpl_calc_paths_batch, "ltpl_calc_paths_batch")
 
     def calc_vel_profile(self) -> None:
@@ -377,9 +386,64 @@ class BatchPlanner(object):
 
     def tick(self) -> None:
         """calc_paths + calc_vel_profile back to back."""
+        if self._state is not None:
+            self.t["trim"].zero_()   # a first tick exports from point 0
         self._tick_count += 1
         self.params.traj_base_id = 10 * self._tick_count
         self._call(self.lib.ltpl_tick_batch, "ltpl_tick_batch")
+
+    # -- stateful tick (EXPERIMENTAL: DESIGN.md section 11, csrc/ltpl_state.cuh) ----------------------------------------------
+    _BIG = ("path", "node_idx", "nodes", "coeff", "s_vx_ax")          # swapped by pointer
+    _SMALL = ("path_len", "n_nodes", "action_id", "traj_len", "trim")  # copied (a few bytes per path)
+
+    def _alloc_state(self) -> None:
+        dev, B = self.device, self.dims.batch
+        f64, i32 = torch.float64, torch.int32
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
+        t = self.t
+        st = dict(other={k: torch.zeros_like(t[k]) for k in self._BIG},
+                  prev_small={"path_len": torch.zeros_like(t["path_len"]), "n_nodes": torch.zeros_like(t["n_nodes"]),
+                              "action_id": z((NSLOT, B), i32), "traj_len": z((NSLOT, B), i32),
+                              "trim": z((NSLOT * B, 4), i32)},
+                  sel_action=z((B,), i32), pos_last=z((B, 2), f64), t_const=z((B,), f64), st_info=z((B, 8), i32),
+                  vel_plan=z((B,), f64), course=z((B, 8), f64), obj_dist=z((B,), f64))
+        t["trim"] = z((NSLOT * B, 4), i32)
+        self.buf.trim = t["trim"].data_ptr()
+        self._state = st
+
+    def next_tick(self, sc: ScenarioBatch, sel_action, t_const, vel_est=None) -> None:
+        """One stateful tick for the whole batch (EXPERIMENTAL): ``sc.pos`` = position estimates, ``sel_action`` =
+        action id (capi.ACT_*) every scenario executed since the last tick, ``t_const`` = min(average calculation time
+        * calc_time_safety, 0.5) per scenario (OTH:353-375; the caller keeps the moving average), ``vel_est`` = velocity
+        estimates.  The previous tick (tick() after set_startpos(), or next_tick()) must have run on this planner."""
+        if self._state is None:
+            self._alloc_state()
+        st, t, buf = self._state, self.t, self.buf
+        ps = st["prev_small"]
+        for k in ("path_len", "n_nodes", "action_id", "traj_len", "trim"):
+            ps[k].copy_(t[k].view(ps[k].shape))
+        for k in self._BIG:                                   # this tick writes the other set, the last one is memory
+            t[k], st["other"][k] = st["other"][k], t[k]
+            setattr(buf, k, t[k].data_ptr())
+            setattr(buf, "prev_" + k, st["other"][k].data_ptr())
+        for k in ("path_len", "n_nodes", "action_id", "traj_len", "trim"):
+            setattr(buf, "prev_" + k, ps[k].data_ptr())
+        st["pos_last"].copy_(t["pos"])                        # pos_est of the previous calc_vel_profile (OTH:537)
+        st["sel_action"].copy_(torch.as_tensor(np.asarray(sel_action, dtype=np.int32).reshape(-1)))
+        st["t_const"].copy_(torch.as_tensor(np.broadcast_to(np.asarray(t_const, dtype=np.float64),
+                                                            (self.dims.batch,)).copy()))
+        for k in ("sel_action", "pos_last", "t_const", "st_info", "vel_plan", "course", "obj_dist"):
+            setattr(buf, k, st[k].data_ptr())
+        self.stage_scenarios(sc, vel_est=vel_est)
+        self.upload()
+        keep_vel = buf.vel
+        buf.vel = st["vel_plan"].data_ptr()
+        try:
+            self._tick_count += 1
+            self.params.traj_base_id = 10 * self._tick_count
+            self._call(self.lib.ltpl_next_tick_batch, "ltpl_next_tick_batch")
+        finally:
+            buf.vel = keep_vel
 
     def launch_count(self) -> int:
         return int(self.lib.ltpl_launch_count())
@@ -395,6 +459,7 @@ class BatchPlanner(object):
         f = self.fetch("sc_flags", "start_node", "action_id", "status", "n_nodes", "nodes", "node_idx", "closest_obj",
                        "path_len", "path", "coeff", "s_vx_ax", "traj", "traj_row", "traj_len", "traj_id", "const_seg",
                        "const_len", "em_info")
+        trim = self.t["trim"].cpu().numpy() if "trim" in self.t else None   # stateful ticks: trajectories start at the cut
         B = self.dims.batch
         out = []
         for b in (range(B) if indices is None else indices):
@@ -430,8 +495,10 @@ class BatchPlanner(object):
                 rec["red_len"][name] = [bool(st & capi.ST_REDUCED_HORIZON)]
                 rec["tie"][name] = bool(st & capi.ST_TIE_AMBIGUOUS)
                 if st & capi.ST_TRAJ_VALID:
-                    full = np.column_stack((f["s_vx_ax"][0, q, :n], f["path"][0:4, q, :n].T, f["s_vx_ax"][1, q, :n],
-                                            f["s_vx_ax"][2, q, :n]))
+                    cut = 0 if trim is None else int(trim[q, 2])
+                    m = n - cut
+                    full = np.column_stack((f["s_vx_ax"][0, q, :m], f["path"][0:4, q, cut:n].T, f["s_vx_ax"][1, q, :m],
+                                            f["s_vx_ax"][2, q, :m]))
                     rec["traj_full"][name] = [full]
                     tl = int(f["traj_len"][s, b])
                     rec["traj"][name] = [f["traj"][int(f["traj_row"][s, b]), :tl].astype(np.float64)]

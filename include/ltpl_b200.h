@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 6
+#define LTPL_ABI_VERSION 7
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -54,6 +54,8 @@ extern "C" {
 #define LTPL_SC_OUT_OF_TRACK     (1 << 0)  /* OTH:214-219                                                             */
 #define LTPL_SC_HEADING_MISMATCH (1 << 1)  /* OTH:234-240                                                             */
 #define LTPL_SC_CAPACITY         (1 << 2)  /* a fixed-capacity buffer (P0_MAX / P_MAX / H_MAX) would overflow          */
+#define LTPL_SC_STATE_FALLBACK   (1 << 4)  /* stateful tick: the last executed trajectory is not usable as memory       */
+                                           /* (OTH:393-407 branch / backup plan OTH:950-1006): re-anchor with set_startpos */
 #define LTPL_SC_BRAKE_PREFIX     (1 << 3)  /* vel_plan > vel_max + 0.1: the reference path raises here (OTH:747-754,   */
                                            /* 830/919 column_stack length mismatch); reported instead of planned       */
 
@@ -137,6 +139,8 @@ typedef struct LtplParams {
     int32_t incl_emerg_traj;     /* calc_vel_profile(incl_emerg_traj=True): append the brake-to-stop profile on the   */
                                  /* first kept trajectory of every scenario (OTH:1027-1034, calc_brake_emergency.py)   */
     int32_t pad0;
+    double delaycomp;            /* DELAY.delaycomp (OTH:117, 570)                    */
+    double w_last_edges[4];      /* COST.w_last_edges, first three entries (GLNT:155-162); [3] unused */
     double axm_v[LTPL_MAX_AXM];
     double axm_a[LTPL_MAX_AXM];
     double axm_s[LTPL_MAX_AXM];  /* slopes (a[i+1] - a[i]) / (v[i+1] - v[i]) exactly as np.interp forms them  */
@@ -209,6 +213,30 @@ typedef struct LtplBuffers {
     const int32_t* n_pred;    /* [B][K] number of prediction points of the object, -1: none given -> one constant-        */
                               /*        velocity point at 0.2 s (OLI:121-127).  At most 32 discs (on-track objects +     */
                               /*        their prediction points) per scenario, else LTPL_SC_CAPACITY                     */
+    /* ---- stateful tick (ltpl_next_*_batch; EXPERIMENTAL): the iterative memory of            */
+    /* OnlineTrajectoryHandler (OTH:64-87) = the output buffers of the previous tick (a second buffer set, used            */
+    /* ping-pong) + per-path trims instead of the slicing of OTH:705-731.  NULL for first ticks.                           */
+    const double* prev_path;        /* previous tick's `path`                                                             */
+    const int32_t* prev_path_len;   /* ... `path_len`                                                                     */
+    const int32_t* prev_node_idx;   /* ... `node_idx`                                                                     */
+    const int32_t* prev_nodes;      /* ... `nodes`                                                                        */
+    const int32_t* prev_n_nodes;    /* ... `n_nodes`                                                                      */
+    const double* prev_coeff;       /* ... `coeff`                                                                        */
+    const double* prev_s_vx_ax;     /* ... `s_vx_ax` (rows 0 .. traj_len-1 = the exported trajectory = __last_bp_action_set) */
+    const int32_t* prev_action_id;  /* ... `action_id`                                                                    */
+    const int32_t* prev_traj_len;   /* ... `traj_len`                                                                     */
+    const int32_t* prev_trim;       /* ... `trim`                                                                         */
+    const int32_t* sel_action;      /* [B] LTPL_ACT_* the caller executed since the previous tick (prev_action_id)        */
+    const double* pos_last;         /* [B][2] pos_est of the previous calc_vel_profile call (OTH:537, MOPG:80-84)         */
+    const double* t_const;          /* [B] min(average calculation time * calc_time_safety, 0.5) (OTH:353-375): the host  */
+                                    /*     keeps the moving average, so the wall clock is an input                         */
+    int32_t* st_info;               /* [B][8] k_state: prev path id, prev m, prev L, constant nodes, #factored edges, e0..e2 */
+    int32_t* trim;                  /* [NSLOT*B][4] m = first memory point, L = first memory node, c = first trajectory   */
+                                    /*     point (path-plane indices of THIS tick, OTH:586-598, 705-731), pref = #points    */
+                                    /*     of vel_course; zero on first ticks                                               */
+    double* vel_plan;               /* [B] planned velocity at the cut (OTH:572); the kernels read it through `vel`        */
+    double* course;                 /* [B][8] vel_course (OTH:574)                                                         */
+    double* obj_dist;               /* [B] s_obj - s_start on the cut follow path (OTH:774-784)                            */
 } LtplBuffers;
 
 /* stand-alone forward/backward ggv velocity profile over dense path arrays (BASELINE.json config 5).                   */
@@ -244,6 +272,10 @@ int ltpl_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const L
 int ltpl_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims,
                                 const LtplBuffers* buf, void* stream);
 /* calc_paths + calc_vel_profile back to back (one planning tick)                                                        */
+/* stateful tick (EXPERIMENTAL): start node + constant segment from the previous tick (replaces ltpl_set_startpos_batch  */
+/* from the second tick on), then calc_paths / calc_vel_profile with the iterative memory                               */
+int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* params, const LtplDims* dims,
+                         const LtplBuffers* buffers, void* stream);
 int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims, const LtplBuffers* buf,
                     void* stream);
 /* one kernel of the tick on its own (profiling / per-kernel roofline timing in bench.py):                               */
