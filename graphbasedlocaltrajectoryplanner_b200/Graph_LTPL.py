@@ -59,6 +59,11 @@ class Graph_LTPL(object):
         self.__pos = None
         self.__heading = None
         self.__objects = None
+        # iterative memory across ticks (EXPERIMENTAL): the clock is injectable for tests
+        self.clock = time.time
+        self.__tick_no = 0
+        self.__last_path_timestamp = None
+        self.__calc_buffer = []
 
     # ------------------------------------------------------------------------------------------------------------------
     def graph_init(self, veh_param_dyn_model_exp: float = 1.0, veh_param_dragcoeff: float = 0.85,
@@ -70,7 +75,8 @@ class Graph_LTPL(object):
                                                   overrides=lattice_overrides)
         self.__planner = BatchPlanner(self.__lattice, online=self.__online, device=self.__device,
                                       veh_param_dyn_model_exp=veh_param_dyn_model_exp,
-                                      veh_param_dragcoeff=veh_param_dragcoeff, veh_param_mass=veh_param_mass)
+                                      veh_param_dragcoeff=veh_param_dragcoeff, veh_param_mass=veh_param_mass,
+                                      stateful=True)
 
     @property
     def lattice(self):
@@ -106,13 +112,19 @@ class Graph_LTPL(object):
             raise RuntimeError("start pose too far from the lattice for the constant-segment capacity")
         out_of_track = bool(flags & (capi.SC_OUT_OF_TRACK | capi.SC_HEADING_MISMATCH))
         self.__state = None if out_of_track else "start"
+        self.__tick_no = 0
+        self.__last_path_timestamp = None
+        self.__calc_buffer = []
         return out_of_track
 
     def calc_paths(self, prev_action_id: str, prev_traj_idx: int = 0, object_list: list = None,
                    blocked_zones: dict = None) -> dict:
         if self.__state is None:
-            raise NotImplementedError("calc_paths() plans the first tick after set_startpos(); the reference's "
-                                      "wall-clock dependent multi-tick memory (OTH:346-414) is SURVEY 8(f) rank 1")
+            raise ValueError("calc_paths() needs a start pose: call set_startpos() first (after an out-of-track result or "
+                             "a memory fallback again)")
+        if self.__state == "next":   # EXPERIMENTAL stateful tick: the memory of the last tick lives on the device
+            return self.__calc_paths_next(prev_action_id, object_list, blocked_zones)
+        self.__last_path_timestamp = self.clock()   # OTH:395
         sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel],
                                              [[o for o in (object_list or []) if o.get('type') == 'physical']],
                                              blocked_zones=[blocked_zones] if blocked_zones else None)
@@ -131,9 +143,49 @@ class Graph_LTPL(object):
                                 "Track useems to be blocked.")
         return {k: [a.copy() for a in v] for k, v in self.__records["paths"].items()}
 
+    def __calc_paths_next(self, prev_action_id, object_list, blocked_zones):
+        """OTH:346-392 on the device: the calculation time since the last calc_paths (moving average over 5 ticks, safety
+        factor 2, at most 0.5 s -- ltpl_config_online.ini:84-94) decides how much of the last trajectory stays constant."""
+        if blocked_zones:
+            raise NotImplementedError("blocked zones are not part of the stateful tick yet")
+        if prev_action_id not in ("straight", "follow", "left", "right"):
+            raise NotImplementedError("prev_action_id '%s' is not tracked by the stateful tick" % prev_action_id)
+        now = self.clock()
+        calc_time = now - self.__last_path_timestamp
+        self.__last_path_timestamp = self.clock()
+        if len(self.__calc_buffer) >= 5:
+            self.__calc_buffer.pop(0)
+        self.__calc_buffer.append(calc_time)
+        t_const = min(float(np.sum(self.__calc_buffer) / len(self.__calc_buffer)) * 2.0, 0.5)
+        sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel],
+                                             [[o for o in (object_list or []) if o.get('type') == 'physical']])
+        sel = {v: k for k, v in capi.ACTION_NAMES.items()}[prev_action_id]
+        pl = self.__planner
+        pl.next_calc_paths(sc, [sel], t_const)
+        rec = pl.records()[0]
+        if rec["flags"] & capi.SC_STATE_FALLBACK:
+            self.__state = None
+            raise RuntimeError("the last trajectory of action '%s' cannot serve as memory (OTH:393-407 / backup plan are "
+                               "not on the device yet): call set_startpos() again" % prev_action_id)
+        self.__records = rec
+        self.__state = "paths_next"
+        return {k: [a.copy() for a in v] for k, v in rec["paths"].items()}
+
     def calc_vel_profile(self, pos_est: np.ndarray, vel_est: float, vel_max: float = 100.0, gg_scale: float = 1.0,
                          local_gg: dict = (5.0, 5.0), ax_max_machines: np.ndarray = np.atleast_2d([100.0, 5.0]),
                          safety_d: float = 30.0, incl_emerg_traj: bool = False) -> tuple:
+        if self.__state == "paths_next":
+            if incl_emerg_traj:
+                raise NotImplementedError("the emergency trajectory is not part of the stateful tick yet")
+            pl = self.__planner
+            pl.set_vel_params(vel_max=vel_max, gg_scale=gg_scale, local_gg=local_gg, ax_max_machines=ax_max_machines,
+                              safety_d=safety_d)
+            self.__pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
+            pl.next_calc_vel_profile(pos_est=[self.__pos], vel_est=[float(vel_est)])
+            rec = pl.records()[0]
+            self.__records = rec
+            self.__state = "next" if rec["traj"] else None
+            return ({k: [a.copy() for a in v] for k, v in rec["traj"].items()}, dict(rec["ids"]), time.time())
         if self.__state != "paths":
             raise ValueError("calc_paths() must be called before calc_vel_profile()")
         if type(local_gg) is dict:
@@ -158,7 +210,8 @@ class Graph_LTPL(object):
                 self.__log.warning("Too close to object! Entering safety distance... [Follow-Mode]")
             if (st & capi.ST_VEL_BOUND_VIOL) and not (st & capi.ST_TRAJ_VALID):
                 self.__log.warning("Removed action set, since vel constraints were broken! (Action Set: " + name + ")")
-        self.__state = None
+        self.__pos = pos
+        self.__state = "next" if rec["traj"] else None   # later ticks continue from the device-resident memory
         return ({k: [a.copy() for a in v] for k, v in rec["traj"].items()}, dict(rec["ids"]), time.time())
 
     def last_node_sequences(self) -> dict:

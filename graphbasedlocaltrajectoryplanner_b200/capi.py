@@ -87,7 +87,8 @@ class VelBatch(C.Structure):
 
 EXPORTS = ("ltpl_version", "ltpl_last_error", "ltpl_sizeof", "ltpl_lattice_create", "ltpl_lattice_destroy",
            "ltpl_set_startpos_batch", "ltpl_calc_paths_batch", "ltpl_calc_vel_profile_batch", "ltpl_tick_batch",
-           "ltpl_velprofile_batch", "ltpl_launch_count", "ltpl_launch_stage", "ltpl_next_tick_batch")
+           "ltpl_velprofile_batch", "ltpl_launch_count", "ltpl_launch_stage", "ltpl_next_tick_batch",
+           "ltpl_next_calc_paths_batch", "ltpl_next_calc_vel_profile_batch")
 
 
 def build_library(verbose: bool = False) -> str:
@@ -130,7 +131,8 @@ def load_library():
     lib.ltpl_lattice_create.argtypes = [C.POINTER(LatticeHeader), C.c_void_p, C.POINTER(C.c_void_p)]
     lib.ltpl_lattice_destroy.argtypes = [C.c_void_p]
     for fn in (lib.ltpl_set_startpos_batch, lib.ltpl_calc_paths_batch, lib.ltpl_calc_vel_profile_batch,
-               lib.ltpl_tick_batch, lib.ltpl_next_tick_batch):
+               lib.ltpl_tick_batch, lib.ltpl_next_tick_batch, lib.ltpl_next_calc_paths_batch,
+               lib.ltpl_next_calc_vel_profile_batch):
         fn.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(Dims), C.POINTER(Buffers), C.c_void_p]
         fn.restype = C.c_int
     lib.ltpl_launch_stage.argtypes = [C.c_int, C.c_void_p, C.POINTER(Params), C.POINTER(Dims), C.POINTER(Buffers),

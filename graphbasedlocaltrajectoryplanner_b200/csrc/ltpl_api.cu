@@ -299,24 +299,30 @@ int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDim
     return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
 }
 
-// stateful tick (EXPERIMENTAL, ltpl_state.cuh): k_state -> k_plan<.., true> -> k_path<true> -> k_ref -> k_vel_tiled<true>
-// -> k_prefix -> k_export
-int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
-                         void* stream) {
+// stateful tick (EXPERIMENTAL, ltpl_state.cuh):
+//   ltpl_next_calc_paths_batch        k_state -> k_plan<.., true> -> k_path<true>
+//   ltpl_next_calc_vel_profile_batch  k_ref -> k_vel_tiled<true> -> k_prefix -> k_export
+static int check_stateful(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf) {
     if (int r = check_common(lat, prm, dm, bf)) return r;
     if (!bf->prev_path || !bf->prev_path_len || !bf->prev_node_idx || !bf->prev_nodes || !bf->prev_n_nodes ||
         !bf->prev_coeff || !bf->prev_s_vx_ax || !bf->prev_action_id || !bf->prev_traj_len || !bf->prev_trim ||
         !bf->sel_action || !bf->pos_last || !bf->t_const || !bf->st_info || !bf->trim || !bf->vel_plan || !bf->course ||
         !bf->obj_dist)
-        return fail("ltpl_next_tick_batch: the stateful buffers (prev_*, sel_action, pos_last, t_const, st_info, trim, "
-                    "vel_plan, course, obj_dist) must be set");
-    if (bf->vel != bf->vel_plan) return fail("ltpl_next_tick_batch: buffers.vel must point at buffers.vel_plan");
+        return fail("stateful tick: the buffers prev_*, sel_action, pos_last, t_const, st_info, trim, vel_plan, course, "
+                    "obj_dist must be set");
     if (dm->n_zones > 0 || prm->incl_emerg_traj)
-        return fail("ltpl_next_tick_batch: zones and the emergency trajectory are not part of the stateful tick yet");
+        return fail("stateful tick: zones and the emergency trajectory are not part of it yet");
     if (prm->delaycomp <= 0.0) return fail("params.delaycomp must be > 0");
 #if !LTPL_VEL_TILED || LTPL_VEL_SPLIT
-    return fail("ltpl_next_tick_batch needs the default velocity kernel (LTPL_VEL_TILED=1, LTPL_VEL_SPLIT=0)");
+    return fail("the stateful tick needs the default velocity kernel (LTPL_VEL_TILED=1, LTPL_VEL_SPLIT=0)");
 #else
+    return 0;
+#endif
+}
+
+int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                               void* stream) {
+    if (int r = check_stateful(lat, prm, dm, bf)) return r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
     const int hl = dm->h_max;
@@ -333,14 +339,23 @@ int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* prm, const Lt
         return fail("cudaFuncSetAttribute(k_path) failed");
     if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
     const int grid_b = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    const int nq = LTPL_NSLOT * dm->batch;
-    const int grid_q = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    const int grid_q = (LTPL_NSLOT * dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
     k_state<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
     if (int r = check_launch("k_state")) return r;
     k_plan<false, true><<<grid_b, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
     if (int r = check_launch("k_plan")) return r;
     k_path<true><<<grid_q, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
-    if (int r = check_launch("k_path")) return r;
+    return check_launch("k_path");
+}
+
+int ltpl_next_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,
+                                     const LtplBuffers* bf, void* stream) {
+    if (int r = check_stateful(lat, prm, dm, bf)) return r;
+    if (bf->vel != bf->vel_plan) return fail("stateful tick: buffers.vel must point at buffers.vel_plan");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid_b = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    const int nq = LTPL_NSLOT * dm->batch;
+    const int grid_q = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
     k_ref<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
     if (int r = check_launch("k_ref")) return r;
     if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
@@ -351,7 +366,12 @@ int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* prm, const Lt
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
         *dm, *bf);
     return check_launch("k_export");
-#endif
+}
+
+int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                         void* stream) {
+    if (int r = ltpl_next_calc_paths_batch(lat, prm, dm, bf, stream)) return r;
+    return ltpl_next_calc_vel_profile_batch(lat, prm, dm, bf, stream);
 }
 
 int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,

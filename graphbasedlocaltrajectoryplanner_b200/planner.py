@@ -411,22 +411,23 @@ class BatchPlanner(object):
         self.buf.trim = t["trim"].data_ptr()
         self._state = st
 
-    def next_tick(self, sc: ScenarioBatch, sel_action, t_const, vel_est=None) -> None:
-        """One stateful tick for the whole batch (EXPERIMENTAL): ``sc.pos`` = position estimates, ``sel_action`` =
-        action id (capi.ACT_*) every scenario executed since the last tick, ``t_const`` = min(average calculation time
-        * calc_time_safety, 0.5) per scenario (OTH:353-375; the caller keeps the moving average), ``vel_est`` = velocity
-        estimates.  The previous tick (tick() after set_startpos(), or next_tick()) must have run on this planner."""
+    def next_calc_paths(self, sc: ScenarioBatch, sel_action, t_const) -> None:
+        """calc_paths of a stateful tick (EXPERIMENTAL; OTH:289-516 with the iterative memory): ``sc`` carries the object
+        lists (its poses are only used by ``next_calc_vel_profile``), ``sel_action`` = action id (capi.ACT_*) every
+        scenario executed since the last tick, ``t_const`` = min(average calculation time * calc_time_safety, 0.5) per
+        scenario (OTH:353-375; the caller keeps the moving average).  The previous tick (tick() / calc_paths() +
+        calc_vel_profile() after set_startpos(), or a stateful tick) must have run on this planner."""
         if self._state is None:
             self._alloc_state()
         st, t, buf = self._state, self.t, self.buf
         ps = st["prev_small"]
-        for k in ("path_len", "n_nodes", "action_id", "traj_len", "trim"):
+        for k in self._SMALL:
             ps[k].copy_(t[k].view(ps[k].shape))
         for k in self._BIG:                                   # this tick writes the other set, the last one is memory
             t[k], st["other"][k] = st["other"][k], t[k]
             setattr(buf, k, t[k].data_ptr())
             setattr(buf, "prev_" + k, st["other"][k].data_ptr())
-        for k in ("path_len", "n_nodes", "action_id", "traj_len", "trim"):
+        for k in self._SMALL:
             setattr(buf, "prev_" + k, ps[k].data_ptr())
         st["pos_last"].copy_(t["pos"])                        # pos_est of the previous calc_vel_profile (OTH:537)
         st["sel_action"].copy_(torch.as_tensor(np.asarray(sel_action, dtype=np.int32).reshape(-1)))
@@ -434,16 +435,33 @@ class BatchPlanner(object):
                                                             (self.dims.batch,)).copy()))
         for k in ("sel_action", "pos_last", "t_const", "st_info", "vel_plan", "course", "obj_dist"):
             setattr(buf, k, st[k].data_ptr())
-        self.stage_scenarios(sc, vel_est=vel_est)
+        self.stage_scenarios(sc)
         self.upload()
+        self._call(self.lib.ltpl_next_calc_paths_batch, "ltpl_next_calc_paths_batch")
+
+    def next_calc_vel_profile(self, pos_est=None, vel_est=None) -> None:
+        """calc_vel_profile of a stateful tick (EXPERIMENTAL; OTH:518-601 + 603-1040): position / velocity estimates per
+        scenario (None: the poses / velocities staged by ``next_calc_paths``)."""
+        t, buf, st = self.t, self.buf, self._state
+        if pos_est is not None:
+            self.h_in["pos"].numpy()[...] = np.asarray(pos_est, dtype=np.float64).reshape(-1, 2)
+            t["pos"].copy_(self.h_in["pos"], non_blocking=True)
+        if vel_est is not None:
+            self.h_in["vel_est"].numpy()[...] = np.asarray(vel_est, dtype=np.float64).reshape(-1)
+            t["vel_est"].copy_(self.h_in["vel_est"], non_blocking=True)
         keep_vel = buf.vel
-        buf.vel = st["vel_plan"].data_ptr()
+        buf.vel = st["vel_plan"].data_ptr()                   # the planned velocity at the cut replaces the start velocity
         try:
             self._tick_count += 1
             self.params.traj_base_id = 10 * self._tick_count
-            self._call(self.lib.ltpl_next_tick_batch, "ltpl_next_tick_batch")
+            self._call(self.lib.ltpl_next_calc_vel_profile_batch, "ltpl_next_calc_vel_profile_batch")
         finally:
             buf.vel = keep_vel
+
+    def next_tick(self, sc: ScenarioBatch, sel_action, t_const, vel_est=None) -> None:
+        """One stateful tick for the whole batch (EXPERIMENTAL): ``sc.pos`` = position estimates."""
+        self.next_calc_paths(sc, sel_action, t_const)
+        self.next_calc_vel_profile(vel_est=vel_est)
 
     def launch_count(self) -> int:
         return int(self.lib.ltpl_launch_count())

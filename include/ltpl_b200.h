@@ -274,8 +274,12 @@ int ltpl_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, c
 /* calc_paths + calc_vel_profile back to back (one planning tick)                                                        */
 /* stateful tick (EXPERIMENTAL): start node + constant segment from the previous tick (replaces ltpl_set_startpos_batch  */
 /* from the second tick on), then calc_paths / calc_vel_profile with the iterative memory                               */
+int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* params, const LtplDims* dims,
+                               const LtplBuffers* buffers, void* stream);       /* OTH:289-516 with memory           */
+int ltpl_next_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* params, const LtplDims* dims,
+                                     const LtplBuffers* buffers, void* stream); /* OTH:518-601 + 603-1040            */
 int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* params, const LtplDims* dims,
-                         const LtplBuffers* buffers, void* stream);
+                         const LtplBuffers* buffers, void* stream);             /* both                              */
 int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims, const LtplBuffers* buf,
                     void* stream);
 /* one kernel of the tick on its own (profiling / per-kernel roofline timing in bench.py):                               */

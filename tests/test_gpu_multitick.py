@@ -77,3 +77,158 @@ def test_next_tick_matches_reference_sequences():
     assert not fails, "%d sequences diverged (of %d; %d trajectories matched before):\\n%s" % (
         len(fails), n_seq, compared, "\\n".join(fails[:8]))
     assert compared > 150
+
+
+def test_closed_loop_matches_session_oracle():
+    """larger closed loop driven by the DEVICE results (vehicle dummy on the selected trajectory, moving opponents,
+    changing action preference); the stateful oracle (oracle/ltpl_session.py, pinned against the reference) replays the
+    same inputs tick by tick.  Sequences the device flags as LTPL_SC_STATE_FALLBACK (memory not usable) leave the loop."""
+    from graphbasedlocaltrajectoryplanner_b200 import capi
+    from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch, Track, make_scenarios
+    from oracle.gen_golden import advance_on_traj
+    from oracle.ltpl_oracle import OracleLTPL
+    from oracle.ltpl_session import OracleSession
+    g = H.golden("ticks_multitick_default.npz")
+    lat = H.lattice_for("default")
+    n_seq, n_ticks = 96, 8
+    vel = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    sc0 = make_scenarios(Track(H.TRACK_CSV), n_seq, seed=2718, n_obj_min=0, n_obj_max=2)
+    rng = np.random.default_rng(2719)
+    prefer = (("right", "left", "straight", "follow"), ("follow", "straight", "left", "right"),
+              ("left", "right", "follow", "straight"), ("straight", "follow", "right", "left"))
+    pl = BatchPlanner(lat, device="cuda:0", stateful=True)
+    pl.set_vel_params(**vel)
+
+    class Clk(object):
+        def __init__(self):
+            self.t = 50.0
+
+        def __call__(self):
+            return self.t
+    clks = [Clk() for _ in range(n_seq)]
+    ses = [OracleSession(OracleLTPL(lat), clock=clks[q]) for q in range(n_seq)]
+    objs = sc0.obj.copy()
+    pos_est, vel_est = sc0.pos.copy(), sc0.vel.copy()
+    sel = ["straight"] * n_seq
+    cbuf = [[] for _ in range(n_seq)]
+    alive = np.ones(n_seq, dtype=bool)
+    fails, compared, fell_back, ticks_ok = [], 0, 0, 0
+    last_traj = [None] * n_seq
+    for k in range(n_ticks):
+        dts = rng.uniform(0.04, 0.16, size=n_seq)
+        tcs = np.zeros(n_seq)
+        for q in range(n_seq):
+            dt = float(dts[q])
+            clks[q].t += dt
+            for j in range(int(sc0.n_obj[q])):
+                objs[q, j, 0] -= np.sin(objs[q, j, 2]) * objs[q, j, 3] * dt
+                objs[q, j, 1] += np.cos(objs[q, j, 2]) * objs[q, j, 3] * dt
+            if k > 0:
+                if last_traj[q] is not None:
+                    pos_est[q], vel_est[q] = advance_on_traj(last_traj[q], dt)
+                if len(cbuf[q]) >= 5:
+                    cbuf[q].pop(0)
+                cbuf[q].append(dt)
+                tcs[q] = min(float(np.sum(cbuf[q]) / len(cbuf[q])) * 2.0, 0.5)
+        sc = ScenarioBatch(pos_est.copy(), sc0.heading.copy(), sc0.vel.copy(), sc0.n_obj.copy(), objs.copy())
+        if k == 0:
+            pl.stage_scenarios(sc, vel_est=vel_est)
+            pl.upload()
+            pl.set_startpos()
+            pl.tick()
+        else:
+            pl.next_tick(sc, sel_action=[H.ACTIONS.index(a) for a in sel], t_const=tcs, vel_est=vel_est)
+        recs = pl.records()
+        for q in range(n_seq):
+            if not alive[q]:
+                continue
+            ctx = "sequence %d tick %d (sel %s)" % (q, k, sel[q])
+            rec = recs[q]
+            if rec["out_of_track"] or (rec["flags"] & (capi.SC_STATE_FALLBACK | capi.SC_CAPACITY | capi.SC_BRAKE_PREFIX)):
+                alive[q] = False
+                fell_back += int(bool(rec["flags"] & capi.SC_STATE_FALLBACK))
+                continue
+            try:
+                if k == 0:
+                    assert ses[q].set_startpos(sc.pos[q], sc.heading[q], sc.vel[q]) is False
+                paths = ses[q].calc_paths(sel[q], sc.object_list(q))
+                traj, ids = ses[q].calc_vel_profile(sc.pos[q], float(vel_est[q]), **vel)
+            except Exception as e:   # noqa: BLE001  (e.g. the reference's own brake-prefix failure)
+                alive[q] = False
+                continue
+            try:
+                assert sorted(rec["paths"]) == sorted(paths), "%s: paths %s vs %s" % (ctx, sorted(rec["paths"]),
+                                                                                   sorted(paths))
+                for act in paths:
+                    if ses[q].tie.get(act) or rec["tie"].get(act):
+                        continue
+                    nd = [[-1 if v is None else int(v) for v in p] for p in rec["nodes"][act][0]]
+                    want = [[-1 if v is None else int(v) for v in p] for p in ses[q].m_nodes[act][0]] \
+                        if act in ses[q].m_nodes else None
+                    assert want is None or nd == want, "%s: nodes of %s\n got  %s\n want %s" % (ctx, act, nd, want)
+                    assert rec["paths"][act][0].shape[0] == paths[act][0].shape[0], ctx + " path length " + act
+                assert sorted(rec["traj"]) == sorted(traj), "%s: trajectories %s vs %s" % (ctx, sorted(rec["traj"]),
+                                                                                        sorted(traj))
+                for act in traj:
+                    assert rec["traj"][act][0].shape == traj[act][0].shape, ctx + " rows " + act
+                    H.assert_close("traj[%s]" % act, rec["traj"][act][0], traj[act][0],
+                                   ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+                    compared += 1
+                ticks_ok += 1
+            except AssertionError as e:
+                fails.append(str(e).split("\\n")[0][:400])
+                alive[q] = False
+                continue
+            cand = [a for a in prefer[(q + k) % len(prefer)] if a in rec["traj"]]
+            if not cand:
+                alive[q] = False
+                continue
+            sel[q] = cand[0]
+            last_traj[q] = rec["traj"][sel[q]][0]
+    assert not fails, "%d sequences diverged (%d ticks matched, %d fell back):\\n%s" % (
+        len(fails), ticks_ok, fell_back, "\\n".join(fails[:8]))
+    print("closed loop: %d of %d ticks compared, %d trajectories, %d sequences fell back, %d alive at the end" % (
+        ticks_ok, n_seq * n_ticks, compared, fell_back, int(alive.sum())))
+    assert ticks_ok > n_seq * n_ticks // 2 and compared > n_seq * n_ticks // 2, (ticks_ok, compared, fell_back)
+
+
+def test_facade_runs_closed_loop_like_the_reference():
+    """Graph_LTPL facade with the reference's call sequence over several ticks (main_std_example.py:99-126): an injected
+    clock takes the place of time.time(); three recorded sequences of the reference are replayed."""
+    from graphbasedlocaltrajectoryplanner_b200.Graph_LTPL import Graph_LTPL
+    g = H.golden("ticks_multitick_default.npz")
+    pd = {'globtraj_input_path': H.TRACK_CSV, 'graph_store_path': "/tmp/_lat_default_test.npz",
+          'ltpl_offline_param_path': H.OFFLINE_INI, 'ltpl_online_param_path': H.ONLINE_INI}
+    ltpl = Graph_LTPL(path_dict=pd, visual_mode=False, log_to_file=False, device="cuda:0")
+    ltpl.graph_init()
+
+    class Clk(object):
+        t = 10.0
+
+        def __call__(self):
+            return self.t
+    clk = Clk()
+    ltpl.clock = clk
+    vel = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    n_ticks = g["dt"].shape[1]
+    compared = 0
+    for q in (0, 5, 11):
+        assert ltpl.set_startpos(pos_est=g["sc_pos"][q], heading_est=g["sc_heading"][q], vel_est=g["sc_vel"][q]) is False
+        n_obj = int(g["sc_n_obj"][q])
+        for k in range(n_ticks):
+            clk.t += float(g["dt"][q, k])
+            ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
+                   'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(g["obj"][q, k, :n_obj])]
+            paths = ltpl.calc_paths(prev_action_id=H.ACTIONS[int(g["sel"][q, k])], object_list=ol)
+            traj, ids, _ = ltpl.calc_vel_profile(pos_est=g["pos_est"][q, k], vel_est=float(g["vel_est"][q, k]), **vel)
+            ctx = "facade sequence %d tick %d" % (q, k)
+            for a, act in enumerate(H.ACTIONS):
+                assert (act in paths) == (int(g["path_len"][q, k, a]) > 0), ctx + " paths " + act
+                t_want = int(g["traj_len"][q, k, a])
+                assert (act in traj) == (t_want > 0), ctx + " trajectories " + act
+                if t_want:
+                    H.assert_close("traj[%s]" % act, traj[act][0], g["traj"][q, k, a, :t_want],
+                                   ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+                    compared += 1
+    assert compared > 40
