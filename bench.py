@@ -501,6 +501,74 @@ def main():
             del pl_4
         except Exception as e:   # noqa: BLE001
             extra["config4_l430_error"] = str(e)[:200]
+        try:   # stateful ticks (EXPERIMENTAL): closed loop of 8 ticks on the bench workload; a
+            # vehicle dummy advances every scenario 0.1 s on its first kept trajectory; the loop is recorded once
+            # (untimed host work between the ticks) and replayed with CUDA events around every next_tick
+            from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
+            pl_s = BatchPlanner(lat, online=read_online_config(ONLINE_INI), device=device, stateful=True)
+            pl_s.set_vel_params(**vel_kwargs())
+            n_loop, dt_loop = 8, 0.1
+
+            def first_tick():
+                pl_s.stage_scenarios(sc)
+                pl_s.upload()
+                pl_s.set_startpos()
+                pl_s.tick()
+
+            def advance(out):
+                rows = out["traj_row"].numpy()
+                lens = out["traj_len"].numpy()
+                acts = out["action_id"].numpy()
+                slot = np.argmax(rows >= 0, axis=0)                      # first kept trajectory of every scenario
+                bidx = np.arange(rows.shape[1])
+                ok = rows[slot, bidx] >= 0
+                r = np.where(ok, rows[slot, bidx], 0)
+                tr = out["traj"].numpy()[r].astype(np.float64)           # (B, 115, 7)
+                n = np.maximum(lens[slot, bidx], 2)
+                s_t = tr[:, 0, 0] + np.maximum(tr[:, 0, 5] * dt_loop + 0.5 * tr[:, 0, 6] * dt_loop ** 2, 0.0)
+                valid = np.arange(tr.shape[1])[None, :] < n[:, None]
+                i0 = np.clip((np.where(valid, tr[:, :, 0], np.inf) <= s_t[:, None]).sum(axis=1) - 1, 0, n - 2)
+                s0, s1 = tr[bidx, i0, 0], tr[bidx, i0 + 1, 0]
+                f = np.clip((s_t - s0) / np.maximum(s1 - s0, 1e-9), 0.0, 1.0)
+                lerp = lambda c: tr[bidx, i0, c] * (1 - f) + tr[bidx, i0 + 1, c] * f   # noqa: E731
+                return np.column_stack((lerp(1), lerp(2))), lerp(5), np.where(ok, acts[slot, bidx], 0), ok
+
+            first_tick()
+            rec_in = []
+            pos_e, vel_e = sc.pos.copy(), sc.vel.copy()
+            for _ in range(n_loop):
+                out = pl_s.download()
+                torch.cuda.synchronize(device)
+                p_new, v_new, sel_a, ok = advance(out)
+                pos_e, vel_e = np.where(ok[:, None], p_new, pos_e), np.where(ok, v_new, vel_e)
+                rec_in.append((pos_e.copy(), vel_e.copy(), sel_a.astype(np.int32)))
+                sc_k = ScenarioBatch(pos_e.copy(), sc.heading, sc.vel, sc.n_obj, sc.obj)
+                pl_s.next_tick(sc_k, sel_a, 2.0 * dt_loop, vel_est=vel_e)
+            torch.cuda.synchronize(device)
+            flags = pl_s.fetch("sc_flags")["sc_flags"]
+            first_tick()
+            t_st = 0.0
+            stream_s = torch.cuda.current_stream(device)
+            for pos_k, vel_k, sel_k in rec_in:
+                sc_k = ScenarioBatch(pos_k, sc.heading, sc.vel, sc.n_obj, sc.obj)
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream_s)
+                pl_s.next_tick(sc_k, sel_k, 2.0 * dt_loop, vel_est=vel_k)
+                e1.record(stream_s)
+                torch.cuda.synchronize(device)
+                t_st += e0.elapsed_time(e1) * 1e-3
+            extra["stateful_tick"] = {"ticks_per_s": args.batch * n_loop / t_st, "ms_per_tick": 1e3 * t_st / n_loop,
+                                      "ticks": n_loop, "scenarios_still_planned_at_the_end": int((flags == 0).sum()),
+                                      "flags_at_the_end": {name: int(((flags & bit) != 0).sum()) for name, bit in (
+                                          ("out_of_track", capi.SC_OUT_OF_TRACK),
+                                          ("heading_mismatch", capi.SC_HEADING_MISMATCH), ("capacity", capi.SC_CAPACITY),
+                                          ("brake_prefix", capi.SC_BRAKE_PREFIX),
+                                          ("state_fallback", capi.SC_STATE_FALLBACK))},
+                                      "note": "closed loop, 0.1 s per tick; device time of one next_tick incl. its input upload"}
+            del pl_s
+        except Exception as e:   # noqa: BLE001
+            extra["stateful_tick_error"] = str(e)[:300]
         try:   # 100 k paths x 500 points forward/backward solver
             from graphbasedlocaltrajectoryplanner_b200.scenarios import make_velocity_microbench
             from graphbasedlocaltrajectoryplanner_b200.velprofile import velprofile_batch_device
