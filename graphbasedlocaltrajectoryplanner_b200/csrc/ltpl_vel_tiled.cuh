@@ -829,6 +829,10 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     // acceptance (OTH:943-1025; no backup plan exists on the first tick)
     if (live && !prefix && n > 0 && role == 0) {
         if (!vel_bound) st |= LTPL_ST_VEL_BOUND_VIOL;
+        // stateful tick: a backup plan exists (OTH:325-344), so a straight / follow profile that breaks the bound is
+        // replaced by a brake profile on the OLD path in the reference (OTH:950-1006) -- not on the device yet: flag
+        if (STATE && !vel_bound && (action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT))
+            atomicOr(&bf.sc_flags[b], LTPL_SC_STATE_FALLBACK);
         if (vel_bound || action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT) {
             st |= LTPL_ST_TRAJ_VALID;
             bf.traj_len[q] = min(n, dm.n_export);
