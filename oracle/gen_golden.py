@@ -291,7 +291,7 @@ def advance_on_traj(traj, dt):
             float(np.interp(s, traj[:, 0], traj[:, 5])))
 
 
-def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs):
+def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids)."""
     import graph_ltpl.online_graph.src.OnlineTrajectoryHandler as oth_mod
@@ -300,8 +300,11 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs):
     real_time = oth_mod.time
     oth_mod.time = clock
     try:
-        sc = make_scenarios(track, n_seq, seed=31337, n_obj_min=0, n_obj_max=2)
-        rng = np.random.default_rng(31338)
+        sc = make_scenarios(track, n_seq, seed=seed, n_obj_min=0, n_obj_max=2)
+        rng = np.random.default_rng(seed + 1)
+        emerg = bool(vel_kwargs.get('incl_emerg_traj'))
+        zones = [(make_zone(lat, rng, sc.pos[q]) if (lat is not None and q % 2 == 0) else None) for q in range(n_seq)]
+        zmax = max([len(z[0]) for z in zones if z is not None] + [1])
         prefer = (("right", "left", "straight", "follow"), ("follow", "straight", "left", "right"),
                   ("left", "straight", "follow", "right"))
         hmax, pmax = 40, 115
@@ -312,7 +315,14 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs):
                    traj_id=np.full((n_seq, n_ticks, 4), -1, dtype=np.int32),
                    nodes=np.full((n_seq, n_ticks, 4, hmax, 2), -1, dtype=np.int32),
                    nodes_len=np.zeros((n_seq, n_ticks, 4), dtype=np.int32),
-                   path_len=np.zeros((n_seq, n_ticks, 4), dtype=np.int32), n_done=np.zeros(n_seq, dtype=np.int32))
+                   path_len=np.zeros((n_seq, n_ticks, 4), dtype=np.int32), n_done=np.zeros(n_seq, dtype=np.int32),
+                   em_traj=np.zeros((n_seq, n_ticks, pmax, 7)), em_len=np.zeros((n_seq, n_ticks), dtype=np.int32),
+                   zone_layers=np.full((n_seq, zmax), -1, dtype=np.int32),
+                   zone_nodes=np.full((n_seq, zmax), -1, dtype=np.int32))
+        for q in range(n_seq):
+            if zones[q] is not None:
+                out['zone_layers'][q, :len(zones[q][0])] = zones[q][0]
+                out['zone_nodes'][q, :len(zones[q][1])] = zones[q][1]
         for q in range(n_seq):
             if ltpl.set_startpos(pos_est=np.array(sc.pos[q]), heading_est=float(sc.heading[q]), vel_est=float(sc.vel[q])):
                 continue
@@ -335,7 +345,8 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs):
                 out['dt'][q, k], out['sel'][q, k] = dt, ACTIONS.index(sel)
                 out['pos_est'][q, k], out['vel_est'][q, k] = pos_est, vel_est
                 out['obj'][q, k, :objs.shape[0]] = objs
-                paths = ltpl.calc_paths(prev_action_id=sel, object_list=ol)
+                bz = None if zones[q] is None else {'zone_%d' % q: zones[q]}
+                paths = ltpl.calc_paths(prev_action_id=sel, object_list=ol, blocked_zones=bz)
                 nodes = oth._OnlineTrajectoryHandler__last_action_set_nodes
                 for a, act in enumerate(ACTIONS):
                     if act in paths and len(paths[act]) and np.size(paths[act][0]):
@@ -350,6 +361,10 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs):
                         out['traj'][q, k, a, :t.shape[0]] = t
                         out['traj_len'][q, k, a] = t.shape[0]
                         out['traj_id'][q, k, a] = ids[act]
+                if emerg and 'emergency' in traj_set:
+                    t = traj_set['emergency'][0]
+                    out['em_traj'][q, k, :t.shape[0]] = t
+                    out['em_len'][q, k] = t.shape[0]
                 out['n_done'][q] = k + 1
                 cand = [a for a in order if a in traj_set and len(traj_set[a])]
                 if not cand:
@@ -487,6 +502,10 @@ def main():
         if tag == "default" and (args.multitick_only or not (args.pred_only or args.ext_only)):
             np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_default.npz'),
                                 **multitick_fixture(graph_ltpl, ltpl, track, 16, 10, vel_kwargs))
+            # the same with a blocked zone on every second sequence and the emergency trajectory switched on
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_ext_default.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 12, 8,
+                                                    dict(vel_kwargs, incl_emerg_traj=True), lat=lat, seed=4141))
             if args.multitick_only:
                 return
         if tag == "default":

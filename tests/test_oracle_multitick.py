@@ -14,12 +14,19 @@ class _Clock(object):
         return self.t
 
 
-def test_session_oracle_matches_reference_sequences():
+import pytest
+
+
+@pytest.mark.parametrize("fixture,emerg", [("ticks_multitick_default.npz", False),
+                                           ("ticks_multitick_ext_default.npz", True)])
+def test_session_oracle_matches_reference_sequences(fixture, emerg):
+    """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory."""
     from oracle.ltpl_oracle import OracleLTPL
     from oracle.ltpl_session import OracleSession
-    g = H.golden("ticks_multitick_default.npz")
+    g = H.golden(fixture)
     lat = H.lattice_for("default")
-    vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0,
+              incl_emerg_traj=emerg)
     n_seq, n_ticks = g["dt"].shape
     compared = 0
     for q in range(n_seq):
@@ -35,7 +42,7 @@ def test_session_oracle_matches_reference_sequences():
             ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
                    'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(g["obj"][q, k, :n_obj])]
             sel = H.ACTIONS[int(g["sel"][q, k])]
-            paths = ses.calc_paths(sel, ol)
+            paths = ses.calc_paths(sel, ol, blocked_zones=H.zone_of(g, q))
             for a, act in enumerate(H.ACTIONS):
                 n_want = int(g["path_len"][q, k, a])
                 assert (act in paths) == (n_want > 0), "%s: path %s present=%s, golden %d" % (ctx, act, act in paths,
@@ -55,4 +62,10 @@ def test_session_oracle_matches_reference_sequences():
                     H.assert_close("traj[%s]" % act, traj[act][0], g["traj"][q, k, a, :t_want],
                                    ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
                     compared += 1
-    assert compared > 150
+            if emerg:
+                n_em = int(g["em_len"][q, k])
+                assert ("emergency" in traj) == (n_em > 0), ctx + " emergency"
+                if n_em:
+                    H.assert_close("traj[emergency]", traj["emergency"][0], g["em_traj"][q, k, :n_em],
+                                   ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+    assert compared > (80 if emerg else 150)
