@@ -146,8 +146,6 @@ class Graph_LTPL(object):
     def __calc_paths_next(self, prev_action_id, object_list, blocked_zones):
         """OTH:346-392 on the device: the calculation time since the last calc_paths (moving average over 5 ticks, safety
         factor 2, at most 0.5 s -- ltpl_config_online.ini:84-94) decides how much of the last trajectory stays constant."""
-        if blocked_zones:
-            raise NotImplementedError("blocked zones are not part of the stateful tick yet")
         if prev_action_id not in ("straight", "follow", "left", "right"):
             raise NotImplementedError("prev_action_id '%s' is not tracked by the stateful tick" % prev_action_id)
         now = self.clock()
@@ -158,7 +156,8 @@ class Graph_LTPL(object):
         self.__calc_buffer.append(calc_time)
         t_const = min(float(np.sum(self.__calc_buffer) / len(self.__calc_buffer)) * 2.0, 0.5)
         sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel],
-                                             [[o for o in (object_list or []) if o.get('type') == 'physical']])
+                                             [[o for o in (object_list or []) if o.get('type') == 'physical']],
+                                             blocked_zones=[blocked_zones] if blocked_zones else None)
         sel = {v: k for k, v in capi.ACTION_NAMES.items()}[prev_action_id]
         pl = self.__planner
         pl.next_calc_paths(sc, [sel], t_const)
@@ -175,11 +174,9 @@ class Graph_LTPL(object):
                          local_gg: dict = (5.0, 5.0), ax_max_machines: np.ndarray = np.atleast_2d([100.0, 5.0]),
                          safety_d: float = 30.0, incl_emerg_traj: bool = False) -> tuple:
         if self.__state == "paths_next":
-            if incl_emerg_traj:
-                raise NotImplementedError("the emergency trajectory is not part of the stateful tick yet")
             pl = self.__planner
             pl.set_vel_params(vel_max=vel_max, gg_scale=gg_scale, local_gg=local_gg, ax_max_machines=ax_max_machines,
-                              safety_d=safety_d)
+                              safety_d=safety_d, incl_emerg_traj=incl_emerg_traj)
             self.__pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
             pl.next_calc_vel_profile(pos_est=[self.__pos], vel_est=[float(vel_est)])
             rec = pl.records()[0]

@@ -310,8 +310,8 @@ static int check_stateful(const LtplLattice* lat, const LtplParams* prm, const L
         !bf->obj_dist)
         return fail("stateful tick: the buffers prev_*, sel_action, pos_last, t_const, st_info, trim, vel_plan, course, "
                     "obj_dist must be set");
-    if (dm->n_zones > 0 || prm->incl_emerg_traj)
-        return fail("stateful tick: zones and the emergency trajectory are not part of it yet");
+    if (dm->n_zones > 0 && !bf->zone_s0) return fail("stateful tick with zones: buffers.zone_s0 must be set");
+    if (prm->incl_emerg_traj && !bf->em_info) return fail("params.incl_emerg_traj needs buffers.em_info");
     if (prm->delaycomp <= 0.0) return fail("params.delaycomp must be > 0");
 #if !LTPL_VEL_TILED || LTPL_VEL_SPLIT
     return fail("the stateful tick needs the default velocity kernel (LTPL_VEL_TILED=1, LTPL_VEL_SPLIT=0)");
@@ -331,8 +331,10 @@ int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, co
     const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
     if (smem_plan > 200 * 1024 || smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
     if (smem_plan > 48 * 1024 &&
-        cudaFuncSetAttribute(k_plan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
-            cudaSuccess)
+        (cudaFuncSetAttribute(k_plan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
+             cudaSuccess ||
+         cudaFuncSetAttribute(k_plan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
+             cudaSuccess))
         return fail("cudaFuncSetAttribute(k_plan) failed");
     if (smem_path > 48 * 1024 &&
         cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
@@ -342,7 +344,10 @@ int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, co
     const int grid_q = (LTPL_NSLOT * dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
     k_state<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
     if (int r = check_launch("k_state")) return r;
-    k_plan<false, true><<<grid_b, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    if (dm->n_zones > 0)
+        k_plan<true, true><<<grid_b, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    else
+        k_plan<false, true><<<grid_b, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
     if (int r = check_launch("k_plan")) return r;
     k_path<true><<<grid_q, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
     return check_launch("k_path");
@@ -365,7 +370,14 @@ int ltpl_next_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* p
     if (int r = check_launch("k_prefix")) return r;
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
         *dm, *bf);
-    return check_launch("k_export");
+    if (int r = check_launch("k_export")) return r;
+    if (prm->incl_emerg_traj) {
+        const size_t smem = emerg_smem_bytes_per_warp(dm->n_export) * LTPL_WARPS_PER_CTA;
+        if (smem > 48 * 1024) return fail("n_export too large for k_emergency");
+        k_emergency<<<grid_b, LTPL_WARPS_PER_CTA * 32, smem, st>>>(*prm, *dm, *bf);
+        return check_launch("k_emergency");
+    }
+    return 0;
 }
 
 int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,

@@ -40,7 +40,8 @@ k_emergency(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
         }
         return;
     }
-    const int n = bf.path_len[q];
+    const int cut = bf.trim ? bf.trim[4 * q + 2] : 0;   // stateful tick: the trajectory starts at the cut index
+    const int n = bf.path_len[q] - cut;
     const int ne = min(n, dm.n_export);          // exported rows
     const int m = min(n, ne + 1);                // points the rows depend on (ax of row ne - 1 needs w[ne])
     double* ss = reinterpret_cast<double*>(em_smem) + (size_t)wib * 3 * (dm.n_export + 1);
@@ -49,7 +50,7 @@ k_emergency(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
     const double* s_row = bf.s_vx_ax + (size_t)q * dm.p_max;
     const double* vx_row = s_row + pplane;
-    const double* pp = bf.path + (size_t)q * dm.p_max;
+    const double* pp = bf.path + (size_t)q * dm.p_max + cut;
     for (int i = lane; i < m; i += 32) {
         ss[i] = s_row[i];
         sk[i] = fabs(pp[3 * pplane + i]);

@@ -210,7 +210,7 @@ __device__ __forceinline__ bool zone_unblocked(int l, int s0, int L) {
 template <bool ZONE, bool COSTF = false>
 __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int start_layer, int start_node, int n_steps,
                                       const unsigned* mask, int e_base, int rem_layer, int rem_lo, int rem_hi,
-                                      int li_begin, int snap_at, const unsigned* zone) {
+                                      int li_begin, int snap_at, const unsigned* zone, int zone_s0 = -1) {
     const int maxn = c.maxn;
     int tie = 0;
     if (li_begin == 1) {
@@ -233,7 +233,7 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
         const int nbase = mt.x, nl = mt.y;
         const int moff = (mt.z >= e_base) ? -e_base : lt.E - e_base;  // edge id -> bit of the window mask
         // 'overtaking_zones' is the base of every other filter (GLNT:96-99, 144-147): zone nodes are absent everywhere
-        const unsigned* zs = (ZONE && zone && !zone_unblocked(nxt, start_layer, lt.L)) ? zone : nullptr;
+        const unsigned* zs = (ZONE && zone && !zone_unblocked(nxt, zone_s0, lt.L)) ? zone : nullptr;
         const double* dcur = c.dist + cur * maxn;
         double* dnxt = c.dist + (cur ^ 1) * maxn;
         int any = 0;
@@ -682,9 +682,15 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     //  * 'overtake_left' and 'overtake_right' differ only from the object's layer onwards -> the second one resumes
     //    from a snapshot of the first one's state one layer before it.
     const unsigned* zone = nullptr;   // k_plan<false> is launched when the batch carries no zones (dims.n_zones == 0)
+    int zone_s0 = start_layer;        // start layer of the tick that processed the zone (GLNT:43-77)
     if (ZONE) {
         const int zsel = bf.zone_sel[b];
         if (zsel >= 0 && zsel < dm.n_zones) zone = bf.zone_bits + (size_t)zsel * dm.n_zone_words;
+        if (bf.zone_s0) {
+            if (STATE && zone && bf.zone_s0[b] >= 0) zone_s0 = bf.zone_s0[b];
+            __syncwarp();
+            if (lane == 0) bf.zone_s0[b] = zone ? zone_s0 : -1;
+        }
     }
     unsigned mask_any = 0;
     #pragma unroll 1
@@ -750,7 +756,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
                 const int li_begin = (f == 3 && c.snap_li >= 1) ? c.snap_li + 1 : 1;
                 const int snap_at = (f == 2 && a + 1 < n_act && filt[a + 1] == 3) ? closest_dist - 1 : 0;
                 reach = dp_run<ZONE, STATE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
-                               rem_layer, rem_lo, rem_hi, li_begin, snap_at, zone);
+                               rem_layer, rem_lo, rem_hi, li_begin, snap_at, zone, zone_s0);
                 tie = c.tie;
             }
             LTPL_PH(21)

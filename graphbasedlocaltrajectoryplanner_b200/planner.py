@@ -80,6 +80,7 @@ class BatchPlanner(object):
             if self.blob.device != self.device or self.blob.dtype != torch.uint8 \
                     or self.blob.numel() != self.header.blob_bytes:
                 raise ValueError("blob tensor does not match the lattice header")
+        self._stateful = bool(stateful)
         if stateful:   # stateful ticks carry constant nodes / points of earlier ticks in front of the new plan
             self.cap = dict(self.cap, h_max=self.cap["h_max"] + 8, p_max=self.cap["p_max"] + 96)
         handle = C.c_void_p()
@@ -223,6 +224,8 @@ class BatchPlanner(object):
         self.h_in, self.h_out = self.h_in_sets[0], self.h_out_sets[0]
         self._meta_names = tuple(n for n, _, _ in meta_spec)
         self._row_bytes = NE * 7 * 4
+        if self._stateful:
+            self._alloc_state()   # incl. zone_s0, which the FIRST tick has to fill
 
     def device_bytes(self) -> int:
         return int(sum(v.numel() * v.element_size() for v in self.t.values()) + self.blob.numel())
@@ -372,6 +375,8 @@ class BatchPlanner(object):
                    what)
 
     def set_startpos(self) -> None:
+        if self._state is not None:
+            self._state["zone_s0"].fill_(-1)   # zones are processed anew by the first tick (GLNT:43-77)
         self._call(self.lib.ltpl_set_startpos_batch, "ltpl_set_startpos_batch")
 
     def calc_paths(self) -> None:
@@ -407,6 +412,8 @@ class BatchPlanner(object):
                               "trim": z((NSLOT * B, 4), i32)},
                   sel_action=z((B,), i32), pos_last=z((B, 2), f64), t_const=z((B,), f64), st_info=z((B, 8), i32),
                   vel_plan=z((B,), f64), course=z((B, 8), f64), obj_dist=z((B,), f64))
+        st["zone_s0"] = torch.full((B,), -1, dtype=i32, device=dev)
+        self.buf.zone_s0 = st["zone_s0"].data_ptr()
         t["trim"] = z((NSLOT * B, 4), i32)
         self.buf.trim = t["trim"].data_ptr()
         self._state = st

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 7
+#define LTPL_ABI_VERSION 8
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -213,7 +213,7 @@ typedef struct LtplBuffers {
     const int32_t* n_pred;    /* [B][K] number of prediction points of the object, -1: none given -> one constant-        */
                               /*        velocity point at 0.2 s (OLI:121-127).  At most 32 discs (on-track objects +     */
                               /*        their prediction points) per scenario, else LTPL_SC_CAPACITY                     */
-    /* ---- stateful tick (ltpl_next_*_batch; EXPERIMENTAL): the iterative memory of            */
+    /* ---- stateful tick (ltpl_next_*_batch): the iterative memory of            */
     /* OnlineTrajectoryHandler (OTH:64-87) = the output buffers of the previous tick (a second buffer set, used            */
     /* ping-pong) + per-path trims instead of the slicing of OTH:705-731.  NULL for first ticks.                           */
     const double* prev_path;        /* previous tick's `path`                                                             */
@@ -237,6 +237,9 @@ typedef struct LtplBuffers {
     double* vel_plan;               /* [B] planned velocity at the cut (OTH:572); the kernels read it through `vel`        */
     double* course;                 /* [B][8] vel_course (OTH:574)                                                         */
     double* obj_dist;               /* [B] s_obj - s_start on the cut follow path (OTH:774-784)                            */
+    int32_t* zone_s0;               /* [B] start layer of the tick in which the scenario's zone was processed (GLNT:43-77:  */
+                                    /*     the unblock window is evaluated once), -1: not yet; needed for zones in stateful  */
+                                    /*     ticks, optional (NULL) otherwise                                                   */
 } LtplBuffers;
 
 /* stand-alone forward/backward ggv velocity profile over dense path arrays (BASELINE.json config 5).                   */
@@ -272,7 +275,7 @@ int ltpl_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const L
 int ltpl_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims,
                                 const LtplBuffers* buf, void* stream);
 /* calc_paths + calc_vel_profile back to back (one planning tick)                                                        */
-/* stateful tick (EXPERIMENTAL): start node + constant segment from the previous tick (replaces ltpl_set_startpos_batch  */
+/* stateful tick: start node + constant segment from the previous tick (replaces ltpl_set_startpos_batch  */
 /* from the second tick on), then calc_paths / calc_vel_profile with the iterative memory                               */
 int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* params, const LtplDims* dims,
                                const LtplBuffers* buffers, void* stream);       /* OTH:289-516 with memory           */

@@ -20,22 +20,28 @@ def _t_const(dts):
     return out
 
 
-def test_next_tick_matches_reference_sequences():
+@pytest.mark.parametrize("fixture,emerg", [("ticks_multitick_default.npz", False),
+                                           ("ticks_multitick_ext_default.npz", True)])
+def test_next_tick_matches_reference_sequences(fixture, emerg):
+    """second fixture: a blocked zone on every second sequence + the emergency trajectory in every tick."""
     from graphbasedlocaltrajectoryplanner_b200 import capi
     from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
     from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
-    g = H.golden("ticks_multitick_default.npz")
+    g = H.golden(fixture)
     n_seq, n_ticks = g["dt"].shape
     assert int(g["n_done"].min()) == n_ticks
+    zones = [H.zone_of(g, q) for q in range(n_seq)]
     pl = BatchPlanner(H.lattice_for("default"), device="cuda:0", stateful=True)
     pl.set_vel_params(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"],
-                      safety_d=30.0)
+                      safety_d=30.0, incl_emerg_traj=emerg)
     tc = np.array([_t_const(g["dt"][q, 1:]) for q in range(n_seq)])       # t_const of ticks 1 ..
     fails, compared = [], 0
     alive = np.ones(n_seq, dtype=bool)
     for k in range(n_ticks):
         sc = ScenarioBatch(g["pos_est"][:, k].copy(), g["sc_heading"].copy(), g["sc_vel"].copy(), g["sc_n_obj"].copy(),
                            g["obj"][:, k].copy())
+        if any(z is not None for z in zones):
+            sc.set_zones(zones)
         if k == 0:
             pl.stage_scenarios(sc, vel_est=g["vel_est"][:, k])
             pl.upload()
@@ -71,12 +77,18 @@ def test_next_tick_matches_reference_sequences():
                         H.assert_close("traj[%s]" % act, rec["traj"][act][0], g["traj"][q, k, a, :t_want],
                                        ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
                         compared += 1
+                if emerg:
+                    n_em = min(int(g["em_len"][q, k]), 115)
+                    assert ("emergency" in rec["traj"]) == (n_em > 0), ctx + " emergency presence"
+                    if n_em:
+                        H.assert_close("traj[emergency]", rec["traj"]["emergency"][0], g["em_traj"][q, k, :n_em],
+                                       ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
             except AssertionError as e:
                 fails.append(str(e).split("\\n")[0][:400] if "nodes of" not in str(e) else str(e)[:700])
                 alive[q] = False            # later ticks of this sequence depend on this one
     assert not fails, "%d sequences diverged (of %d; %d trajectories matched before):\\n%s" % (
         len(fails), n_seq, compared, "\\n".join(fails[:8]))
-    assert compared > 150
+    assert compared > (80 if emerg else 150)
 
 
 def test_closed_loop_matches_session_oracle():
