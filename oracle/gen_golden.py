@@ -291,7 +291,7 @@ def advance_on_traj(traj, dt):
             float(np.interp(s, traj[:, 0], traj[:, 5])))
 
 
-def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337):
+def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids)."""
     import graph_ltpl.online_graph.src.OnlineTrajectoryHandler as oth_mod
@@ -318,7 +318,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                    path_len=np.zeros((n_seq, n_ticks, 4), dtype=np.int32), n_done=np.zeros(n_seq, dtype=np.int32),
                    em_traj=np.zeros((n_seq, n_ticks, pmax, 7)), em_len=np.zeros((n_seq, n_ticks), dtype=np.int32),
                    zone_layers=np.full((n_seq, zmax), -1, dtype=np.int32),
-                   zone_nodes=np.full((n_seq, zmax), -1, dtype=np.int32))
+                   zone_nodes=np.full((n_seq, zmax), -1, dtype=np.int32), gg_scale=np.ones((n_seq, n_ticks)))
         for q in range(n_seq):
             if zones[q] is not None:
                 out['zone_layers'][q, :len(zones[q][0])] = zones[q][0]
@@ -354,7 +354,11 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                         nd = [[-1 if v is None else int(v) for v in pair] for pair in nodes[act][0]]
                         out['nodes'][q, k, a, :len(nd)] = nd
                         out['nodes_len'][q, k, a] = len(nd)
-                traj_set, ids, _ = ltpl.calc_vel_profile(pos_est=pos_est, vel_est=vel_est, **vel_kwargs)
+                vk = dict(vel_kwargs)
+                if gg_drop is not None and q % 2 == 1 and k >= gg_drop[0]:
+                    vk['gg_scale'] = gg_drop[1]       # grip drops: profiles can no longer start at the planned velocity
+                out['gg_scale'][q, k] = vk.get('gg_scale', 1.0)
+                traj_set, ids, _ = ltpl.calc_vel_profile(pos_est=pos_est, vel_est=vel_est, **vk)
                 for a, act in enumerate(ACTIONS):
                     if act in traj_set and len(traj_set[act]):
                         t = traj_set[act][0]
@@ -506,6 +510,11 @@ def main():
             np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_ext_default.npz'),
                                 **multitick_fixture(graph_ltpl, ltpl, track, 12, 8,
                                                     dict(vel_kwargs, incl_emerg_traj=True), lat=lat, seed=4141))
+            # grip drop on every second sequence from tick 3 on: recursive infeasibility -> brake on the backup plan
+            # (OTH:950-1006)
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_backup_default.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 12, 7, vel_kwargs, seed=5151,
+                                                    gg_drop=(3, 0.45)))
             if args.multitick_only:
                 return
         if tag == "default":
