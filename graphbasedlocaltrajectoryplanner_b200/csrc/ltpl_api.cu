@@ -366,6 +366,8 @@ int ltpl_next_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* p
     if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
     if (launch_k_vel(lat, prm, dm, bf, st, true) != cudaSuccess) return fail("k_vel: cudaFuncSetAttribute failed");
     if (int r = check_launch("k_vel")) return r;
+    k_backup<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*prm, *dm, *bf);
+    if (int r = check_launch("k_backup")) return r;
     k_prefix<<<grid_q, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*dm, *bf);
     if (int r = check_launch("k_prefix")) return r;
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(

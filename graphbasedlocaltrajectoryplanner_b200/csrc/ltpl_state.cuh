@@ -320,3 +320,86 @@ k_prefix(const LtplDims dm, const LtplBuffers bf) {
         bf.traj_len[q] = min(n_p + pref, dm.n_export);
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_backup: recursive infeasibility (OTH:950-1006).  A straight / follow profile of a stateful tick that cannot start at
+// the planned velocity (e.g. the grip dropped) is replaced by full braking on the BACKUP plan = the memory of the last
+// tick's follow / straight path (OTH:325-344; both live in slot 0): the path, node and coefficient lists of this tick
+// become the backup's (OTH:958-963), the trajectory is vel_course followed by tph.calc_vel_profile_brake on the backup
+// path behind it with the caller's local_gg WITHOUT gg_scale (VPFB:229-255, OTH:965-1003).  One warp per scenario, between
+// the velocity kernel and k_prefix (which adds vel_course, the arc-length offset and the row count as for every path).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
+k_backup(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (b >= dm.batch) return;
+    const int B = dm.batch;
+    const int q = b;   // slot 0: follow / straight
+    const int st = bf.status[q];
+    const int act = bf.action_id[q];
+    if (!(st & LTPL_ST_TRAJ_VALID) || !(st & LTPL_ST_VEL_BOUND_VIOL) ||
+        !(act == LTPL_ACT_FOLLOW || act == LTPL_ACT_STRAIGHT))
+        return;
+    const int pa = bf.prev_action_id[q];
+    if (!(pa == LTPL_ACT_FOLLOW || pa == LTPL_ACT_STRAIGHT)) return;   // no backup plan: stays flagged
+    const int m_b = bf.prev_trim[4 * q + 0], L_b = bf.prev_trim[4 * q + 1];
+    const int n_bk = bf.prev_path_len[q] - m_b, nn_bk = bf.prev_n_nodes[q] - L_b;
+    const int cut = bf.trim[4 * q + 2], pref = bf.trim[4 * q + 3];
+    const int n_p = n_bk - cut - pref;                     // points of the brake profile
+    if (n_p < 1 || nn_bk < 1) return;
+    const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
+    // the backup becomes this tick's memory (OTH:958-963); the trims of k_ref stay (they are what the slices use)
+    for (int c = 0; c < 5; ++c) {
+        const double* src = bf.prev_path + c * pplane + (size_t)q * dm.p_max + m_b;
+        double* dst = bf.path + c * pplane + (size_t)q * dm.p_max;
+        for (int i = lane; i < n_bk; i += 32) dst[i] = src[i];
+    }
+    for (int j = lane; j < nn_bk; j += 32) {
+        bf.node_idx[(size_t)q * dm.h_max + j] = bf.prev_node_idx[(size_t)q * dm.h_max + L_b + j] - m_b;
+        bf.nodes[((size_t)q * dm.h_max + j) * 2] = bf.prev_nodes[((size_t)q * dm.h_max + L_b + j) * 2];
+        bf.nodes[((size_t)q * dm.h_max + j) * 2 + 1] = bf.prev_nodes[((size_t)q * dm.h_max + L_b + j) * 2 + 1];
+    }
+    for (int j = lane; j < max(nn_bk - 1, 1) * 8; j += 32)
+        bf.coeff[(size_t)q * dm.h_max * 8 + j] = bf.prev_coeff[((size_t)q * dm.h_max + L_b) * 8 + j];
+    __syncwarp();
+    if (lane == 0) {
+        bf.path_len[q] = n_bk;
+        bf.n_nodes[q] = nn_bk;
+        // full braking from the planned velocity behind vel_course (tph.calc_vel_profile_brake, mode 'decel_forw')
+        const double* K = bf.path + 3 * pplane + (size_t)q * dm.p_max + cut + pref;
+        const double* E = K + pplane;
+        double* S = bf.s_vx_ax + (size_t)q * dm.p_max + pref;   // rows behind vel_course, arc length 0 at their first point
+        double* VX = S + pplane;
+        double* AX = VX + pplane;
+        const double dmq = prm.drag_coeff / prm.m_veh, inv_ay = 1.0 / prm.gg_ay;
+        double v0 = bf.vel[b];                                  // == vel_plan (the host points `vel` at it)
+        if (v0 < 0.0) v0 = 0.0;
+        double w = v0 * v0, s = 0.0;
+        bool stopped = false;
+        for (int i = 0; i < n_p; ++i) {
+            S[i] = s;
+            VX[i] = sqrt(w);
+            double wn = 0.0;
+            if (i + 1 < n_p) {
+                if (!stopped) {
+                    const double a = acc_brake(w, fabs(K[i]), prm.gg_ax, inv_ay, prm.dyn_model_exp, dmq);
+                    const double nx = fma(2.0 * a, E[i], w);
+                    if (nx < 0.0)
+                        stopped = true;
+                    else
+                        wn = nx;
+                }
+                double ax = (wn - w) / (2 * E[i]);
+                if (w <= 1e-16 && fabs(ax) <= 1e-8) ax = -5.0;   // OTH:999
+                AX[i] = ax;
+                s = __dadd_rn(s, E[i]);
+            } else {
+                AX[i] = 0.0;
+            }
+            w = wn;
+        }
+        bf.traj_len[q] = min(n_p, dm.n_export);                 // k_prefix adds the vel_course rows
+        atomicAnd(&bf.sc_flags[b], ~LTPL_SC_STATE_FALLBACK);    // handled
+    }
+}

@@ -20,14 +20,30 @@ def _t_const(dts):
     return out
 
 
-@pytest.mark.parametrize("fixture,emerg", [("ticks_multitick_default.npz", False),
-                                           ("ticks_multitick_ext_default.npz", True)])
-def test_next_tick_matches_reference_sequences(fixture, emerg):
-    """second fixture: a blocked zone on every second sequence + the emergency trajectory in every tick."""
+class _Rows(object):
+    """the sequences `idx` of a multi-tick fixture (gg_scale is a per-batch parameter: grip-drop sequences run apart)."""
+
+    def __init__(self, g, idx):
+        self.g, self.idx, self.files = g, np.asarray(idx), g.files
+
+    def __getitem__(self, k):
+        a = self.g[k]
+        return a if k == "ax_max_machines" else a[self.idx]
+
+
+@pytest.mark.parametrize("fixture,emerg,group", [("ticks_multitick_default.npz", False, None),
+                                                 ("ticks_multitick_ext_default.npz", True, None),
+                                                 ("ticks_multitick_backup_default.npz", False, 0),
+                                                 ("ticks_multitick_backup_default.npz", False, 1)])
+def test_next_tick_matches_reference_sequences(fixture, emerg, group):
+    """second fixture: a blocked zone on every second sequence + the emergency trajectory in every tick; third fixture:
+    the grip (gg_scale) drops on the odd sequences from tick 3 on -> brake on the backup plan (OTH:950-1006)."""
     from graphbasedlocaltrajectoryplanner_b200 import capi
     from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
     from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
     g = H.golden(fixture)
+    if group is not None:
+        g = _Rows(g, np.arange(group, g["dt"].shape[0], 2))
     n_seq, n_ticks = g["dt"].shape
     assert int(g["n_done"].min()) == n_ticks
     zones = [H.zone_of(g, q) for q in range(n_seq)]
@@ -42,6 +58,9 @@ def test_next_tick_matches_reference_sequences(fixture, emerg):
                            g["obj"][:, k].copy())
         if any(z is not None for z in zones):
             sc.set_zones(zones)
+        assert len(set(g["gg_scale"][:, k].tolist())) == 1
+        pl.set_vel_params(vel_max=100.0, gg_scale=float(g["gg_scale"][0, k]), local_gg=(5.0, 5.0),
+                          ax_max_machines=g["ax_max_machines"], safety_d=30.0, incl_emerg_traj=emerg)
         if k == 0:
             pl.stage_scenarios(sc, vel_est=g["vel_est"][:, k])
             pl.upload()
@@ -88,7 +107,7 @@ def test_next_tick_matches_reference_sequences(fixture, emerg):
                 alive[q] = False            # later ticks of this sequence depend on this one
     assert not fails, "%d sequences diverged (of %d; %d trajectories matched before):\\n%s" % (
         len(fails), n_seq, compared, "\\n".join(fails[:8]))
-    assert compared > (80 if emerg else 150)
+    assert compared > (30 if group is not None else (80 if emerg else 150))
 
 
 def test_closed_loop_matches_session_oracle():
