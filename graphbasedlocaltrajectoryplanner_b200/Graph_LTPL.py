@@ -146,8 +146,8 @@ class Graph_LTPL(object):
     def __calc_paths_next(self, prev_action_id, object_list, blocked_zones):
         """OTH:346-392 on the device: the calculation time since the last calc_paths (moving average over 5 ticks, safety
         factor 2, at most 0.5 s -- ltpl_config_online.ini:84-94) decides how much of the last trajectory stays constant."""
-        if prev_action_id not in ("straight", "follow", "left", "right"):
-            raise NotImplementedError("prev_action_id '%s' is not tracked by the stateful tick" % prev_action_id)
+        if prev_action_id not in ("straight", "follow", "left", "right", "emergency"):
+            raise ValueError("unknown prev_action_id '%s'" % prev_action_id)
         now = self.clock()
         calc_time = now - self.__last_path_timestamp
         self.__last_path_timestamp = self.clock()
@@ -158,13 +158,14 @@ class Graph_LTPL(object):
         sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel],
                                              [[o for o in (object_list or []) if o.get('type') == 'physical']],
                                              blocked_zones=[blocked_zones] if blocked_zones else None)
-        sel = {v: k for k, v in capi.ACTION_NAMES.items()}[prev_action_id]
+        # 'emergency': the device translates it to the action its profile was based on (OTH:307-309)
+        sel = dict({v: k for k, v in capi.ACTION_NAMES.items()}, emergency=capi.ACT_EMERGENCY)[prev_action_id]
         pl = self.__planner
         pl.next_calc_paths(sc, [sel], t_const)
         rec = pl.records()[0]
         if rec["flags"] & capi.SC_STATE_FALLBACK:
             self.__state = None
-            raise RuntimeError("the last trajectory of action '%s' cannot serve as memory (OTH:393-407 / backup plan are "
+            raise RuntimeError("the last trajectory of action '%s' cannot serve as memory (OTH:393-407 is "
                                "not on the device yet): call set_startpos() again" % prev_action_id)
         self.__records = rec
         self.__state = "paths_next"

@@ -12,12 +12,13 @@ import os
 import subprocess
 import sys
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 NSLOT = 3
 KMAX = 16
 MAX_AXM = 32
 
 ACT_NONE, ACT_STRAIGHT, ACT_FOLLOW, ACT_LEFT, ACT_RIGHT = -1, 0, 1, 2, 3
+ACT_EMERGENCY = 4   # only as the executed action of a stateful tick (OTH:307-309)
 ACTION_NAMES = {ACT_STRAIGHT: "straight", ACT_FOLLOW: "follow", ACT_LEFT: "left", ACT_RIGHT: "right"}
 
 ST_FOUND, ST_REDUCED_HORIZON, ST_TIE_AMBIGUOUS, ST_START_BLOCKED = 1, 2, 4, 8
@@ -72,7 +73,7 @@ BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags",
                  "vel_t", "traj", "traj_len", "traj_id", "zone_bits", "zone_sel", "em_info", "obj_pred",
                  "n_pred", "prev_path", "prev_path_len", "prev_node_idx", "prev_nodes", "prev_n_nodes", "prev_coeff",
                  "prev_s_vx_ax", "prev_action_id", "prev_traj_len", "prev_trim", "sel_action", "pos_last", "t_const",
-                 "st_info", "trim", "vel_plan", "course", "obj_dist", "zone_s0")
+                 "st_info", "trim", "vel_plan", "course", "obj_dist", "zone_s0", "em_vx", "prev_em_vx", "prev_em_info")
 STATE_FIELDS = BUFFER_FIELDS[BUFFER_FIELDS.index("prev_path"):]   # NULL unless a stateful tick is planned
 
 

@@ -379,6 +379,9 @@ int ltpl_next_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* p
         k_emergency<<<grid_b, LTPL_WARPS_PER_CTA * 32, smem, st>>>(*prm, *dm, *bf);
         return check_launch("k_emergency");
     }
+    // no emergency trajectory in this tick: the next one must not take a stale one for executed (k_state)
+    if (bf->em_info && cudaMemsetAsync(bf->em_info, 0xFF, sizeof(int) * 3 * (size_t)dm->batch, st) != cudaSuccess)
+        return fail("memset(em_info) failed");
     return 0;
 }
 

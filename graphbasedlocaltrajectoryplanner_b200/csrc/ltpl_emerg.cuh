@@ -9,7 +9,8 @@
 //
 // One WARP per scenario, launched after k_export: lanes stage s and kappa of the first n_export + 1 points in shared
 // memory, lane 0 runs the brake recurrence in w = v^2 (same arithmetic as brake_profile_w), all lanes write the fp32 row
-// into the next free row of the compact export buffer (queue_cnt[2]).
+// into the next free row of the compact export buffer (queue_cnt[2]); the f64 velocities also go to em_vx (stateful ticks:
+// get_ref_idx reads them when the caller executes this trajectory, OTH:307-309 / 518-601).
 #pragma once
 #include "ltpl_vel.cuh"
 
@@ -93,7 +94,9 @@ k_emergency(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
         o[2] = (float)pp[1 * pplane + i];
         o[3] = (float)pp[2 * pplane + i];
         o[4] = (float)pp[3 * pplane + i];
-        o[5] = (float)sqrt(sw[i]);
+        const double v = sqrt(sw[i]);
+        o[5] = (float)v;
+        if (bf.em_vx) bf.em_vx[(size_t)b * dm.n_export + i] = v;   // f64 copy: memory of an executed 'emergency' (k_ref)
         o[6] = (float)a;
     }
     if (lane == 0) {

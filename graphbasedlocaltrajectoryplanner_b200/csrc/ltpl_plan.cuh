@@ -653,7 +653,8 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         n_act = 1;
         names[0] = LTPL_ACT_FOLLOW;
         filt[0] = 0;
-        const int last_act = STATE ? bf.sel_action[b] : LTPL_ACT_STRAIGHT;
+        // last_action_id (MOPG:130): the executed action, 'emergency' already translated by k_state (st_info[0] = its slot)
+        const int last_act = STATE ? bf.prev_action_id[bf.st_info[8 * (size_t)b]] : LTPL_ACT_STRAIGHT;
         if (!obj_in_const && (last_act == LTPL_ACT_LEFT || last_act == LTPL_ACT_RIGHT)) {   // MOPG:130-133: keep overtaking
             names[1] = last_act;
             filt[1] = 1;

@@ -64,8 +64,15 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
         bf.start_node[2 * b + 1] = -1;
         bf.const_len[b] = 0;
     }
-    // the executed action (OTH:307-315; 'emergency' is not tracked here)
-    const int sel = bf.sel_action[b];
+    // the executed action (OTH:307-315); 'emergency' stands for the action its profile was based on = the first kept
+    // trajectory of the last tick (OTH:1027-1030, k_emergency), provided that tick had an emergency trajectory
+    int sel = bf.sel_action[b];
+    if (sel == LTPL_ACT_EMERGENCY) {
+        sel = LTPL_ACT_NONE;
+        if (bf.prev_em_info && bf.prev_em_vx && bf.prev_em_info[3 * (size_t)b] >= 0)
+            for (int s = LTPL_NSLOT - 1; s >= 0; --s)
+                if (bf.prev_traj_len[s * B + b] > 0) sel = bf.prev_action_id[s * B + b];
+    }
     int qp = -1;
     for (int s = 0; s < LTPL_NSLOT; ++s)
         if (bf.prev_action_id[s * B + b] == sel && sel != LTPL_ACT_NONE) qp = s * B + b;
@@ -165,6 +172,8 @@ k_ref(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
     const double* Py = Px + pplane;
     const double* S = bf.prev_s_vx_ax + (size_t)qp * dm.p_max;
     const double* V = S + pplane;
+    // an executed 'emergency' trajectory shares s, x, y with its base (calc_brake_emergency.py:40-45) but not the velocity
+    if (bf.sel_action[b] == LTPL_ACT_EMERGENCY) V = bf.prev_em_vx + (size_t)b * dm.n_export;
     const double px = bf.pos[2 * b], py = bf.pos[2 * b + 1];
 
     // cut index: first of the two trajectory points around pos_est (OTH:551-556); n_export <= 128 rows

@@ -830,7 +830,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
     if (live && !prefix && n > 0 && role == 0) {
         if (!vel_bound) st |= LTPL_ST_VEL_BOUND_VIOL;
         // stateful tick: a backup plan exists (OTH:325-344), so a straight / follow profile that breaks the bound is
-        // replaced by a brake profile on the OLD path in the reference (OTH:950-1006) -- not on the device yet: flag
+        // replaced by a brake profile on the OLD path (OTH:950-1006): flag here, k_backup plans it and clears the flag
         if (STATE && !vel_bound && (action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT))
             atomicOr(&bf.sc_flags[b], LTPL_SC_STATE_FALLBACK);
         if (vel_bound || action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT) {

@@ -384,7 +384,12 @@ class BatchPlanner(object):
             self.t["trim"].zero_()   # a first tick exports from point 0
         self._call(self.lib.ltpl_calc_paths_batch, "ltpl_calc_paths_batch")
 
+    def _no_stale_emergency(self) -> None:
+        if self._state is not None and not self.params.incl_emerg_traj:
+            self.t["em_info"].fill_(-1)   # a later stateful tick must not take an older emergency trajectory for executed
+
     def calc_vel_profile(self) -> None:
+        self._no_stale_emergency()
         self._tick_count += 1
         self.params.traj_base_id = 10 * self._tick_count   # OTH:669
         self._call(self.lib.ltpl_calc_vel_profile_batch, "ltpl_calc_vel_profile_batch")
@@ -393,23 +398,27 @@ class BatchPlanner(object):
         """calc_paths + calc_vel_profile back to back."""
         if self._state is not None:
             self.t["trim"].zero_()   # a first tick exports from point 0
+        self._no_stale_emergency()
         self._tick_count += 1
         self.params.traj_base_id = 10 * self._tick_count
         self._call(self.lib.ltpl_tick_batch, "ltpl_tick_batch")
 
     # -- stateful tick (EXPERIMENTAL: DESIGN.md section 11, csrc/ltpl_state.cuh) ----------------------------------------------
-    _BIG = ("path", "node_idx", "nodes", "coeff", "s_vx_ax")          # swapped by pointer
-    _SMALL = ("path_len", "n_nodes", "action_id", "traj_len", "trim")  # copied (a few bytes per path)
+    _BIG = ("path", "node_idx", "nodes", "coeff", "s_vx_ax", "em_vx")            # swapped by pointer
+    _SMALL = ("path_len", "n_nodes", "action_id", "traj_len", "trim", "em_info")  # copied (a few bytes per path)
 
     def _alloc_state(self) -> None:
         dev, B = self.device, self.dims.batch
         f64, i32 = torch.float64, torch.int32
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
         t = self.t
+        t["em_vx"] = z((B, self.dims.n_export), f64)   # f64 velocity of the emergency trajectory (executed 'emergency')
+        self.buf.em_vx = t["em_vx"].data_ptr()
+        t["em_info"].fill_(-1)
         st = dict(other={k: torch.zeros_like(t[k]) for k in self._BIG},
                   prev_small={"path_len": torch.zeros_like(t["path_len"]), "n_nodes": torch.zeros_like(t["n_nodes"]),
                               "action_id": z((NSLOT, B), i32), "traj_len": z((NSLOT, B), i32),
-                              "trim": z((NSLOT * B, 4), i32)},
+                              "trim": z((NSLOT * B, 4), i32), "em_info": torch.full((B, 3), -1, dtype=i32, device=dev)},
                   sel_action=z((B,), i32), pos_last=z((B, 2), f64), t_const=z((B,), f64), st_info=z((B, 8), i32),
                   vel_plan=z((B,), f64), course=z((B, 8), f64), obj_dist=z((B,), f64))
         st["zone_s0"] = torch.full((B,), -1, dtype=i32, device=dev)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 8
+#define LTPL_ABI_VERSION 9
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -35,6 +35,7 @@ extern "C" {
 #define LTPL_ACT_FOLLOW 1
 #define LTPL_ACT_LEFT 2
 #define LTPL_ACT_RIGHT 3
+#define LTPL_ACT_EMERGENCY 4 /* only as `sel_action`: the caller executed the 'emergency' trajectory (OTH:307-309) */
 
 /* action slots per scenario: slot 0 = straight | follow (mutually exclusive, MOPG:124-174), 1 = left, 2 = right */
 #define LTPL_NSLOT 3
@@ -55,7 +56,7 @@ extern "C" {
 #define LTPL_SC_HEADING_MISMATCH (1 << 1)  /* OTH:234-240                                                             */
 #define LTPL_SC_CAPACITY         (1 << 2)  /* a fixed-capacity buffer (P0_MAX / P_MAX / H_MAX) would overflow          */
 #define LTPL_SC_STATE_FALLBACK   (1 << 4)  /* stateful tick: the last executed trajectory is not usable as memory       */
-                                           /* (OTH:393-407 branch / backup plan OTH:950-1006): re-anchor with set_startpos */
+                                           /* (OTH:393-407 branch, or no backup plan to brake on): re-anchor w/ set_startpos */
 #define LTPL_SC_BRAKE_PREFIX     (1 << 3)  /* vel_plan > vel_max + 0.1: the reference path raises here (OTH:747-754,   */
                                            /* 830/919 column_stack length mismatch); reported instead of planned       */
 
@@ -240,6 +241,11 @@ typedef struct LtplBuffers {
     int32_t* zone_s0;               /* [B] start layer of the tick in which the scenario's zone was processed (GLNT:43-77:  */
                                     /*     the unblock window is evaluated once), -1: not yet; needed for zones in stateful  */
                                     /*     ticks, optional (NULL) otherwise                                                   */
+    /* executed 'emergency' trajectory (sel_action = LTPL_ACT_EMERGENCY): get_ref_idx (OTH:518-601) reads the velocity of  */
+    /* THAT trajectory; optional (NULL: such scenarios are flagged LTPL_SC_STATE_FALLBACK)                                 */
+    double* em_vx;                  /* [B][n_export] f64 velocity of this tick's emergency trajectory (k_emergency)        */
+    const double* prev_em_vx;       /* [B][n_export] the previous tick's                                                   */
+    const int32_t* prev_em_info;    /* [B][3] the previous tick's em_info (all -1 when it had no emergency trajectory)     */
 } LtplBuffers;
 
 /* stand-alone forward/backward ggv velocity profile over dense path arrays (BASELINE.json config 5).                   */

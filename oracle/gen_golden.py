@@ -291,9 +291,11 @@ def advance_on_traj(traj, dt):
             float(np.interp(s, traj[:, 0], traj[:, 5])))
 
 
-def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None):
+def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
+                      em_select=None):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
-    selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids)."""
+    selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
+    em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4)."""
     import graph_ltpl.online_graph.src.OnlineTrajectoryHandler as oth_mod
     from graphbasedlocaltrajectoryplanner_b200.scenarios import make_scenarios
     clock = ScriptedClock()
@@ -342,7 +344,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                        'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(objs)]
                 if traj_set is not None:
                     pos_est, vel_est = advance_on_traj(traj_set[sel][0], dt)
-                out['dt'][q, k], out['sel'][q, k] = dt, ACTIONS.index(sel)
+                out['dt'][q, k], out['sel'][q, k] = dt, (4 if sel == 'emergency' else ACTIONS.index(sel))
                 out['pos_est'][q, k], out['vel_est'][q, k] = pos_est, vel_est
                 out['obj'][q, k, :objs.shape[0]] = objs
                 bz = None if zones[q] is None else {'zone_%d' % q: zones[q]}
@@ -374,10 +376,13 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                 if not cand:
                     break
                 sel = cand[0]
+                if (em_select is not None and q % 2 == 1 and em_select[0] <= k <= em_select[1]
+                        and 'emergency' in traj_set):
+                    sel = 'emergency'
         out.update(sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj,
                    ax_max_machines=vel_kwargs['ax_max_machines'])
         print("[multitick] %d sequences, %d ticks; selected actions %s" % (
-            n_seq, int(out['n_done'].sum()), {a: int((out['sel'] == i).sum()) for i, a in enumerate(ACTIONS)}))
+            n_seq, int(out['n_done'].sum()), {a: int((out['sel'] == i).sum()) for i, a in enumerate(ACTIONS + ('emergency',))}))
         return out
     finally:
         oth_mod.time = real_time
@@ -446,6 +451,7 @@ def main():
     ap.add_argument('--ext-only', action='store_true', help='only the zone / emergency fixture (default lattice)')
     ap.add_argument('--n-ext', type=int, default=64)
     ap.add_argument('--multitick-only', action='store_true', help='only the closed-loop (stateful) fixture')
+    ap.add_argument('--emsel-only', action='store_true', help="only the closed-loop fixture executing 'emergency'")
     ap.add_argument('--pred-only', action='store_true', help="only the explicit-'prediction' fixture (default lattice)")
     ap.add_argument('--only', default=None, help='only this lattice configuration of the main loop (e.g. layers14)')
     ap.add_argument('--open-only', action='store_true', help='only the open-track fixture')
@@ -462,7 +468,7 @@ def main():
                       safety_d=30.0, incl_emerg_traj=False)
 
     if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
-                              or args.multitick_only):
+                              or args.multitick_only or args.emsel_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -503,7 +509,13 @@ def main():
     for tag, overrides, n, omin, omax in configs:
         ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
         fx, lat = lattice_fixture(graph_ltpl, ltpl)
-        if tag == "default" and (args.multitick_only or not (args.pred_only or args.ext_only)):
+        if tag == "default" and (args.emsel_only or args.multitick_only or not (args.pred_only or args.ext_only)):
+            # the odd sequences execute the emergency trajectory of ticks 2 .. 4 (OTH:307-309, get_ref_idx on it)
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_emsel_default.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 12, 8,
+                                                    dict(vel_kwargs, incl_emerg_traj=True), seed=6161, em_select=(2, 4)))
+            if args.emsel_only:
+                return
             np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_default.npz'),
                                 **multitick_fixture(graph_ltpl, ltpl, track, 16, 10, vel_kwargs))
             # the same with a blocked zone on every second sequence and the emergency trajectory switched on

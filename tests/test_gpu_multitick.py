@@ -34,10 +34,12 @@ class _Rows(object):
 @pytest.mark.parametrize("fixture,emerg,group", [("ticks_multitick_default.npz", False, None),
                                                  ("ticks_multitick_ext_default.npz", True, None),
                                                  ("ticks_multitick_backup_default.npz", False, 0),
-                                                 ("ticks_multitick_backup_default.npz", False, 1)])
+                                                 ("ticks_multitick_backup_default.npz", False, 1),
+                                                 ("ticks_multitick_emsel_default.npz", True, None)])
 def test_next_tick_matches_reference_sequences(fixture, emerg, group):
     """second fixture: a blocked zone on every second sequence + the emergency trajectory in every tick; third fixture:
-    the grip (gg_scale) drops on the odd sequences from tick 3 on -> brake on the backup plan (OTH:950-1006)."""
+    the grip (gg_scale) drops on the odd sequences from tick 3 on -> brake on the backup plan (OTH:950-1006); fourth
+    fixture: the odd sequences execute the 'emergency' trajectory of ticks 2 .. 4 (sel_action 4; OTH:307-309, 518-601)."""
     from graphbasedlocaltrajectoryplanner_b200 import capi
     from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
     from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
@@ -224,11 +226,14 @@ def test_closed_loop_matches_session_oracle():
     assert ticks_ok > n_seq * n_ticks // 2 and compared > n_seq * n_ticks // 2, (ticks_ok, compared, fell_back)
 
 
-def test_facade_runs_closed_loop_like_the_reference():
+@pytest.mark.parametrize("fixture,seqs,emerg", [("ticks_multitick_default.npz", (0, 5, 11), False),
+                                                ("ticks_multitick_emsel_default.npz", (1, 3), True)])
+def test_facade_runs_closed_loop_like_the_reference(fixture, seqs, emerg):
     """Graph_LTPL facade with the reference's call sequence over several ticks (main_std_example.py:99-126): an injected
-    clock takes the place of time.time(); three recorded sequences of the reference are replayed."""
+    clock takes the place of time.time(); recorded sequences of the reference are replayed (second case: the caller
+    executes the 'emergency' trajectory for three ticks, prev_action_id='emergency')."""
     from graphbasedlocaltrajectoryplanner_b200.Graph_LTPL import Graph_LTPL
-    g = H.golden("ticks_multitick_default.npz")
+    g = H.golden(fixture)
     pd = {'globtraj_input_path': H.TRACK_CSV, 'graph_store_path': "/tmp/_lat_default_test.npz",
           'ltpl_offline_param_path': H.OFFLINE_INI, 'ltpl_online_param_path': H.ONLINE_INI}
     ltpl = Graph_LTPL(path_dict=pd, visual_mode=False, log_to_file=False, device="cuda:0")
@@ -241,17 +246,18 @@ def test_facade_runs_closed_loop_like_the_reference():
             return self.t
     clk = Clk()
     ltpl.clock = clk
-    vel = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
+    vel = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0,
+               incl_emerg_traj=emerg)
     n_ticks = g["dt"].shape[1]
     compared = 0
-    for q in (0, 5, 11):
+    for q in seqs:
         assert ltpl.set_startpos(pos_est=g["sc_pos"][q], heading_est=g["sc_heading"][q], vel_est=g["sc_vel"][q]) is False
         n_obj = int(g["sc_n_obj"][q])
         for k in range(n_ticks):
             clk.t += float(g["dt"][q, k])
             ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
                    'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(g["obj"][q, k, :n_obj])]
-            paths = ltpl.calc_paths(prev_action_id=H.ACTIONS[int(g["sel"][q, k])], object_list=ol)
+            paths = ltpl.calc_paths(prev_action_id=(H.ACTIONS + ("emergency",))[int(g["sel"][q, k])], object_list=ol)
             traj, ids, _ = ltpl.calc_vel_profile(pos_est=g["pos_est"][q, k], vel_est=float(g["vel_est"][q, k]), **vel)
             ctx = "facade sequence %d tick %d" % (q, k)
             for a, act in enumerate(H.ACTIONS):
@@ -262,4 +268,7 @@ def test_facade_runs_closed_loop_like_the_reference():
                     H.assert_close("traj[%s]" % act, traj[act][0], g["traj"][q, k, a, :t_want],
                                    ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
                     compared += 1
-    assert compared > 40
+            if emerg and int(g["em_len"][q, k]):
+                H.assert_close("traj[emergency]", traj["emergency"][0], g["em_traj"][q, k, :int(g["em_len"][q, k])],
+                               ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+    assert compared > (20 if emerg else 40)

@@ -19,9 +19,11 @@ import pytest
 
 @pytest.mark.parametrize("fixture,emerg", [("ticks_multitick_default.npz", False),
                                            ("ticks_multitick_ext_default.npz", True),
-                                           ("ticks_multitick_backup_default.npz", False)])
+                                           ("ticks_multitick_backup_default.npz", False),
+                                           ("ticks_multitick_emsel_default.npz", True)])
 def test_session_oracle_matches_reference_sequences(fixture, emerg):
-    """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory."""
+    """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory; third:
+    grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks."""
     from oracle.ltpl_oracle import OracleLTPL
     from oracle.ltpl_session import OracleSession
     g = H.golden(fixture)
@@ -42,7 +44,7 @@ def test_session_oracle_matches_reference_sequences(fixture, emerg):
             clock.t += float(g["dt"][q, k])
             ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
                    'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(g["obj"][q, k, :n_obj])]
-            sel = H.ACTIONS[int(g["sel"][q, k])]
+            sel = (H.ACTIONS + ("emergency",))[int(g["sel"][q, k])]   # 4: OTH:307-309
             paths = ses.calc_paths(sel, ol, blocked_zones=H.zone_of(g, q))
             for a, act in enumerate(H.ACTIONS):
                 n_want = int(g["path_len"][q, k, a])
