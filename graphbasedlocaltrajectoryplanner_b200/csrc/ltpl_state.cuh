@@ -21,22 +21,23 @@
 
 #define LTPL_COURSE_MAX 8
 
-// get_s_coord(..., only_index=True)[1] on an OPEN polyline given by a gather (get_s_coord.py:40-58, 94-97): lanes hold the
-// polyline points; returns the pair (i0, i1)
-__device__ __forceinline__ int2 open_index_pair(double2 mine, int n, double px, double py, int lane) {
-    double d = LTPL_INF;
-    if (lane < n) d = dist2_rn(mine.x, mine.y, px, py);
-    const ArgMinD m = warp_argmin(d, (lane < n) ? lane : 0x7fffffff);
-    const int nb = m.i;
+// get_s_coord(..., only_index=True)[1] on an OPEN polyline given by a gather pt(i), i < n (get_s_coord.py:40-58, 94-97):
+// nearest point (first minimum), then the neighbour on the side of the larger angle; returns the pair (i0, i1)
+template <class PT>
+__device__ __forceinline__ int2 open_index_pair(PT pt, int n, double px, double py, int lane) {
+    double bv = LTPL_INF;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < n; j += 32) {
+        const double2 p = pt(j);
+        const double d = dist2_rn(p.x, p.y, px, py);
+        if (d < bv) {
+            bv = d;
+            bi = j;
+        }
+    }
+    const int nb = warp_argmin(bv, bi).i;
     const int idx1 = max(nb - 1, 0), idx2 = min(nb + 1, n - 1);
-    double2 pn, p1, p2;
-    pn.x = __shfl_sync(LTPL_FULL, mine.x, nb);
-    pn.y = __shfl_sync(LTPL_FULL, mine.y, nb);
-    p1.x = __shfl_sync(LTPL_FULL, mine.x, idx1);
-    p1.y = __shfl_sync(LTPL_FULL, mine.y, idx1);
-    p2.x = __shfl_sync(LTPL_FULL, mine.x, idx2);
-    p2.y = __shfl_sync(LTPL_FULL, mine.y, idx2);
-    return angle_cmp(pn, px, py, p1, p2).ge ? make_int2(idx1, nb) : make_int2(nb, idx2);
+    return angle_cmp(pt(nb), px, py, pt(idx1), pt(idx2)).ge ? make_int2(idx1, nb) : make_int2(nb, idx2);
 }
 
 // lattice edge (start layer, src node) -> (next layer, dst node), or -1 (GB.get_eid on the filtered graph, GB:505-511)
@@ -59,6 +60,9 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
     if (b >= dm.batch) return;
     const int B = dm.batch;
     int* info = bf.st_info + 8 * (size_t)b;
+    // a scenario whose start pose was rejected (set_startpos returned True, LTPL:268-298) stays so until it is re-anchored
+    if (bf.sc_flags[b] & (LTPL_SC_OUT_OF_TRACK | LTPL_SC_HEADING_MISMATCH)) return;
+    __syncwarp();
     if (lane == 0) {
         bf.start_node[2 * b] = -1;
         bf.start_node[2 * b + 1] = -1;
@@ -78,7 +82,7 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
         if (bf.prev_action_id[s * B + b] == sel && sel != LTPL_ACT_NONE) qp = s * B + b;
     const int nb_rows = (qp >= 0) ? bf.prev_traj_len[qp] : 0;
     if (qp < 0 || nb_rows <= 2) {   // OTH:319-322: no valid solution in the last step -> OTH:393-407 branch
-        if (lane == 0) bf.sc_flags[b] = LTPL_SC_STATE_FALLBACK;
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_STATE_FALLBACK | ((qp < 0 ? 1 : 2) << LTPL_SC_REASON_SHIFT);
         return;
     }
     const int m_p = bf.prev_trim[4 * qp + 0], L_p = bf.prev_trim[4 * qp + 1], c_p = bf.prev_trim[4 * qp + 2];
@@ -110,23 +114,19 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
 
     // first node after the predicted position (OTH:381-386)
     const int nn_mem = bf.prev_n_nodes[qp] - L_p;   // nodes of the (trimmed) memory
-    if (nn_mem < 2 || nn_mem > 32) {
-        if (lane == 0) bf.sc_flags[b] = (nn_mem > 32) ? LTPL_SC_CAPACITY : LTPL_SC_STATE_FALLBACK;
+    if (nn_mem < 2) {
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_STATE_FALLBACK | (3 << LTPL_SC_REASON_SHIFT);
         return;
     }
     const int* Ip = bf.prev_node_idx + (size_t)qp * dm.h_max + L_p;
     const int* Np = bf.prev_nodes + ((size_t)qp * dm.h_max + L_p) * 2;
-    double2 mine = make_double2(0.0, 0.0);
-    if (lane < nn_mem) {
-        const int pi = Ip[lane];
-        mine = make_double2(Px[pi], Py[pi]);
-    }
-    const int2 pair = open_index_pair(mine, nn_mem, ppx, ppy, lane);
+    const int2 pair = open_index_pair([&](int i) { const int pi = Ip[i]; return make_double2(Px[pi], Py[pi]); },
+                                      nn_mem, ppx, ppy, lane);
     const int sni = pair.y;                          // start_node_idx within the memory node list
     const int loc = Ip[sni] - m_p;                   // loc_path_start_idx within the memory path
     const int sl = Np[2 * sni], sn = Np[2 * sni + 1];
     if (sl < 0 || loc + 1 > dm.p_max) {
-        if (lane == 0) bf.sc_flags[b] = LTPL_SC_STATE_FALLBACK;
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_STATE_FALLBACK | ((sl < 0 ? 4 : 5) << LTPL_SC_REASON_SHIFT);
         return;
     }
     if (lane == 0) {
@@ -409,6 +409,6 @@ k_backup(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
             w = wn;
         }
         bf.traj_len[q] = min(n_p, dm.n_export);                 // k_prefix adds the vel_course rows
-        atomicAnd(&bf.sc_flags[b], ~LTPL_SC_STATE_FALLBACK);    // handled
+        atomicAnd(&bf.sc_flags[b], ~(LTPL_SC_STATE_FALLBACK | (7 << LTPL_SC_REASON_SHIFT)));    // handled
     }
 }

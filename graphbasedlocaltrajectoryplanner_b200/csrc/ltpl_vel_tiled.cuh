@@ -832,7 +832,7 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         // stateful tick: a backup plan exists (OTH:325-344), so a straight / follow profile that breaks the bound is
         // replaced by a brake profile on the OLD path (OTH:950-1006): flag here, k_backup plans it and clears the flag
         if (STATE && !vel_bound && (action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT))
-            atomicOr(&bf.sc_flags[b], LTPL_SC_STATE_FALLBACK);
+            atomicOr(&bf.sc_flags[b], LTPL_SC_STATE_FALLBACK | (6 << LTPL_SC_REASON_SHIFT));
         if (vel_bound || action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT) {
             st |= LTPL_ST_TRAJ_VALID;
             bf.traj_len[q] = min(n, dm.n_export);
