@@ -501,7 +501,7 @@ def main():
             del pl_4
         except Exception as e:   # noqa: BLE001
             extra["config4_l430_error"] = str(e)[:200]
-        try:   # stateful ticks (EXPERIMENTAL): closed loop of 8 ticks on the bench workload; a
+        try:   # stateful ticks: closed loop of 8 ticks on the bench workload; a
             # vehicle dummy advances every scenario 0.1 s on its first kept trajectory; the loop is recorded once
             # (untimed host work between the ticks) and replayed with CUDA events around every next_tick
             from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch

@@ -59,7 +59,7 @@ class Graph_LTPL(object):
         self.__pos = None
         self.__heading = None
         self.__objects = None
-        # iterative memory across ticks (EXPERIMENTAL): the clock is injectable for tests
+        # iterative memory across ticks: the clock is injectable for tests
         self.clock = time.time
         self.__tick_no = 0
         self.__last_path_timestamp = None
@@ -122,7 +122,7 @@ class Graph_LTPL(object):
         if self.__state is None:
             raise ValueError("calc_paths() needs a start pose: call set_startpos() first (after an out-of-track result or "
                              "a memory fallback again)")
-        if self.__state == "next":   # EXPERIMENTAL stateful tick: the memory of the last tick lives on the device
+        if self.__state == "next":   # stateful tick: the memory of the last tick lives on the device
             return self.__calc_paths_next(prev_action_id, object_list, blocked_zones)
         self.__last_path_timestamp = self.clock()   # OTH:395
         sc = ScenarioBatch.from_object_lists([self.__pos], [self.__heading], [self.__start_vel],

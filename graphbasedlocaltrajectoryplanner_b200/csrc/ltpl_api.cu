@@ -299,7 +299,7 @@ int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDim
     return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
 }
 
-// stateful tick (EXPERIMENTAL, ltpl_state.cuh):
+// stateful tick (ltpl_state.cuh):
 //   ltpl_next_calc_paths_batch        k_state -> k_plan<.., true> -> k_path<true>
 //   ltpl_next_calc_vel_profile_batch  k_ref -> k_vel_tiled<true> -> k_prefix -> k_export
 static int check_stateful(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf) {

@@ -1,4 +1,4 @@
-// ltpl_state.cuh -- stateful tick (EXPERIMENTAL): the iterative memory of OnlineTrajectoryHandler
+// ltpl_state.cuh -- stateful tick: the iterative memory of OnlineTrajectoryHandler
 // on the device.  The memory of the reference (OTH:64-87: __last_action_set_{path_param, node_idx, nodes, coeff},
 // __last_bp_action_set) IS the output of the previous tick: a second LtplBuffers set (prev_*) used ping-pong, plus three
 // integers per path instead of the slicing of OTH:705-731:

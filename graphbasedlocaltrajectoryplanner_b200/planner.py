@@ -403,7 +403,7 @@ class BatchPlanner(object):
         self.params.traj_base_id = 10 * self._tick_count
         self._call(self.lib.ltpl_tick_batch, "ltpl_tick_batch")
 
-    # -- stateful tick (EXPERIMENTAL: DESIGN.md section 11, csrc/ltpl_state.cuh) ----------------------------------------------
+    # -- stateful tick (csrc/ltpl_state.cuh) ----------------------------------------------
     _BIG = ("path", "node_idx", "nodes", "coeff", "s_vx_ax", "em_vx")            # swapped by pointer
     _SMALL = ("path_len", "n_nodes", "action_id", "traj_len", "trim", "em_info")  # copied (a few bytes per path)
 
@@ -428,7 +428,7 @@ class BatchPlanner(object):
         self._state = st
 
     def next_calc_paths(self, sc: ScenarioBatch, sel_action, t_const) -> None:
-        """calc_paths of a stateful tick (EXPERIMENTAL; OTH:289-516 with the iterative memory): ``sc`` carries the object
+        """calc_paths of a stateful tick (OTH:289-516 with the iterative memory): ``sc`` carries the object
         lists (its poses are only used by ``next_calc_vel_profile``), ``sel_action`` = action id (capi.ACT_*) every
         scenario executed since the last tick, ``t_const`` = min(average calculation time * calc_time_safety, 0.5) per
         scenario (OTH:353-375; the caller keeps the moving average).  The previous tick (tick() / calc_paths() +
@@ -456,7 +456,7 @@ class BatchPlanner(object):
         self._call(self.lib.ltpl_next_calc_paths_batch, "ltpl_next_calc_paths_batch")
 
     def next_calc_vel_profile(self, pos_est=None, vel_est=None) -> None:
-        """calc_vel_profile of a stateful tick (EXPERIMENTAL; OTH:518-601 + 603-1040): position / velocity estimates per
+        """calc_vel_profile of a stateful tick (OTH:518-601 + 603-1040): position / velocity estimates per
         scenario (None: the poses / velocities staged by ``next_calc_paths``)."""
         t, buf, st = self.t, self.buf, self._state
         if pos_est is not None:
@@ -475,7 +475,7 @@ class BatchPlanner(object):
             buf.vel = keep_vel
 
     def next_tick(self, sc: ScenarioBatch, sel_action, t_const, vel_est=None) -> None:
-        """One stateful tick for the whole batch (EXPERIMENTAL): ``sc.pos`` = position estimates."""
+        """One stateful tick for the whole batch: ``sc.pos`` = position estimates."""
         self.next_calc_paths(sc, sel_action, t_const)
         self.next_calc_vel_profile(vel_est=vel_est)
 

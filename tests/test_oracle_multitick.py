@@ -1,6 +1,6 @@
 """Stateful (multi-tick) oracle, oracle/ltpl_session.py, against closed-loop sequences of the unmodified reference driven
 with a scripted clock (tests/golden/ticks_multitick_default.npz, oracle/gen_golden.py:multitick_fixture).
-Groundwork of SURVEY 8(f) rank 1: the CUDA path plans first ticks only."""
+The checker of the stateful tick on the device (tests/test_gpu_multitick.py)."""
 import numpy as np
 
 from tests import helpers as H
