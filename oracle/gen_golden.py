@@ -292,10 +292,12 @@ def advance_on_traj(traj, dt):
 
 
 def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
-                      em_select=None):
+                      em_select=None, bad_select=None):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
-    em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4)."""
+    em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4).
+    bad_select=(k, ...): after those ticks the odd sequences name an action the tick did NOT return (OTH:393-407: no valid
+    last solution; the vehicle dummy keeps driving on the first returned trajectory)."""
     import graph_ltpl.online_graph.src.OnlineTrajectoryHandler as oth_mod
     from graphbasedlocaltrajectoryplanner_b200.scenarios import make_scenarios
     clock = ScriptedClock()
@@ -333,6 +335,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
             ltpl._Graph_LTPL__obj_list_handler._ObjectListInterface__object_zones = []
             objs = sc.obj[q, :int(sc.n_obj[q])].copy()
             pos_est, vel_est, sel, traj_set = np.array(sc.pos[q]), float(sc.vel[q]), "straight", None
+            drive = sel
             order = prefer[q % len(prefer)]
             for k in range(n_ticks):
                 dt = float(rng.uniform(0.04, 0.16))
@@ -343,7 +346,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                 ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
                        'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(objs)]
                 if traj_set is not None:
-                    pos_est, vel_est = advance_on_traj(traj_set[sel][0], dt)
+                    pos_est, vel_est = advance_on_traj(traj_set[drive][0], dt)
                 out['dt'][q, k], out['sel'][q, k] = dt, (4 if sel == 'emergency' else ACTIONS.index(sel))
                 out['pos_est'][q, k], out['vel_est'][q, k] = pos_est, vel_est
                 out['obj'][q, k, :objs.shape[0]] = objs
@@ -379,6 +382,11 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                 if (em_select is not None and q % 2 == 1 and em_select[0] <= k <= em_select[1]
                         and 'emergency' in traj_set):
                     sel = 'emergency'
+                drive = sel
+                if bad_select is not None and q % 2 == 1 and k in bad_select:
+                    missing = [a for a in ("left", "right", "follow", "straight") if a not in traj_set]
+                    if missing:
+                        sel, drive = missing[0], cand[0]
         out.update(sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj,
                    ax_max_machines=vel_kwargs['ax_max_machines'])
         print("[multitick] %d sequences, %d ticks; selected actions %s" % (
@@ -452,6 +460,7 @@ def main():
     ap.add_argument('--n-ext', type=int, default=64)
     ap.add_argument('--multitick-only', action='store_true', help='only the closed-loop (stateful) fixture')
     ap.add_argument('--emsel-only', action='store_true', help="only the closed-loop fixture executing 'emergency'")
+    ap.add_argument('--invalid-only', action='store_true', help='only the closed-loop fixture naming actions not returned')
     ap.add_argument('--pred-only', action='store_true', help="only the explicit-'prediction' fixture (default lattice)")
     ap.add_argument('--only', default=None, help='only this lattice configuration of the main loop (e.g. layers14)')
     ap.add_argument('--open-only', action='store_true', help='only the open-track fixture')
@@ -468,7 +477,7 @@ def main():
                       safety_d=30.0, incl_emerg_traj=False)
 
     if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
-                              or args.multitick_only or args.emsel_only):
+                              or args.multitick_only or args.emsel_only or args.invalid_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -509,6 +518,13 @@ def main():
     for tag, overrides, n, omin, omax in configs:
         ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
         fx, lat = lattice_fixture(graph_ltpl, ltpl)
+        if tag == "default" and (args.invalid_only or args.multitick_only or not (args.pred_only or args.ext_only)):
+            # the odd sequences name an action that was not returned after ticks 2 and 5 (OTH:393-407)
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_invalid_default.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 12, 8, vel_kwargs, seed=7171,
+                                                    bad_select=(2, 5)))
+            if args.invalid_only:
+                return
         if tag == "default" and (args.emsel_only or args.multitick_only or not (args.pred_only or args.ext_only)):
             # the odd sequences execute the emergency trajectory of ticks 2 .. 4 (OTH:307-309, get_ref_idx on it)
             np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_emsel_default.npz'),

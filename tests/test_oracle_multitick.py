@@ -20,10 +20,12 @@ import pytest
 @pytest.mark.parametrize("fixture,emerg", [("ticks_multitick_default.npz", False),
                                            ("ticks_multitick_ext_default.npz", True),
                                            ("ticks_multitick_backup_default.npz", False),
-                                           ("ticks_multitick_emsel_default.npz", True)])
+                                           ("ticks_multitick_emsel_default.npz", True),
+                                           ("ticks_multitick_invalid_default.npz", False)])
 def test_session_oracle_matches_reference_sequences(fixture, emerg):
     """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory; third:
-    grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks."""
+    grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks; fifth: the odd sequences name an action
+    the last tick did not return (OTH:393-407: old start node, no cost reduction, velocity from the initial v_start)."""
     from oracle.ltpl_oracle import OracleLTPL
     from oracle.ltpl_session import OracleSession
     g = H.golden(fixture)
