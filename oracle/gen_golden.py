@@ -292,7 +292,7 @@ def advance_on_traj(traj, dt):
 
 
 def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
-                      em_select=None, bad_select=None):
+                      em_select=None, bad_select=None, n_obj=(0, 2)):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
     em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4).
@@ -304,7 +304,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
     real_time = oth_mod.time
     oth_mod.time = clock
     try:
-        sc = make_scenarios(track, n_seq, seed=seed, n_obj_min=0, n_obj_max=2)
+        sc = make_scenarios(track, n_seq, seed=seed, n_obj_min=n_obj[0], n_obj_max=n_obj[1])
         rng = np.random.default_rng(seed + 1)
         emerg = bool(vel_kwargs.get('incl_emerg_traj'))
         zones = [(make_zone(lat, rng, sc.pos[q]) if (lat is not None and q % 2 == 0) else None) for q in range(n_seq)]
@@ -460,6 +460,7 @@ def main():
     ap.add_argument('--n-ext', type=int, default=64)
     ap.add_argument('--multitick-only', action='store_true', help='only the closed-loop (stateful) fixture')
     ap.add_argument('--emsel-only', action='store_true', help="only the closed-loop fixture executing 'emergency'")
+    ap.add_argument('--mt-l216-only', action='store_true', help='only the closed-loop fixture on the ~200 x 11 lattice')
     ap.add_argument('--invalid-only', action='store_true', help='only the closed-loop fixture naming actions not returned')
     ap.add_argument('--pred-only', action='store_true', help="only the explicit-'prediction' fixture (default lattice)")
     ap.add_argument('--only', default=None, help='only this lattice configuration of the main loop (e.g. layers14)')
@@ -477,7 +478,7 @@ def main():
                       safety_d=30.0, incl_emerg_traj=False)
 
     if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
-                              or args.multitick_only or args.emsel_only or args.invalid_only):
+                              or args.multitick_only or args.emsel_only or args.invalid_only or args.mt_l216_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -512,12 +513,21 @@ def main():
                         args.n_other, 5, 5))
         # planning horizon as a fixed number of layers (GLNT:126-136)
         configs.append(("layers14", {"plan_horizon_mode": "layers", "min_plan_horizon": 14}, args.n_other, 0, 3))
+    if args.mt_l216_only:
+        args.only = "l216"
     if args.only:
         configs = [c for c in configs if c[0] == args.only]
 
     for tag, overrides, n, omin, omax in configs:
         ltpl, path_dict = make_ltpl(graph_ltpl, tag, overrides)
         fx, lat = lattice_fixture(graph_ltpl, ltpl)
+        if tag == "l216":
+            # BASELINE's ~200 x 11 lattice: node lists of more than 32 entries, 1-3 objects, emergency trajectory on
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_l216.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 12, 8,
+                                                    dict(vel_kwargs, incl_emerg_traj=True), seed=8181, n_obj=(1, 3)))
+            if args.mt_l216_only:
+                return
         if tag == "default" and (args.invalid_only or args.multitick_only or not (args.pred_only or args.ext_only)):
             # the odd sequences name an action that was not returned after ticks 2 and 5 (OTH:393-407)
             np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_invalid_default.npz'),

@@ -17,19 +17,21 @@ class _Clock(object):
 import pytest
 
 
-@pytest.mark.parametrize("fixture,emerg", [("ticks_multitick_default.npz", False),
-                                           ("ticks_multitick_ext_default.npz", True),
-                                           ("ticks_multitick_backup_default.npz", False),
-                                           ("ticks_multitick_emsel_default.npz", True),
-                                           ("ticks_multitick_invalid_default.npz", False)])
-def test_session_oracle_matches_reference_sequences(fixture, emerg):
+@pytest.mark.parametrize("fixture,emerg,tag", [("ticks_multitick_default.npz", False, "default"),
+                                               ("ticks_multitick_ext_default.npz", True, "default"),
+                                               ("ticks_multitick_backup_default.npz", False, "default"),
+                                               ("ticks_multitick_emsel_default.npz", True, "default"),
+                                               ("ticks_multitick_invalid_default.npz", False, "default"),
+                                               ("ticks_multitick_l216.npz", True, "l216")])
+def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
     """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory; third:
     grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks; fifth: the odd sequences name an action
-    the last tick did not return (OTH:393-407: old start node, no cost reduction, velocity from the initial v_start)."""
+    the last tick did not return (OTH:393-407: old start node, no cost reduction, velocity from the initial v_start);
+    sixth: BASELINE's ~200 x 11 lattice (node lists of more than 32 entries), 1-3 objects, emergency trajectory."""
     from oracle.ltpl_oracle import OracleLTPL
     from oracle.ltpl_session import OracleSession
     g = H.golden(fixture)
-    lat = H.lattice_for("default")
+    lat = H.lattice_for(tag)
     vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0,
               incl_emerg_traj=emerg)
     n_seq, n_ticks = g["dt"].shape
