@@ -292,12 +292,14 @@ def advance_on_traj(traj, dt):
 
 
 def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
-                      em_select=None, bad_select=None, n_obj=(0, 2)):
+                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
     em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4).
     bad_select=(k, ...): after those ticks the odd sequences name an action the tick did NOT return (OTH:393-407: no valid
-    last solution; the vehicle dummy keeps driving on the first returned trajectory)."""
+    last solution; the vehicle dummy keeps driving on the first returned trajectory).
+    zone_swap=k: from tick k on the sequences with a zone pass ANOTHER zone under a new id (the old one is flagged removed
+    by ObjectListInterface.update_zone and emptied at once, BLOCK_N_LAYERS_WHEN_REMOVING_ZONE = 0; GLNT:43-99)."""
     import graph_ltpl.online_graph.src.OnlineTrajectoryHandler as oth_mod
     from graphbasedlocaltrajectoryplanner_b200.scenarios import make_scenarios
     clock = ScriptedClock()
@@ -327,6 +329,9 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
             if zones[q] is not None:
                 out['zone_layers'][q, :len(zones[q][0])] = zones[q][0]
                 out['zone_nodes'][q, :len(zones[q][1])] = zones[q][1]
+        if zone_swap is not None:
+            out.update(zone_swap_tick=np.int32(zone_swap), zone2_layers=np.full((n_seq, 400), -1, dtype=np.int32),
+                       zone2_nodes=np.full((n_seq, 400), -1, dtype=np.int32))
         for q in range(n_seq):
             if ltpl.set_startpos(pos_est=np.array(sc.pos[q]), heading_est=float(sc.heading[q]), vel_est=float(sc.vel[q])):
                 continue
@@ -351,6 +356,14 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                 out['pos_est'][q, k], out['vel_est'][q, k] = pos_est, vel_est
                 out['obj'][q, k, :objs.shape[0]] = objs
                 bz = None if zones[q] is None else {'zone_%d' % q: zones[q]}
+                if zone_swap is not None and zones[q] is not None and k >= zone_swap:
+                    if k == zone_swap:
+                        z2 = make_zone(lat, rng, pos_est)
+                        out['zone2_layers'][q, :len(z2[0])] = z2[0]
+                        out['zone2_nodes'][q, :len(z2[1])] = z2[1]
+                    n2 = int((out['zone2_layers'][q] >= 0).sum())
+                    bz = {'zone_%d_b' % q: [out['zone2_layers'][q, :n2].tolist(), out['zone2_nodes'][q, :n2].tolist(),
+                                            np.zeros((2, 2)), np.zeros((2, 2))]}
                 paths = ltpl.calc_paths(prev_action_id=sel, object_list=ol, blocked_zones=bz)
                 nodes = oth._OnlineTrajectoryHandler__last_action_set_nodes
                 for a, act in enumerate(ACTIONS):
@@ -461,6 +474,7 @@ def main():
     ap.add_argument('--multitick-only', action='store_true', help='only the closed-loop (stateful) fixture')
     ap.add_argument('--emsel-only', action='store_true', help="only the closed-loop fixture executing 'emergency'")
     ap.add_argument('--mt-l216-only', action='store_true', help='only the closed-loop fixture on the ~200 x 11 lattice')
+    ap.add_argument('--zswap-only', action='store_true', help='only the closed-loop fixture with a zone replaced')
     ap.add_argument('--invalid-only', action='store_true', help='only the closed-loop fixture naming actions not returned')
     ap.add_argument('--pred-only', action='store_true', help="only the explicit-'prediction' fixture (default lattice)")
     ap.add_argument('--only', default=None, help='only this lattice configuration of the main loop (e.g. layers14)')
@@ -478,7 +492,8 @@ def main():
                       safety_d=30.0, incl_emerg_traj=False)
 
     if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
-                              or args.multitick_only or args.emsel_only or args.invalid_only or args.mt_l216_only):
+                              or args.multitick_only or args.emsel_only or args.invalid_only or args.mt_l216_only
+                              or args.zswap_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -527,6 +542,13 @@ def main():
                                 **multitick_fixture(graph_ltpl, ltpl, track, 12, 8,
                                                     dict(vel_kwargs, incl_emerg_traj=True), seed=8181, n_obj=(1, 3)))
             if args.mt_l216_only:
+                return
+        if tag == "default" and (args.zswap_only or args.multitick_only or not (args.pred_only or args.ext_only)):
+            # the even sequences replace their zone by another one at tick 4
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_zswap_default.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 12, 8, vel_kwargs, lat=lat, seed=9191,
+                                                    zone_swap=4))
+            if args.zswap_only:
                 return
         if tag == "default" and (args.invalid_only or args.multitick_only or not (args.pred_only or args.ext_only)):
             # the odd sequences name an action that was not returned after ticks 2 and 5 (OTH:393-407)

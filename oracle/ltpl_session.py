@@ -135,8 +135,9 @@ class OracleSession(object):
                 raise NotImplementedError("more than one blocked zone per tick is not a defined input of the reference")
             zid = list(blocked_zones.keys())[0]
             if self.zone_nodes is None or self.zone_nodes[0] != zid:
-                if self.zone_nodes is not None:
-                    raise NotImplementedError("zone replacement (disabled zones, GLNT:78-91) is not restated")
+                # a zone under a new id: update_zone (OLI:155-237) flags the old one as removed; GLNT:78-91 keeps its nodes
+                # within the next BLOCK_N_LAYERS_WHEN_REMOVING_ZONE = 0 layers, i.e. none -- it is empty from this tick on
+                # and dropped by the next update_zone; the new zone is processed with the CURRENT start node
                 self.zone_nodes = (zid, orc.zone_removed_nodes(self.start_node, blocked_zones))
             zone = self.zone_nodes[1]
         elif self.zone_nodes is not None:

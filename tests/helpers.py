@@ -130,11 +130,16 @@ def compare_records(got, want, ctx=""):
                      ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
 
 
-def zone_of(g, b):
-    """blocked_zones dict of scenario b of the zone / emergency fixture (None: no zone)."""
+def zone_of(g, b, tick=0):
+    """blocked_zones dict of scenario b of the zone / emergency fixture (None: no zone); fixtures with a zone swap pass
+    another zone under a new id from tick `zone_swap_tick` on."""
     n = int((g["zone_layers"][b] >= 0).sum())
     if n == 0:
         return None
+    if "zone_swap_tick" in g.files and tick >= int(g["zone_swap_tick"]):
+        n2 = int((g["zone2_layers"][b] >= 0).sum())
+        return {"zone_%d_b" % b: [g["zone2_layers"][b, :n2].tolist(), g["zone2_nodes"][b, :n2].tolist(), np.zeros((2, 2)),
+                                  np.zeros((2, 2))]}
     return {"zone_%d" % b: [g["zone_layers"][b, :n].tolist(), g["zone_nodes"][b, :n].tolist(), np.zeros((2, 2)),
                             np.zeros((2, 2))]}
 

@@ -22,12 +22,14 @@ import pytest
                                                ("ticks_multitick_backup_default.npz", False, "default"),
                                                ("ticks_multitick_emsel_default.npz", True, "default"),
                                                ("ticks_multitick_invalid_default.npz", False, "default"),
-                                               ("ticks_multitick_l216.npz", True, "l216")])
+                                               ("ticks_multitick_l216.npz", True, "l216"),
+                                               ("ticks_multitick_zswap_default.npz", False, "default")])
 def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
     """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory; third:
     grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks; fifth: the odd sequences name an action
     the last tick did not return (OTH:393-407: old start node, no cost reduction, velocity from the initial v_start);
-    sixth: BASELINE's ~200 x 11 lattice (node lists of more than 32 entries), 1-3 objects, emergency trajectory."""
+    sixth: BASELINE's ~200 x 11 lattice (node lists of more than 32 entries), 1-3 objects, emergency trajectory; seventh:
+    the even sequences replace their blocked zone by another one (new id) at tick 4 (OLI:155-237, GLNT:43-99)."""
     from oracle.ltpl_oracle import OracleLTPL
     from oracle.ltpl_session import OracleSession
     g = H.golden(fixture)
@@ -49,7 +51,7 @@ def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
             ol = [{'id': j + 1, 'type': 'physical', 'X': float(o[0]), 'Y': float(o[1]), 'theta': float(o[2]),
                    'v': float(o[3]), 'length': float(o[4]), 'width': 2.5} for j, o in enumerate(g["obj"][q, k, :n_obj])]
             sel = (H.ACTIONS + ("emergency",))[int(g["sel"][q, k])]   # 4: OTH:307-309
-            paths = ses.calc_paths(sel, ol, blocked_zones=H.zone_of(g, q))
+            paths = ses.calc_paths(sel, ol, blocked_zones=H.zone_of(g, q, k))
             for a, act in enumerate(H.ACTIONS):
                 n_want = int(g["path_len"][q, k, a])
                 assert (act in paths) == (n_want > 0), "%s: path %s present=%s, golden %d" % (ctx, act, act in paths,
