@@ -292,7 +292,7 @@ def advance_on_traj(traj, dt):
 
 
 def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
-                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None):
+                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None, s_max=None):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
     em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4).
@@ -306,7 +306,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
     real_time = oth_mod.time
     oth_mod.time = clock
     try:
-        sc = make_scenarios(track, n_seq, seed=seed, n_obj_min=n_obj[0], n_obj_max=n_obj[1])
+        sc = make_scenarios(track, n_seq, seed=seed, n_obj_min=n_obj[0], n_obj_max=n_obj[1], s_max=s_max)
         rng = np.random.default_rng(seed + 1)
         emerg = bool(vel_kwargs.get('incl_emerg_traj'))
         zones = [(make_zone(lat, rng, sc.pos[q]) if (lat is not None and q % 2 == 0) else None) for q in range(n_seq)]
@@ -474,6 +474,7 @@ def main():
     ap.add_argument('--multitick-only', action='store_true', help='only the closed-loop (stateful) fixture')
     ap.add_argument('--emsel-only', action='store_true', help="only the closed-loop fixture executing 'emergency'")
     ap.add_argument('--mt-l216-only', action='store_true', help='only the closed-loop fixture on the ~200 x 11 lattice')
+    ap.add_argument('--mt-open-only', action='store_true', help='only the closed-loop fixture on the open track')
     ap.add_argument('--zswap-only', action='store_true', help='only the closed-loop fixture with a zone replaced')
     ap.add_argument('--invalid-only', action='store_true', help='only the closed-loop fixture naming actions not returned')
     ap.add_argument('--pred-only', action='store_true', help="only the explicit-'prediction' fixture (default lattice)")
@@ -491,7 +492,7 @@ def main():
     vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
                       safety_d=30.0, incl_emerg_traj=False)
 
-    if args.open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
+    if args.open_only or args.mt_open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
                               or args.multitick_only or args.emsel_only or args.invalid_only or args.mt_l216_only
                               or args.zswap_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
@@ -503,6 +504,12 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, 'lattice_open.npz'), **fx)
         print("[open] lattice: %s" % lat.summary())
         tr_open = Track(open_csv)
+        # closed loop on the open track: the vehicle runs towards the end of the race line (reduced horizons, v_end = 0)
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_open.npz'),
+                            **multitick_fixture(graph_ltpl, ltpl, tr_open, 16, 8, vel_kwargs, seed=1212,
+                                                s_max=tr_open.length - 8.0))
+        if args.mt_open_only:
+            return
         sc = make_scenarios(tr_open, args.n_open, seed=DEFAULT_SEED + 99, n_obj_min=0, n_obj_max=3,
                             s_max=tr_open.length - 8.0)
         recs = [run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], sc.object_list(b), vel_kwargs, full=True)

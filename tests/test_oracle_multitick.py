@@ -23,13 +23,15 @@ import pytest
                                                ("ticks_multitick_emsel_default.npz", True, "default"),
                                                ("ticks_multitick_invalid_default.npz", False, "default"),
                                                ("ticks_multitick_l216.npz", True, "l216"),
-                                               ("ticks_multitick_zswap_default.npz", False, "default")])
+                                               ("ticks_multitick_zswap_default.npz", False, "default"),
+                                               ("ticks_multitick_open.npz", False, "open")])
 def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
     """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory; third:
     grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks; fifth: the odd sequences name an action
     the last tick did not return (OTH:393-407: old start node, no cost reduction, velocity from the initial v_start);
     sixth: BASELINE's ~200 x 11 lattice (node lists of more than 32 entries), 1-3 objects, emergency trajectory; seventh:
-    the even sequences replace their blocked zone by another one (new id) at tick 4 (OLI:155-237, GLNT:43-99)."""
+    the even sequences replace their blocked zone by another one (new id) at tick 4 (OLI:155-237, GLNT:43-99); eighth:
+    the open track, vehicles running towards the end of the race line (reduced horizons, v_end = 0)."""
     from oracle.ltpl_oracle import OracleLTPL
     from oracle.ltpl_session import OracleSession
     g = H.golden(fixture)
