@@ -292,7 +292,7 @@ def advance_on_traj(traj, dt):
 
 
 def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
-                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None, s_max=None):
+                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None, s_max=None, hmax=40):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
     em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4).
@@ -313,7 +313,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
         zmax = max([len(z[0]) for z in zones if z is not None] + [1])
         prefer = (("right", "left", "straight", "follow"), ("follow", "straight", "left", "right"),
                   ("left", "straight", "follow", "right"))
-        hmax, pmax = 40, 115
+        pmax = 115
         out = dict(dt=np.zeros((n_seq, n_ticks)), sel=np.full((n_seq, n_ticks), -1, dtype=np.int32),
                    pos_est=np.zeros((n_seq, n_ticks, 2)), vel_est=np.zeros((n_seq, n_ticks)),
                    obj=np.zeros((n_seq, n_ticks, sc.obj.shape[1], 5)),
@@ -474,6 +474,7 @@ def main():
     ap.add_argument('--multitick-only', action='store_true', help='only the closed-loop (stateful) fixture')
     ap.add_argument('--emsel-only', action='store_true', help="only the closed-loop fixture executing 'emergency'")
     ap.add_argument('--mt-l216-only', action='store_true', help='only the closed-loop fixture on the ~200 x 11 lattice')
+    ap.add_argument('--mt-l430-only', action='store_true', help='only the closed-loop fixture on the 400 x 21 lattice')
     ap.add_argument('--mt-open-only', action='store_true', help='only the closed-loop fixture on the open track')
     ap.add_argument('--zswap-only', action='store_true', help='only the closed-loop fixture with a zone replaced')
     ap.add_argument('--invalid-only', action='store_true', help='only the closed-loop fixture naming actions not returned')
@@ -494,7 +495,7 @@ def main():
 
     if args.open_only or args.mt_open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
                               or args.multitick_only or args.emsel_only or args.invalid_only or args.mt_l216_only
-                              or args.zswap_only):
+                              or args.zswap_only or args.mt_l430_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -537,6 +538,8 @@ def main():
         configs.append(("layers14", {"plan_horizon_mode": "layers", "min_plan_horizon": 14}, args.n_other, 0, 3))
     if args.mt_l216_only:
         args.only = "l216"
+    if args.mt_l430_only:
+        args.only = "l430"
     if args.only:
         configs = [c for c in configs if c[0] == args.only]
 
@@ -549,6 +552,13 @@ def main():
                                 **multitick_fixture(graph_ltpl, ltpl, track, 12, 8,
                                                     dict(vel_kwargs, incl_emerg_traj=True), seed=8181, n_obj=(1, 3)))
             if args.mt_l216_only:
+                return
+        if tag == "l430":
+            # config 4: 430 layers x 13-25 nodes, 5 objects per scenario
+            np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_l430.npz'),
+                                **multitick_fixture(graph_ltpl, ltpl, track, 8, 6, vel_kwargs, seed=4343, n_obj=(5, 5),
+                                                    hmax=80))
+            if args.mt_l430_only:
                 return
         if tag == "default" and (args.zswap_only or args.multitick_only or not (args.pred_only or args.ext_only)):
             # the even sequences replace their zone by another one at tick 4
