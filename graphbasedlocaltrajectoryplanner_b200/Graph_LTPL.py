@@ -55,6 +55,7 @@ class Graph_LTPL(object):
         self.__lattice = None
         self.__state = None          # None | "start" | "paths"
         self.__records = None
+        self.__zones = None          # the last blocked_zones dict: the reference keeps its zone objects when none is passed
         self.__start_vel = 0.0
         self.__pos = None
         self.__heading = None
@@ -122,6 +123,9 @@ class Graph_LTPL(object):
         if self.__state is None:
             raise ValueError("calc_paths() needs a start pose: call set_startpos() first (after an out-of-track result or "
                              "a memory fallback again)")
+        if blocked_zones:                # LTPL:324-329: update_zone only runs for a passed dict, the zone objects persist
+            self.__zones = blocked_zones
+        blocked_zones = self.__zones
         if self.__state == "next":   # stateful tick: the memory of the last tick lives on the device
             return self.__calc_paths_next(prev_action_id, object_list, blocked_zones)
         self.__last_path_timestamp = self.clock()   # OTH:395
