@@ -2,7 +2,7 @@
 the first kept trajectory) through the session ORACLE on a sample of the bench workload and count which branches of the
 reference's iterative memory occur -- in particular those the device flags LTPL_SC_STATE_FALLBACK.
 
-    python tools/cpu_stateful_diag.py [--n 400] [--tag l216] [--procs 8]
+    python tests/tools/cpu_stateful_diag.py [--n 400] [--tag l216] [--procs 8]
 """
 import argparse
 import collections
@@ -12,7 +12,7 @@ from multiprocessing import Pool
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 import bench  # noqa: E402
 from tests import helpers as H  # noqa: E402

@@ -1,6 +1,6 @@
 """debug helper (GPU box): per-scenario diff of the CUDA path against the oracle with details."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from tests import helpers as H
 from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner

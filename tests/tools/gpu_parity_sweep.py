@@ -2,7 +2,7 @@
 rules of tests/helpers.compare_records (node sequences bit-exact, coordinates / velocities 1e-4).  The oracle runs in a
 process pool on the host cores.   python tools/gpu_parity_sweep.py [n_per_lattice] [lattice ...]"""
 import os, sys, time
-REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, REPO)
 import numpy as np
 

@@ -2,7 +2,7 @@
 LTPL_SC_STATE_FALLBACK / LTPL_SC_CAPACITY for the first time, by reason code (bits 8..10 of sc_flags), and for a few of
 them what the session oracle (the reference's behaviour) does with the same inputs.
 
-    python tools/gpu_stateful_diag.py [--batch 10000] [--ticks 8] [--show 10] > gpurun_out/stateful_diag.txt
+    python tests/tools/gpu_stateful_diag.py [--batch 10000] [--ticks 8] [--show 10] > gpurun_out/stateful_diag.txt
 """
 import argparse
 import collections
@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 import bench  # noqa: E402
 from graphbasedlocaltrajectoryplanner_b200 import capi  # noqa: E402
