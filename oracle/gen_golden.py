@@ -475,6 +475,7 @@ def main():
     ap.add_argument('--emsel-only', action='store_true', help="only the closed-loop fixture executing 'emergency'")
     ap.add_argument('--mt-l216-only', action='store_true', help='only the closed-loop fixture on the ~200 x 11 lattice')
     ap.add_argument('--mt-l430-only', action='store_true', help='only the closed-loop fixture on the 400 x 21 lattice')
+    ap.add_argument('--mt-variant-only', action='store_true', help='only the closed-loop fixture with the PDtan variant')
     ap.add_argument('--mt-open-only', action='store_true', help='only the closed-loop fixture on the open track')
     ap.add_argument('--zswap-only', action='store_true', help='only the closed-loop fixture with a zone replaced')
     ap.add_argument('--invalid-only', action='store_true', help='only the closed-loop fixture naming actions not returned')
@@ -495,7 +496,7 @@ def main():
 
     if args.open_only or args.mt_open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
                               or args.multitick_only or args.emsel_only or args.invalid_only or args.mt_l216_only
-                              or args.zswap_only or args.mt_l430_only):
+                              or args.zswap_only or args.mt_l430_only or args.mt_variant_only):
         # open (unclosed) track: planning range clamp at the last layer, reduced horizons, v_end = 0 (GLNT:112-124, quirk
         # q7; MOPG:203-243; OTH:846-859)
         open_csv = os.path.join(REPO, "inputs", "traj_ltpl_cl", "traj_ltpl_cl_monteblanco_open.csv")
@@ -524,6 +525,19 @@ def main():
             {a: int((pk['path_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)}, int(pk['red_len'].sum()),
             int(pk['out_of_track'].sum())))
         if args.open_only:
+            return
+    if args.mt_variant_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
+                                    or args.multitick_only or args.emsel_only or args.invalid_only
+                                    or args.mt_l216_only or args.zswap_only or args.mt_l430_only or args.open_only):
+        # closed loop with the first parameter variant (PDtan follow controller, friction-ellipse exponent 1.5, other
+        # mass / drag, gg scale 0.9, asymmetric gg, v_max 85)
+        var = VARIANTS[0]
+        ltpl_v, _ = make_ltpl(graph_ltpl, "default", {}, controller_type=var["controller_type"], veh=var["veh"])
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_pdtan_default.npz'),
+                            **multitick_fixture(graph_ltpl, ltpl_v, track, 12, 8,
+                                                dict(var["vel"], ax_max_machines=ax_max_machines_table(),
+                                                     incl_emerg_traj=False), seed=3131, n_obj=(1, 3)))
+        if args.mt_variant_only:
             return
     if args.variants_only:
         np.savez_compressed(os.path.join(GOLDEN, 'ticks_variants_default.npz'),

@@ -25,27 +25,35 @@ import pytest
                                                ("ticks_multitick_l216.npz", True, "l216"),
                                                ("ticks_multitick_zswap_default.npz", False, "default"),
                                                ("ticks_multitick_open.npz", False, "open"),
-                                               ("ticks_multitick_l430.npz", False, "l430")])
+                                               ("ticks_multitick_l430.npz", False, "l430"),
+                                               ("ticks_multitick_pdtan_default.npz", False, "default:pdtan_exp15")])
 def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
     """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory; third:
     grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks; fifth: the odd sequences name an action
     the last tick did not return (OTH:393-407: old start node, no cost reduction, velocity from the initial v_start);
     sixth: BASELINE's ~200 x 11 lattice (node lists of more than 32 entries), 1-3 objects, emergency trajectory; seventh:
     the even sequences replace their blocked zone by another one (new id) at tick 4 (OLI:155-237, GLNT:43-99); eighth:
-    the open track, vehicles running towards the end of the race line (reduced horizons, v_end = 0)."""
+    the open track, vehicles running towards the end of the race line (reduced horizons, v_end = 0); further: the 400 x 21
+    lattice with 5 objects; the PDtan follow controller with friction-ellipse exponent 1.5, other mass / drag / gg."""
     from oracle.ltpl_oracle import OracleLTPL
     from oracle.ltpl_session import OracleSession
     g = H.golden(fixture)
+    tag, _, variant = tag.partition(":")
     lat = H.lattice_for(tag)
     vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0,
               incl_emerg_traj=emerg)
+    orc_kw = {}
+    if variant:                                            # other controller / vehicle / velocity parameters (H.VARIANTS)
+        online, veh, vel, _ = H.VARIANTS[variant]
+        orc_kw = dict(online=online, **veh)
+        vk.update(vel)
     n_seq, n_ticks = g["dt"].shape
     compared = 0
     for q in range(n_seq):
         if int(g["n_done"][q]) == 0:
             continue
         clock = _Clock()
-        ses = OracleSession(OracleLTPL(lat), clock=clock)
+        ses = OracleSession(OracleLTPL(lat, **orc_kw), clock=clock)
         assert ses.set_startpos(g["sc_pos"][q], g["sc_heading"][q], g["sc_vel"][q]) is False
         n_obj = int(g["sc_n_obj"][q])
         for k in range(int(g["n_done"][q])):
