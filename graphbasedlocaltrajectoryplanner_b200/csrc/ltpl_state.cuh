@@ -82,6 +82,8 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
     int qp = -1;
     for (int s = 0; s < LTPL_NSLOT; ++s)
         if (bf.prev_action_id[s * B + b] == sel && sel != LTPL_ACT_NONE) qp = s * B + b;
+    // an action set removed by the velocity planner (OTH:1007-1025) was popped from the memory dicts as well
+    if (qp >= 0 && bf.prev_traj_len[qp] == 0) qp = -1;
     const int nb_rows = (qp >= 0) ? bf.prev_traj_len[qp] : 0;
     if (qp < 0 && old_flags == 0 && old_sl >= 0) {
         // OTH:393-407 with an executed action the last tick did not return (no constant segment, OTH:409-411): the search
