@@ -12,7 +12,7 @@ import os
 import subprocess
 import sys
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 NSLOT = 3
 KMAX = 16
 MAX_AXM = 32
@@ -45,7 +45,7 @@ class LatticeHeader(C.Structure):
                     "off_node_off", "off_raceline_index", "off_s_raceline", "off_vel_raceline", "off_refline",
                     "off_raceline", "off_bound1", "off_bound2", "off_centerline", "off_node_xy", "off_node_psi",
                     "off_node_layer", "off_in_off", "off_edge_layer_off", "off_edge_src", "off_edge_dst",
-                    "off_edge_cost", "off_edge_len", "off_edge_psi1", "off_samp_off", "off_samp_xy", "off_samp_el",
+                    "off_edge_cost", "off_edge_len", "off_edge_psi1", "off_edge_psi0", "off_samp_off", "off_samp_xy", "off_samp_el",
                     "off_samp_edge", "off_glob_rl", "off_glob_xy", "off_edge_rec", "off_tab_reach", "off_tab_node",
                     "off_tab_edge", "blob_bytes")])
 

@@ -151,6 +151,7 @@ int ltpl_lattice_create(const LtplLatticeHeader* h, void* dev_blob, LtplLattice*
     LTPL_PTR(edge_cost, double, off_edge_cost);
     LTPL_PTR(edge_len, double, off_edge_len);
     LTPL_PTR(edge_psi1, double, off_edge_psi1);
+    LTPL_PTR(edge_psi0, double, off_edge_psi0);
     LTPL_PTR(samp_off, int, off_samp_off);
     LTPL_PTR(samp_xy, double2, off_samp_xy);
     LTPL_PTR(samp_el, double, off_samp_el);

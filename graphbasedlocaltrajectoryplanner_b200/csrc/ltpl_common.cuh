@@ -54,6 +54,7 @@ struct LatDev {
     const double* edge_cost;
     const double* edge_len;
     const double* edge_psi1;
+    const double* edge_psi0;
     const int* samp_off;
     const double2* samp_xy;
     const double* samp_el;

@@ -119,7 +119,9 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     }
     __syncwarp();
     const int p_new = nidx[nseg] + 1;
-    const int loc = p0 - 1;  // closest_path_index(start node) on the constant segment == its last point (OTH:398-404)
+    // closest_path_index(start node) on the constant segment == its last point (OTH:398-404); stateful tick without a
+    // constant segment (p0 == 0, OTH:405-411): nothing in front of the new path
+    const int loc = (STATE && p0 == 0) ? 0 : p0 - 1;
     const int p_tot = loc + p_new;
     if (p_tot > dm.p_max) {
         if (lane == 0) {
@@ -131,7 +133,8 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     }
 
     // ---- C2 spline through the nodes: tridiagonal system in the knot tangents m_k (== tph.calc_splines) ----
-    const double psi_s = cs[2 * cplane + p0 - 1];           // MOPG:300-301: heading at the end of the constant segment
+    // MOPG:300-303: heading at the end of the constant segment, else of the first sample of the first edge
+    const double psi_s = (STATE && p0 == 0) ? lt.edge_psi0[eid[0]] : cs[2 * cplane + p0 - 1];
     const double psi_e = lt.edge_psi1[eid[nseg - 1]];       // MOPG:307: psi of the last sample
     // rows k = 1 .. nseg-1:  (2/el[k-1]) m[k-1] + 4 (1/el[k-1] + 1/el[k]) m[k] + (2/el[k]) m[k+1] = r[k]
     // The rows themselves (lo, r_x, r_y; di and up follow from lo) do not depend on the elimination: all lanes build

@@ -61,7 +61,9 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
     const int B = dm.batch;
     int* info = bf.st_info + 8 * (size_t)b;
     // a scenario whose start pose was rejected (set_startpos returned True, LTPL:268-298) stays so until it is re-anchored
-    if (bf.sc_flags[b] & (LTPL_SC_OUT_OF_TRACK | LTPL_SC_HEADING_MISMATCH)) return;
+    const int old_flags = bf.sc_flags[b];
+    if (old_flags & (LTPL_SC_OUT_OF_TRACK | LTPL_SC_HEADING_MISMATCH)) return;
+    const int old_sl = bf.start_node[2 * b], old_sn = bf.start_node[2 * b + 1];   // start node of the last tick (OTH:393-407)
     __syncwarp();
     if (lane == 0) {
         bf.start_node[2 * b] = -1;
@@ -80,8 +82,30 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
     int qp = -1;
     for (int s = 0; s < LTPL_NSLOT; ++s)
         if (bf.prev_action_id[s * B + b] == sel && sel != LTPL_ACT_NONE) qp = s * B + b;
+    // an action set removed by the velocity planner (OTH:1007-1025) was popped from the memory dicts as well
+    if (qp >= 0 && bf.prev_traj_len[qp] == 0) qp = -1;
     const int nb_rows = (qp >= 0) ? bf.prev_traj_len[qp] : 0;
-    if (qp < 0 || nb_rows <= 2) {   // OTH:319-322: no valid solution in the last step -> OTH:393-407 branch
+    if (qp < 0 && old_flags == 0 && old_sl >= 0) {
+        // OTH:393-407 with an executed action the last tick did not return (no constant segment, OTH:409-411): the search
+        // starts at the OLD start node again, nothing is stitched (OTH:433-472 skipped), no cost reduction (GLNT:155), no
+        // backup plan (OTH:339-344), and get_ref_idx falls back to the initial velocity (OTH:592-598: cut 0, v_start).
+        // Marker for the later kernels: const_len == 0.
+        if (lane == 0) {
+            bf.sc_flags[b] = 0;
+            bf.start_node[2 * b] = old_sl;
+            bf.start_node[2 * b + 1] = old_sn;
+            bf.const_len[b] = 0;
+            info[0] = b;                                 // a valid row; nothing of it is used (cnd = 0, const_len = 0)
+            info[1] = 0;
+            info[2] = 0;
+            info[3] = 0;
+            info[4] = 0;
+            info[5] = info[6] = info[7] = -1;
+            bf.vel_plan[b] = bf.vel[b];                  // `vel` of a stateful tick = v_start of set_startpos (OTH:597)
+        }
+        return;
+    }
+    if (qp < 0 || nb_rows <= 2) {   // OTH:319-322, constant segment exists but <= 2 trajectory rows: not planned
         if (lane == 0) bf.sc_flags[b] = LTPL_SC_STATE_FALLBACK | ((qp < 0 ? 1 : 2) << LTPL_SC_REASON_SHIFT);
         return;
     }
@@ -153,6 +177,52 @@ k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuff
     }
 }
 
+// follow mode: distance to the closest object along the cut follow path (OTH:766-784); no object -> 0 (OTH:766-768)
+__device__ __forceinline__ void ref_obj_dist(const LtplDims& dm, const LtplBuffers& bf, int b, int cut_pos, double px,
+                                             double py, int lane) {
+    const int B = dm.batch;
+    const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
+    if (lane == 0) bf.obj_dist[b] = 0.0;
+    __syncwarp();
+    const int qf = b;   // slot 0
+    if (bf.action_id[qf] == LTPL_ACT_FOLLOW && bf.closest_obj[b] >= 0) {
+        const int n = bf.path_len[qf] - cut_pos;
+        const double* X = bf.path + (size_t)qf * dm.p_max + cut_pos;
+        const double* Y = X + pplane;
+        const double* E = X + 4 * pplane;
+        double s_two[2];
+#pragma unroll 1
+        for (int w = 0; w < 2; ++w) {
+            const double tx = w ? px : bf.cobj[4 * b], ty = w ? py : bf.cobj[4 * b + 1];
+            double v2 = LTPL_INF;
+            int i2 = 0x7fffffff;
+            for (int j = lane; j < n; j += 32) {
+                const double d = dist2_rn(X[j], Y[j], tx, ty);
+                if (d < v2) {
+                    v2 = d;
+                    i2 = j;
+                }
+            }
+            const int nbp = warp_argmin(v2, i2).i;
+            const int i1 = max(nbp - 1, 0), j2 = min(nbp + 1, n - 1);
+            const bool gt = angle_cmp(make_double2(X[nbp], Y[nbp]), tx, ty, make_double2(X[i1], Y[i1]),
+                                      make_double2(X[j2], Y[j2])).gt;
+            const int ia = gt ? i1 : nbp, ib = gt ? nbp : j2;
+            // s_array = cumsum(el) of the cut path; leading 0 inserted when el[0] > 0.05 (get_s_coord.py:67-68)
+            double acc = 0.0;                        // cumsum(el)[ia - 1 + ins] evaluated by lane 0 order of np.cumsum
+            const bool ins = E[0] > 0.05;
+            const int upto = ins ? ia : ia + 1;      // number of el terms summed
+            for (int j = 0; j < upto; ++j) acc = __dadd_rn(acc, E[j]);
+            const double ax_ = X[ia], ay_ = Y[ia], bx = X[ib] - ax_, by = Y[ib] - ay_;
+            const double t = __ddiv_rn(__dadd_rn(__dmul_rn(tx - ax_, bx), __dmul_rn(ty - ay_, by)),
+                                       __dadd_rn(sq_rn(bx), sq_rn(by)));
+            const double sx = __dadd_rn(ax_, __dmul_rn(t, bx)), sy = __dadd_rn(ay_, __dmul_rn(t, by));
+            s_two[w] = __dadd_rn(acc, sqrt(__dadd_rn(sq_rn(ax_ - sx), sq_rn(ay_ - sy))));
+        }
+        if (lane == 0) bf.obj_dist[b] = s_two[0] - s_two[1];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // k_ref: get_ref_idx (OTH:518-601) + follow-mode object distance (OTH:774-784)
 // ---------------------------------------------------------------------------------------------------------------------
@@ -164,6 +234,15 @@ k_ref(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
     const int B = dm.batch;
     if (bf.sc_flags[b] != 0) return;
     const int* info = bf.st_info + 8 * (size_t)b;
+    if (bf.const_len[b] == 0) {   // OTH:592-598: no valid last solution -> cut 0, no vel_course, vel_plan = v_start (k_state)
+        if (lane < LTPL_NSLOT) {
+            int* tr = bf.trim + 4 * (size_t)(lane * B + b);
+            tr[0] = tr[1] = tr[2] = tr[3] = 0;
+        }
+        __syncwarp();
+        ref_obj_dist(dm, bf, b, 0, bf.pos[2 * b], bf.pos[2 * b + 1], lane);
+        return;
+    }
     const int qp = info[0], m_p = info[1];
     const int c_p = bf.prev_trim[4 * qp + 2];
     const int nb_rows = bf.prev_traj_len[qp];
@@ -246,46 +325,7 @@ k_ref(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
         }
     }
 
-    // follow mode: distance to the closest object along the cut follow path (OTH:766-784); no object -> 0 (OTH:766-768)
-    if (lane == 0) bf.obj_dist[b] = 0.0;
-    __syncwarp();
-    const int qf = b;   // slot 0
-    if (bf.action_id[qf] == LTPL_ACT_FOLLOW && bf.closest_obj[b] >= 0) {
-        const int n = bf.path_len[qf] - cut_pos;
-        const double* X = bf.path + (size_t)qf * dm.p_max + cut_pos;
-        const double* Y = X + pplane;
-        const double* E = X + 4 * pplane;
-        double s_two[2];
-#pragma unroll 1
-        for (int w = 0; w < 2; ++w) {
-            const double tx = w ? px : bf.cobj[4 * b], ty = w ? py : bf.cobj[4 * b + 1];
-            double v2 = LTPL_INF;
-            int i2 = 0x7fffffff;
-            for (int j = lane; j < n; j += 32) {
-                const double d = dist2_rn(X[j], Y[j], tx, ty);
-                if (d < v2) {
-                    v2 = d;
-                    i2 = j;
-                }
-            }
-            const int nbp = warp_argmin(v2, i2).i;
-            const int i1 = max(nbp - 1, 0), j2 = min(nbp + 1, n - 1);
-            const bool gt = angle_cmp(make_double2(X[nbp], Y[nbp]), tx, ty, make_double2(X[i1], Y[i1]),
-                                      make_double2(X[j2], Y[j2])).gt;
-            const int ia = gt ? i1 : nbp, ib = gt ? nbp : j2;
-            // s_array = cumsum(el) of the cut path; leading 0 inserted when el[0] > 0.05 (get_s_coord.py:67-68)
-            double acc = 0.0;                        // cumsum(el)[ia - 1 + ins] evaluated by lane 0 order of np.cumsum
-            const bool ins = E[0] > 0.05;
-            const int upto = ins ? ia : ia + 1;      // number of el terms summed
-            for (int j = 0; j < upto; ++j) acc = __dadd_rn(acc, E[j]);
-            const double ax_ = X[ia], ay_ = Y[ia], bx = X[ib] - ax_, by = Y[ib] - ay_;
-            const double t = __ddiv_rn(__dadd_rn(__dmul_rn(tx - ax_, bx), __dmul_rn(ty - ay_, by)),
-                                       __dadd_rn(sq_rn(bx), sq_rn(by)));
-            const double sx = __dadd_rn(ax_, __dmul_rn(t, bx)), sy = __dadd_rn(ay_, __dmul_rn(t, by));
-            s_two[w] = __dadd_rn(acc, sqrt(__dadd_rn(sq_rn(ax_ - sx), sq_rn(ay_ - sy))));
-        }
-        if (lane == 0) bf.obj_dist[b] = s_two[0] - s_two[1];
-    }
+    ref_obj_dist(dm, bf, b, cut_pos, px, py, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -350,6 +390,7 @@ k_backup(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     if (!(st & LTPL_ST_TRAJ_VALID) || !(st & LTPL_ST_VEL_BOUND_VIOL) ||
         !(act == LTPL_ACT_FOLLOW || act == LTPL_ACT_STRAIGHT))
         return;
+    if (bf.const_len[b] == 0) return;                                  // invalid last solution: no backup plan (OTH:339-344)
     const int pa = bf.prev_action_id[q];
     if (!(pa == LTPL_ACT_FOLLOW || pa == LTPL_ACT_STRAIGHT)) return;   // no backup plan: stays flagged
     const int m_b = bf.prev_trim[4 * q + 0], L_b = bf.prev_trim[4 * q + 1];

@@ -831,7 +831,8 @@ k_vel_tiled(const LatDev lt, const LtplParams prm, const LtplDims dm, const Ltpl
         if (!vel_bound) st |= LTPL_ST_VEL_BOUND_VIOL;
         // stateful tick: a backup plan exists (OTH:325-344), so a straight / follow profile that breaks the bound is
         // replaced by a brake profile on the OLD path (OTH:950-1006): flag here, k_backup plans it and clears the flag
-        if (STATE && !vel_bound && (action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT))
+        // (no backup plan exists after an invalid last solution, const_len == 0: the profile is kept, OTH:945-948)
+        if (STATE && !vel_bound && (action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT) && bf.const_len[b] != 0)
             atomicOr(&bf.sc_flags[b], LTPL_SC_STATE_FALLBACK | (6 << LTPL_SC_REASON_SHIFT));
         if (vel_bound || action == LTPL_ACT_FOLLOW || action == LTPL_ACT_STRAIGHT) {
             st |= LTPL_ST_TRAJ_VALID;

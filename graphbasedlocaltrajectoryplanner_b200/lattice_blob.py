@@ -112,6 +112,7 @@ def pack_lattice(lat: Lattice) -> tuple:
         ("off_edge_cost", lat.edge_cost.astype(np.float64)),
         ("off_edge_len", lat.edge_len.astype(np.float64)),
         ("off_edge_psi1", lat.edge_psi1.astype(np.float64)),
+        ("off_edge_psi0", lat.edge_psi0.astype(np.float64)),
         ("off_samp_off", lat.samp_off.astype(np.int32)),
         ("off_samp_xy", np.column_stack((lat.samp_x, lat.samp_y)).astype(np.float64)),
         ("off_samp_el", lat.samp_el.astype(np.float64)),

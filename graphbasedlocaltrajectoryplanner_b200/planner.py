@@ -268,6 +268,7 @@ class BatchPlanner(object):
             h["obj_pred"].numpy()[:, :k, :kp, :] = sc.pred
             self.dims.k_pred = self._k_pred_cap
         self._upload_zones(sc.zones)
+        self._zone_key = sc.zone_key.copy() if sc.zone_key is not None else np.zeros(sc.size, dtype=np.int64)
 
     def _upload_zones(self, zones) -> None:
         """zone bitmasks: bit (node_off[layer] + node) of mask z = that node is blocked by zone z (GLNT:46, 96-99)."""
@@ -446,6 +447,13 @@ class BatchPlanner(object):
         for k in self._SMALL:
             setattr(buf, "prev_" + k, ps[k].data_ptr())
         st["pos_last"].copy_(t["pos"])                        # pos_est of the previous calc_vel_profile (OTH:537)
+        # a zone under a NEW id is a new zone object: its unblock window is evaluated at this tick (OLI:155-237, GLNT:43-77)
+        zkey = sc.zone_key if sc.zone_key is not None else np.zeros(sc.size, dtype=np.int64)
+        last = getattr(self, "_zone_key", None)               # of the batch staged for the previous tick
+        if last is not None and last.shape == zkey.shape:
+            changed = np.nonzero((zkey != last) & (zkey != 0))[0]
+            if changed.size:
+                st["zone_s0"][torch.as_tensor(changed, device=self.device)] = -1
         st["sel_action"].copy_(torch.as_tensor(np.asarray(sel_action, dtype=np.int32).reshape(-1)))
         st["t_const"].copy_(torch.as_tensor(np.broadcast_to(np.asarray(t_const, dtype=np.float64),
                                                             (self.dims.batch,)).copy()))

@@ -33,6 +33,8 @@ class ScenarioBatch:
     # pairs and, per scenario, the index of its zone or -1.  None: no zones in this batch.
     zones: list = None
     zone_sel: np.ndarray = None   # (B,) int32
+    zone_key: np.ndarray = None   # (B,) int64 crc of the zone id (0: none): a stateful planner processes a zone anew when
+    #                               its id changes between ticks (ObjectListInterface.update_zone, OLI:155-237)
     # explicit prediction arrays of the objects (dict key 'prediction', OLI:117-119): n_pred[b, k] points (-1: none
     # given -> the built-in constant-velocity point at 0.2 s, OLI:121-127).  None: no object carries a prediction.
     pred: np.ndarray = None       # (B, K, KP, 2) float64
@@ -58,6 +60,7 @@ class ScenarioBatch:
         return ScenarioBatch(self.pos[idx].copy(), self.heading[idx].copy(), self.vel[idx].copy(),
                              self.n_obj[idx].copy(), self.obj[idx].copy(), self.zones,
                              None if self.zone_sel is None else self.zone_sel[idx].copy(),
+                             None if self.zone_key is None else self.zone_key[idx].copy(),
                              None if self.pred is None else self.pred[idx].copy(),
                              None if self.n_pred is None else self.n_pred[idx].copy())
 
@@ -66,10 +69,13 @@ class ScenarioBatch:
         bound]} exactly as Graph_LTPL.calc_paths takes it (LTPL:311-312).  A scenario may carry ONE zone: with several
         keys the reference's update_zone (OLI:155-237, called once per key at LTPL:326-329) flags all but the last as
         removed and GLNT:69-83 then fails on them."""
+        import zlib
         zones, index, sel = [], {}, np.full(self.size, -1, dtype=np.int32)
+        zkey = np.zeros(self.size, dtype=np.int64)
         for i, bz in enumerate(blocked_zones):
             if not bz:
                 continue
+            zkey[i] = 1 + zlib.crc32(str(next(iter(bz))).encode())
             if len(bz) != 1:
                 raise NotImplementedError("more than one blocked zone per scenario is not a defined input of the reference")
             zid, z = next(iter(bz.items()))
@@ -82,6 +88,7 @@ class ScenarioBatch:
                 zones.append((lay, nod))
             sel[i] = index[key]
         self.zones, self.zone_sel = (zones, sel) if zones else (None, None)
+        self.zone_key = zkey if zones else None
 
     def shard(self, rank: int, world: int) -> "ScenarioBatch":
         """scenario i goes to rank i % world."""

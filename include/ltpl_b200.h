@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 9
+#define LTPL_ABI_VERSION 10
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -102,6 +102,7 @@ typedef struct LtplLatticeHeader {
     uint64_t off_edge_cost;      /* f64 [E]                                           */
     uint64_t off_edge_len;       /* f64 [E]                                           */
     uint64_t off_edge_psi1;      /* f64 [E] heading of the last sample                */
+    uint64_t off_edge_psi0;      /* f64 [E] heading of the first sample (MOPG:302-303)*/
     uint64_t off_samp_off;       /* int32 [E+1]                                       */
     /* per sample [S] */
     uint64_t off_samp_xy;        /* f64x2 [S]                                         */

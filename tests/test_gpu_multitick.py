@@ -31,12 +31,17 @@ class _Rows(object):
         return a if k == "ax_max_machines" else a[self.idx]
 
 
-@pytest.mark.parametrize("fixture,emerg,group", [("ticks_multitick_default.npz", False, None),
-                                                 ("ticks_multitick_ext_default.npz", True, None),
-                                                 ("ticks_multitick_backup_default.npz", False, 0),
-                                                 ("ticks_multitick_backup_default.npz", False, 1),
-                                                 ("ticks_multitick_emsel_default.npz", True, None)])
-def test_next_tick_matches_reference_sequences(fixture, emerg, group):
+@pytest.mark.parametrize("fixture,emerg,group,tag", [("ticks_multitick_default.npz", False, None, "default"),
+                                                     ("ticks_multitick_ext_default.npz", True, None, "default"),
+                                                     ("ticks_multitick_backup_default.npz", False, 0, "default"),
+                                                     ("ticks_multitick_backup_default.npz", False, 1, "default"),
+                                                     ("ticks_multitick_emsel_default.npz", True, None, "default"),
+                                                     ("ticks_multitick_l216.npz", True, None, "l216"),
+                                                     ("ticks_multitick_l430.npz", False, None, "l430"),
+                                                     ("ticks_multitick_open.npz", False, None, "open"),
+                                                     ("ticks_multitick_zswap_default.npz", False, None, "default"),
+                                                     ("ticks_multitick_invalid_default.npz", False, None, "default")])
+def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
     """second fixture: a blocked zone on every second sequence + the emergency trajectory in every tick; third fixture:
     the grip (gg_scale) drops on the odd sequences from tick 3 on -> brake on the backup plan (OTH:950-1006); fourth
     fixture: the odd sequences execute the 'emergency' trajectory of ticks 2 .. 4 (sel_action 4; OTH:307-309, 518-601)."""
@@ -47,9 +52,8 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group):
     if group is not None:
         g = _Rows(g, np.arange(group, g["dt"].shape[0], 2))
     n_seq, n_ticks = g["dt"].shape
-    assert int(g["n_done"].min()) == n_ticks
-    zones = [H.zone_of(g, q) for q in range(n_seq)]
-    pl = BatchPlanner(H.lattice_for("default"), device="cuda:0", stateful=True)
+    n_done = g["n_done"]                                   # open track: sequences end when no trajectory is left
+    pl = BatchPlanner(H.lattice_for(tag), device="cuda:0", stateful=True)
     pl.set_vel_params(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"],
                       safety_d=30.0, incl_emerg_traj=emerg)
     tc = np.array([_t_const(g["dt"][q, 1:]) for q in range(n_seq)])       # t_const of ticks 1 ..
@@ -58,6 +62,7 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group):
     for k in range(n_ticks):
         sc = ScenarioBatch(g["pos_est"][:, k].copy(), g["sc_heading"].copy(), g["sc_vel"].copy(), g["sc_n_obj"].copy(),
                            g["obj"][:, k].copy())
+        zones = [H.zone_of(g, q, k) for q in range(n_seq)]
         if any(z is not None for z in zones):
             sc.set_zones(zones)
         assert len(set(g["gg_scale"][:, k].tolist())) == 1
@@ -72,7 +77,7 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group):
             pl.next_tick(sc, sel_action=g["sel"][:, k], t_const=tc[:, k - 1], vel_est=g["vel_est"][:, k])
         recs = pl.records()
         for q in range(n_seq):
-            if not alive[q]:
+            if not alive[q] or k >= int(n_done[q]):
                 continue
             ctx = "sequence %d tick %d" % (q, k)
             rec = recs[q]
@@ -109,7 +114,7 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group):
                 alive[q] = False            # later ticks of this sequence depend on this one
     assert not fails, "%d sequences diverged (of %d; %d trajectories matched before):\\n%s" % (
         len(fails), n_seq, compared, "\\n".join(fails[:8]))
-    assert compared > (30 if group is not None else (80 if emerg else 150))
+    assert compared > (30 if (group is not None or n_seq < 12) else (80 if (emerg or n_seq < 16) else 150))
 
 
 @pytest.mark.parametrize("tag,n_seq,omin,omax", [("default", 96, 0, 2), ("l216", 64, 1, 3)])
