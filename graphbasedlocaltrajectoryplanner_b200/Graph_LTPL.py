@@ -169,8 +169,8 @@ class Graph_LTPL(object):
         rec = pl.records()[0]
         if rec["flags"] & capi.SC_STATE_FALLBACK:
             self.__state = None
-            raise RuntimeError("the last trajectory of action '%s' cannot serve as memory (OTH:393-407 is "
-                               "not on the device yet): call set_startpos() again" % prev_action_id)
+            raise RuntimeError("the last trajectory of action '%s' cannot serve as memory (flags 0x%x, see "
+                               "LTPL_SC_REASON_SHIFT): call set_startpos() again" % (prev_action_id, rec["flags"]))
         self.__records = rec
         self.__state = "paths_next"
         return {k: [a.copy() for a in v] for k, v in rec["paths"].items()}

@@ -56,11 +56,14 @@ extern "C" {
 #define LTPL_SC_HEADING_MISMATCH (1 << 1)  /* OTH:234-240                                                             */
 #define LTPL_SC_CAPACITY         (1 << 2)  /* a fixed-capacity buffer (P0_MAX / P_MAX / H_MAX) would overflow          */
 #define LTPL_SC_STATE_FALLBACK   (1 << 4)  /* stateful tick: the last executed trajectory is not usable as memory       */
-                                           /* (OTH:393-407 branch, or no backup plan to brake on): re-anchor w/ set_startpos */
-#define LTPL_SC_REASON_SHIFT 8             /* bits 8..10: why STATE_FALLBACK was raised (diagnostic detail): 1 executed action */
-                                           /* not in the memory, 2 its trajectory has <= 2 rows, 3 < 2 memory nodes, 4 start   */
-                                           /* node is the placeholder, 5 constant segment exceeds p_max, 6 follow / straight   */
-                                           /* cannot start at the planned velocity and no backup plan exists                   */
+                                           /* (see the reason codes; re-anchor with ltpl_set_startpos_batch)                */
+#define LTPL_SC_REASON_SHIFT 8             /* bits 8..10: why STATE_FALLBACK was raised (diagnostic detail):            */
+                                           /* 1 the executed action is not in the memory and the last tick was not      */
+                                           /*   planned either (an action the last tick merely did not return is        */
+                                           /*   planned per OTH:393-407), 2 its trajectory has <= 2 rows, 3 fewer than  */
+                                           /*   2 memory nodes, 4 the start node is the placeholder, 5 the constant     */
+                                           /*   segment exceeds p_max, 6 follow / straight cannot start at the planned  */
+                                           /*   velocity and no backup plan exists                                      */
 #define LTPL_SC_BRAKE_PREFIX     (1 << 3)  /* vel_plan > vel_max + 0.1: the reference path raises here (OTH:747-754,   */
                                            /* 830/919 column_stack length mismatch); reported instead of planned       */
 
