@@ -107,3 +107,22 @@ def test_parallel_plumbing_gloo_world2(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert res.returncode == 0 and res.stdout.count("ok") == 2, res.stdout[-2000:]
+
+
+def test_zone_ids_and_masks_of_a_scenario_batch():
+    """set_zones: zones are de-duplicated by content, identified by the crc of their id (a stateful planner processes a zone
+    anew when the id changes, OLI:155-237), and travel through subset() / shard()."""
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
+    z1 = [[3, 3, 4], [0, 1, 0], np.zeros((2, 2)), np.zeros((2, 2))]
+    z2 = [[7], [2], np.zeros((2, 2)), np.zeros((2, 2))]
+    sc = ScenarioBatch.from_object_lists(np.zeros((4, 2)), np.zeros(4), np.ones(4), [[], [], [], []],
+                                         blocked_zones=[{"a": z1}, None, {"b": z1}, {"a": z2}])
+    assert sc.zone_sel.tolist() == [0, -1, 0, 1] and len(sc.zones) == 2          # same content -> same mask
+    assert sc.zone_key[1] == 0 and sc.zone_key[0] == sc.zone_key[3] != sc.zone_key[2] and sc.zone_key[0] > 0
+    sub = sc.subset([3, 1])
+    assert sub.zone_sel.tolist() == [1, -1] and sub.zone_key.tolist() == [int(sc.zone_key[3]), 0]
+    assert sc.shard(1, 2).zone_key.tolist() == [0, int(sc.zone_key[3])]
+    with pytest.raises(NotImplementedError):
+        ScenarioBatch.from_object_lists(np.zeros((1, 2)), np.zeros(1), np.ones(1), [[]], blocked_zones=[{"a": z1, "b": z2}])
+    plain = ScenarioBatch.from_object_lists(np.zeros((2, 2)), np.zeros(2), np.ones(2), [[], []])
+    assert plain.zones is None and plain.zone_key is None
