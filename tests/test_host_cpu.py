@@ -36,6 +36,9 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+    for f in os.listdir(os.path.join(H.REPO, "tools")):   # GPU tuning / profiling helpers: no checker needed, none used
+        if f.endswith(".py"):
+            assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(H.REPO, "tools", f)).read(), flags=re.M), f
 
 
 def test_missing_gpu_fails_loudly():
