@@ -45,3 +45,16 @@ def test_product_arm_fails_loudly_without_a_gpu():
     assert r.returncode != 0
     assert not [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")], "no result line without a GPU"
     assert "NVIDIA" in r.stderr or "CUDA" in r.stderr or "cuda" in r.stderr
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """the driver launches the reference arm like the product arm; rank 0 alone works and prints, the others exit 0."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", BENCH, "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0", "--cpu-sample", "16"], cwd=H.REPO, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
