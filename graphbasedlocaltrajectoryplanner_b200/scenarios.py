@@ -160,11 +160,12 @@ class Track(object):
 
 
 def make_scenarios(track: Track, batch: int, seed: int = DEFAULT_SEED, n_obj_min: int = 1, n_obj_max: int = 3,
-                   k_max: int = None, obj_margin: float = 1.4, ahead=(30.0, 280.0), s_max: float = None) -> ScenarioBatch:
+                   k_max: int = None, obj_margin: float = 1.4, ahead=(30.0, 280.0), s_max: float = None,
+                   s_min: float = 0.0) -> ScenarioBatch:
     """SURVEY 8(d) config 2 (n_obj 1..3) / config 4 (n_obj_min = n_obj_max = 5).  s_max: upper bound of the ego arc
-    length (open tracks: stay in front of the last race line point)."""
+    length (open tracks: stay in front of the last race line point), s_min: lower bound."""
     rng = np.random.default_rng(seed)
-    s_e = rng.uniform(0.0, track.length if s_max is None else s_max, size=batch)
+    s_e = rng.uniform(s_min, track.length if s_max is None else s_max, size=batch)
     pos, heading, v_rl = track.raceline_pose(s_e)
     vel = rng.uniform(5.0, np.maximum(0.9 * v_rl, 5.0))
     n_obj = rng.integers(n_obj_min, n_obj_max + 1, size=batch).astype(np.int32)

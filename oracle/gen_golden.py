@@ -292,7 +292,7 @@ def advance_on_traj(traj, dt):
 
 
 def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
-                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None, s_max=None, hmax=40):
+                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None, s_max=None, hmax=40, s_min=0.0):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
     em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4).
@@ -306,7 +306,7 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
     real_time = oth_mod.time
     oth_mod.time = clock
     try:
-        sc = make_scenarios(track, n_seq, seed=seed, n_obj_min=n_obj[0], n_obj_max=n_obj[1], s_max=s_max)
+        sc = make_scenarios(track, n_seq, seed=seed, n_obj_min=n_obj[0], n_obj_max=n_obj[1], s_max=s_max, s_min=s_min)
         rng = np.random.default_rng(seed + 1)
         emerg = bool(vel_kwargs.get('incl_emerg_traj'))
         zones = [(make_zone(lat, rng, sc.pos[q]) if (lat is not None and q % 2 == 0) else None) for q in range(n_seq)]
@@ -510,6 +510,10 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_open.npz'),
                             **multitick_fixture(graph_ltpl, ltpl, tr_open, 16, 8, vel_kwargs, seed=1212,
                                                 s_max=tr_open.length - 8.0))
+        # ... and starting on the last 150 m: trajectories shrink tick by tick until nothing is left to plan
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_openend.npz'),
+                            **multitick_fixture(graph_ltpl, ltpl, tr_open, 12, 10, vel_kwargs, seed=1313,
+                                                s_max=tr_open.length - 15.0, s_min=tr_open.length - 150.0))
         if args.mt_open_only:
             return
         sc = make_scenarios(tr_open, args.n_open, seed=DEFAULT_SEED + 99, n_obj_min=0, n_obj_max=3,

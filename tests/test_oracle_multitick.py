@@ -25,6 +25,7 @@ import pytest
                                                ("ticks_multitick_l216.npz", True, "l216"),
                                                ("ticks_multitick_zswap_default.npz", False, "default"),
                                                ("ticks_multitick_open.npz", False, "open"),
+                                               ("ticks_multitick_openend.npz", False, "open"),
                                                ("ticks_multitick_l430.npz", False, "l430"),
                                                ("ticks_multitick_pdtan_default.npz", False, "default:pdtan_exp15")])
 def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
