@@ -15,11 +15,16 @@ Kept signatures (same names, argument meaning, return structure and error behavi
 plus the batched variants ``set_startpos_batch`` / ``calc_paths_batch`` / ``calc_vel_profile_batch`` / ``plan_batch``
 over a ``ScenarioBatch`` (thousands of independent ego-start x obstacle scenarios per call).
 
-Scope: ticks are stateless -- ``calc_paths`` plans the first tick after ``set_startpos``; the reference's
-iterative memory across ticks depends on the wall clock (OTH:353-378) and is a listed next row, as are location
-dependent ``local_gg`` dicts.  ``blocked_zones`` takes one zone per scenario ('nodes' type, GLNT:43-99 first-tick
-semantics); ``incl_emerg_traj=True`` adds the 'emergency' entry (OTH:1027-1034).  Offline graph generation is replaced by the flat
-lattice blob (lattice.py); logging and visualisation of the reference are out of scope.
+    log() / visual()   documented no-ops (LTPL:412-463, 465-532): the reference's loops call them every tick
+                       (main_min_example.py:107, main_std_example.py:132-135); file logging and live plots themselves
+                       are out of scope
+
+Scope: the first ``calc_paths`` / ``calc_vel_profile`` pair after ``set_startpos`` is the stateless first
+tick; every later pair is a STATEFUL tick whose iterative memory (OTH:64-87) lives on the device (DESIGN.md section 11,
+csrc/ltpl_state.cuh) -- the wall clock the reference reads (OTH:353-378) is ``self.clock`` here (injectable).
+``blocked_zones`` takes one zone per scenario ('nodes' type, GLNT:43-99); ``incl_emerg_traj=True`` adds the 'emergency'
+entry (OTH:1027-1034); ``local_gg`` is the tuple of the reference or its location dependent dict form
+``{action: [ndarray(P, 2)]}`` (OTH:649-666).  Offline graph generation is replaced by the flat lattice blob (lattice.py).
 """
 
 from __future__ import annotations
@@ -45,9 +50,14 @@ class Graph_LTPL(object):
             if entry not in path_dict:
                 if log_to_file or 'log' not in entry:
                     raise ValueError('Missing path specification in path_dict (Missing entry: "' + entry + '")!')
-        if visual_mode:
-            raise NotImplementedError("live visualisation is out of scope of the B200 planning path (SURVEY 2, row 20)")
         self.__log = logging.getLogger("local_trajectory_logger")
+        # live plots / file logs of the reference (LTPL:96-104, 146-166) are out of scope: the flags are accepted so that
+        # the reference's own loops run unchanged, visual() / log() are no-ops
+        self.__visual_mode = bool(visual_mode)
+        self.__log_to_file = bool(log_to_file)
+        if visual_mode:
+            self.__log.warning("visual_mode=True: live visualisation is not part of the B200 planning path; visual() "
+                               "is a no-op")
         self.__path_dict = path_dict
         self.__device = device
         self.__online = read_online_config(path_dict['ltpl_online_param_path'])
@@ -178,34 +188,25 @@ class Graph_LTPL(object):
     def calc_vel_profile(self, pos_est: np.ndarray, vel_est: float, vel_max: float = 100.0, gg_scale: float = 1.0,
                          local_gg: dict = (5.0, 5.0), ax_max_machines: np.ndarray = np.atleast_2d([100.0, 5.0]),
                          safety_d: float = 30.0, incl_emerg_traj: bool = False) -> tuple:
-        if self.__state == "paths_next":
-            pl = self.__planner
-            pl.set_vel_params(vel_max=vel_max, gg_scale=gg_scale, local_gg=local_gg, ax_max_machines=ax_max_machines,
-                              safety_d=safety_d, incl_emerg_traj=incl_emerg_traj)
-            self.__pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
-            pl.next_calc_vel_profile(pos_est=[self.__pos], vel_est=[float(vel_est)])
-            rec = pl.records()[0]
-            self.__records = rec
-            self.__state = "next" if rec["traj"] else None
-            return ({k: [a.copy() for a in v] for k, v in rec["traj"].items()}, dict(rec["ids"]), time.time())
-        if self.__state != "paths":
+        if self.__state not in ("paths", "paths_next"):
             raise ValueError("calc_paths() must be called before calc_vel_profile()")
-        if type(local_gg) is dict:
-            raise NotImplementedError("location dependent friction (local_gg dict) is not batched yet; pass a tuple")
         pl = self.__planner
         pl.set_vel_params(vel_max=vel_max, gg_scale=gg_scale, local_gg=local_gg, ax_max_machines=ax_max_machines,
                           safety_d=safety_d, incl_emerg_traj=incl_emerg_traj)
-        pl.t["vel_est"].fill_(float(vel_est))
         pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
-        if not np.array_equal(pos, self.__pos):
-            # the position estimate only enters the follow-mode distance (OTH:779-784) on the first tick
-            pl.h_in["pos"].numpy()[0] = pos
-            pl.t["pos"].copy_(pl.h_in["pos"])
-        pl.calc_vel_profile()
+        if self.__state == "paths_next":
+            pl.next_calc_vel_profile(pos_est=[pos], vel_est=[float(vel_est)])
+        else:
+            # first tick: the position estimate only enters the follow-mode distance (OTH:779-784)
+            pl.set_estimates(pos_est=[pos], vel_est=[float(vel_est)])
+            pl.calc_vel_profile()
         rec = pl.records()[0]
         if rec.get("error", 0) & capi.SC_BRAKE_PREFIX:
             raise ValueError("vel_plan exceeds vel_max: the reference's brake-prefix branch (OTH:747-754) yields arrays "
                              "of mismatching length and raises; not planned")
+        if rec.get("error", 0) & capi.SC_CAPACITY:
+            raise RuntimeError("a capacity of the batched path was exceeded (LTPL_SC_CAPACITY, flags 0x%x): e.g. more "
+                               "than %d delay-compensation points (OTH:558-574)" % (rec["flags"], capi.COURSE_MAX))
         self.__records = rec
         for name, st in rec["status"].items():
             if st & capi.ST_TOO_CLOSE:
@@ -213,8 +214,20 @@ class Graph_LTPL(object):
             if (st & capi.ST_VEL_BOUND_VIOL) and not (st & capi.ST_TRAJ_VALID):
                 self.__log.warning("Removed action set, since vel constraints were broken! (Action Set: " + name + ")")
         self.__pos = pos
-        self.__state = "next" if rec["traj"] else None   # later ticks continue from the device-resident memory
+        # later ticks continue from the device-resident memory; when the velocity planner removed every trajectory the
+        # memory is empty and the next calc_paths() takes the "no valid last solution" branch (OTH:393-407) on the device
+        self.__state = "next"
         return ({k: [a.copy() for a in v] for k, v in rec["traj"].items()}, dict(rec["ids"]), time.time())
+
+    def log(self) -> None:
+        """LTPL:412-463 writes the tick to the graph log file; file logging is out of scope -- no-op, kept so
+        that the reference's loops (main_std_example.py:132) run unchanged."""
+        return None
+
+    def visual(self) -> None:
+        """LTPL:465-532 updates the live plot; visualisation is out of scope -- no-op, kept so that the
+        reference's loops (main_min_example.py:107, main_std_example.py:135) run unchanged."""
+        return None
 
     def last_node_sequences(self) -> dict:
         """node sequences of the last calc_paths() call ({action: [[[layer, node], ...]]}, cf. OTH:509)."""

@@ -40,7 +40,10 @@ class _Rows(object):
                                                      ("ticks_multitick_l430.npz", False, None, "l430"),
                                                      ("ticks_multitick_open.npz", False, None, "open"),
                                                      ("ticks_multitick_zswap_default.npz", False, None, "default"),
-                                                     ("ticks_multitick_invalid_default.npz", False, None, "default")])
+                                                     ("ticks_multitick_invalid_default.npz", False, None, "default"),
+                                                     ("ticks_multitick_openend.npz", False, None, "open"),
+                                                     ("ticks_multitick_pdtan_default.npz", False, None,
+                                                      "default:pdtan_exp15")])
 def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
     """second fixture: a blocked zone on every second sequence + the emergency trajectory in every tick; third fixture:
     the grip (gg_scale) drops on the odd sequences from tick 3 on -> brake on the backup plan (OTH:950-1006); fourth
@@ -53,9 +56,14 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
         g = _Rows(g, np.arange(group, g["dt"].shape[0], 2))
     n_seq, n_ticks = g["dt"].shape
     n_done = g["n_done"]                                   # open track: sequences end when no trajectory is left
-    pl = BatchPlanner(H.lattice_for(tag), device="cuda:0", stateful=True)
-    pl.set_vel_params(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"],
-                      safety_d=30.0, incl_emerg_traj=emerg)
+    tag, _, variant = tag.partition(":")
+    pl_kw, vel = {}, dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), safety_d=30.0)
+    if variant:                                            # other controller / vehicle / velocity parameters (H.VARIANTS)
+        online, veh, vel_v, _ = H.VARIANTS[variant]
+        pl_kw = dict(online=online, **veh)
+        vel.update(vel_v)
+    pl = BatchPlanner(H.lattice_for(tag), device="cuda:0", stateful=True, **pl_kw)
+    pl.set_vel_params(ax_max_machines=g["ax_max_machines"], incl_emerg_traj=emerg, **vel)
     tc = np.array([_t_const(g["dt"][q, 1:]) for q in range(n_seq)])       # t_const of ticks 1 ..
     fails, compared = [], 0
     alive = np.ones(n_seq, dtype=bool)
@@ -66,8 +74,8 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
         if any(z is not None for z in zones):
             sc.set_zones(zones)
         assert len(set(g["gg_scale"][:, k].tolist())) == 1
-        pl.set_vel_params(vel_max=100.0, gg_scale=float(g["gg_scale"][0, k]), local_gg=(5.0, 5.0),
-                          ax_max_machines=g["ax_max_machines"], safety_d=30.0, incl_emerg_traj=emerg)
+        pl.set_vel_params(ax_max_machines=g["ax_max_machines"], incl_emerg_traj=emerg,
+                          **dict(vel, gg_scale=float(g["gg_scale"][0, k])))
         if k == 0:
             pl.stage_scenarios(sc, vel_est=g["vel_est"][:, k])
             pl.upload()
