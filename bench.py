@@ -13,8 +13,11 @@ random ego arc length + 1..3 dynamic obstacles, seed 20260924).  set_startpos is
           the scenario arrays, set_startpos + tick kernels, D2H of the per-path arrays and of the kept trajectory rows,
           all inside the timed region (the D2H of step i overlaps the kernels of step i + 1)
   roofline / cpu_baseline : see DESIGN.md "Measurement"
-Multi-GPU: scenarios are independent -> every rank plans its own 10 000-scenario batch ("weak" scaling), no data-path
-collective; the lattice blob is NCCL-broadcast from rank 0 at init and the e2e leg all-gathers the action sets.
+Multi-GPU (config 3, "strong" scaling): the SAME seeded 10 000-scenario batch is sharded i % world over the ranks; the
+lattice blob is NCCL-broadcast from rank 0 at init; the timed region of `value` holds the tick of every shard AND the
+gather of all action sets into rank 0's HBM (parallel.PeerGather: the export kernels store their rows straight into the
+consumer's memory over NVLink; fallback: point-to-point sends of the live rows).  The weak-scaling variant (10 000
+scenarios per GPU, replicas, no gather) is reported under extra.weak.
 """
 
 import argparse
@@ -86,13 +89,13 @@ def make_batch(tag, batch, seed=SEED):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (oracle/ltpl_oracle.py) on all host cores; only this leg may execute oracle/
+# CPU arm: the oracle port (oracle/ltpl_oracle.py) on the host cores; only this leg may execute oracle/
 # ----------------------------------------------------------------------------------------------------------------------
 _W = {}
+_ONE_THREAD = ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS")
 
 
 def _cpu_init(lat_path):
-    os.environ['OPENBLAS_NUM_THREADS'] = '1'   # as main_min_example.py:8
     from graphbasedlocaltrajectoryplanner_b200.lattice import Lattice
     from oracle.ltpl_oracle import OracleLTPL
     _W['orc'] = OracleLTPL(Lattice.load(lat_path))
@@ -102,43 +105,81 @@ def _cpu_init(lat_path):
 def _cpu_work(args):
     pos, heading, vel, objs = args
     orc, vk = _W['orc'], _W['vk']
-    n_traj = 0
+    t0 = time.perf_counter()
     for i in range(pos.shape[0]):
         ol = [{'id': k + 1, 'type': 'physical', 'X': o[0], 'Y': o[1], 'theta': o[2], 'v': o[3], 'length': o[4],
                'width': 2.5} for k, o in enumerate(objs[i])]
-        r = orc.tick(pos[i], heading[i], vel[i], ol, vk)
-        n_traj += len(r.get('traj', {}))
-    return pos.shape[0], n_traj
+        orc.tick(pos[i], heading[i], vel[i], ol, vk)
+    return pos.shape[0], time.perf_counter() - t0
 
 
 class CpuArm(object):
+    """`cores` worker processes, one oracle each, one BLAS thread each (main_min_example.py:8; the variables are set in
+    the parent BEFORE the workers are spawned -- a child imports NumPy before its initializer runs).  A run hands every
+    worker ONE chunk of `per_worker` scenarios (static partition: no dispatch noise) and waits for all of them."""
+
     def __init__(self, tag, cores=None):
         import multiprocessing as mp
         get_lattice(tag)   # make sure the cache file exists
+        self.tag = tag
         self.cores = cores or os.cpu_count()
-        ctx = mp.get_context("spawn")
-        self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(lattice_cache_path(tag),))
-        self.pool.map(_cpu_work, [self._chunk(make_batch(tag, self.cores, seed=1), i, i + 1)
-                                  for i in range(self.cores)])   # start-up + first-touch, untimed
+        keep = {k: os.environ.get(k) for k in _ONE_THREAD}
+        for k in _ONE_THREAD:
+            os.environ[k] = "1"
+        try:
+            ctx = mp.get_context("spawn")
+            self.pool = ctx.Pool(self.cores, initializer=_cpu_init, initargs=(lattice_cache_path(tag),))
+            warm = make_batch(tag, self.cores * 2, seed=1)
+            self.pool.map(_cpu_work, [self._chunk(warm, 2 * i, 2 * i + 2) for i in range(self.cores)], chunksize=1)
+        finally:
+            for k, v in keep.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
 
     @staticmethod
     def _chunk(sc, a, b):
         return (sc.pos[a:b], sc.heading[a:b], sc.vel[a:b],
                 [sc.obj[i, :sc.n_obj[i]].tolist() for i in range(a, b)])
 
-    def run(self, sc):
+    def run(self, sc, workers=None):
+        """wall time of one pass over `sc` with `workers` processes (default: all), and the summed in-worker time"""
+        w = workers or self.cores
         n = sc.size
-        per = max(1, n // (self.cores * 4))
+        per = (n + w - 1) // w
         chunks = [self._chunk(sc, a, min(a + per, n)) for a in range(0, n, per)]
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_work, chunks)
+        res = self.pool.map(_cpu_work, chunks, chunksize=1)
         dt = time.perf_counter() - t0
         assert sum(r[0] for r in res) == n
-        return dt
+        return dt, sum(r[1] for r in res)
+
+    def measure(self, per_worker=160, runs=2):
+        """all-core ticks/s (median of `runs` passes over cores x per_worker scenarios of the seeded batch) and the
+        single-core ticks/s (one worker, per_worker scenarios; BASELINE.md section 2 asks for both)."""
+        sc = make_batch(self.tag, self.cores * per_worker)
+        t_all = sorted(self.run(sc)[0] for _ in range(runs))[(runs - 1) // 2]
+        sc1 = sc.subset(np.arange(per_worker))
+        t_one = self.run(sc1, workers=1)[0]
+        return dict(all=sc.size / t_all, one=sc1.size / t_one, sample=sc.size, seconds_all=t_all, seconds_one=t_one,
+                    per_worker=per_worker, runs=runs)
 
     def close(self):
         self.pool.close()
         self.pool.join()
+
+
+def cpu_baseline_dict(arm, m):
+    return {"value": m["all"], "unit": "ticks/s", "cores": arm.cores, "kind": "port",
+            "ticks_per_s_cpu_allcores": m["all"], "ticks_per_s_cpu_1core": m["one"],
+            "sample": "%d scenarios of the seeded workload (%d per worker process, %d processes, 1 BLAS thread each), "
+                      "median of %d passes, %.2f s per pass; single core: %d scenarios in %.2f s" % (
+                          m["sample"], m["per_worker"], arm.cores, m["runs"], m["seconds_all"], m["per_worker"],
+                          m["seconds_one"]),
+            "note": "float64 NumPy restatement of the reference path (oracle/ltpl_oracle.py); the reference itself needs "
+                    "igraph + tph, not installable offline (its single-core rate on shims, measured in the build "
+                    "container: profiles/r2_cpu_reference_shims.json)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -182,8 +223,10 @@ def clocks_sampler(gpu_index, stop_evt, out, ready_evt=None):
 
 
 def algorithmic_bytes(lat, stats):
-    """ALGORITHMIC bytes per launch of each kernel (every logical array element touched once; float64 / int32 as the
-    kernels use them).  Formulas: DESIGN.md "Kernels and rooflines"."""
+    """ALGORITHMIC bytes per launch of each kernel: inputs + outputs of the kernel, every logical array element once, with
+    the element sizes the kernels use (float64 / int32); scratch is not counted.  Formulas: DESIGN.md section 5.
+    k_plan is counted for the work the kernel DOES (one sample sweep per touched layer pair, table rows instead of
+    searches where it reads them); `k_plan_as_reference` is the reference's work (three searches per tick)."""
     n_pairs = max(1, lat.num_layers)
     e_l = lat.num_edges / n_pairs                     # edges per layer pair
     s_l = lat.num_samples / n_pairs                   # samples per layer pair
@@ -194,12 +237,19 @@ def algorithmic_bytes(lat, stats):
     pts_follow = stats["pts_follow_sum"]
     acts = stats["n_actions"]
     B = stats["batch"]
-    plan = discs * 2 * s_l * (16 + 4) + ah * e_l * (8 + 4 + 0.125) + ah * n_l * 1 + acts * 0 \
-        + stats["nodes_sum"] * (8 + 4) + B * (16 + 8 + 8 + 4) + stats["n_obj_sum"] * 40 + B * stats["p0_mean"] * 16
+    plan_io = B * (16 + 8 + 8 + 4) + stats["n_obj_sum"] * 40 + B * stats["p0_mean"] * 16 + stats["nodes_sum"] * (8 + 4)
+    plan = plan_io + discs * s_l * (16 + 4) + ah * (1 + 4)          # one shared sweep per object, table row per step
+    plan_ref = plan_io + discs * 2 * s_l * (16 + 4) + ah * e_l * (8 + 4 + 0.125) + ah * n_l * 1
     path = pts * (5 * 8 + 8) + ah * (8 * 8 + 16 + 8 + 8 + 4) + acts * stats["p0_mean"] * 5 * 8 * 2
-    vel = pts * (2 * 8 + 3 * 8) + pts_follow * (2 * 8 + 3 * 8 * 2)
+    vel = pts * (2 * 8 + 3 * 8) + pts_follow * (2 * 8)             # kappa, el in; s, vx, ax out; x, y in (follow)
+    vel_fp32 = pts * (2 * 4 + 3 * 4) + pts_follow * (2 * 4)        # SURVEY 8(d) element sizes
     export = stats["export_rows"] * (7 * 8 + 7 * 4)
-    return dict(k_plan=plan, k_path=path, k_vel=vel, k_export=export)
+    # SURVEY 8(d) B_tick (fp32 / int32 element sizes, lattice gathers included), with the batch's own H, K, A, P
+    s_e = lat.num_samples / max(1, lat.num_edges)
+    b_tick = discs * 2 * e_l * s_e * 8 + ah * e_l * (4 + 4 + 0.125) + ah * n_l * 4 + pts * 20 \
+        + (pts * 28 + (ah + acts) * 8 + ah * 32) + discs * 12 + B * 64
+    return dict(k_plan=plan, k_path=path, k_vel=vel, k_export=export, k_plan_as_reference=plan_ref,
+                k_vel_fp32_sizes=vel_fp32, tick_survey_8d=b_tick)
 
 
 def main():
@@ -208,11 +258,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=10000, help="scenarios per GPU")
+    ap.add_argument("--batch", type=int, default=10000, help="scenarios of the job (sharded over the GPUs)")
     ap.add_argument("--lattice", default="l216", choices=sorted(LATTICES))
-    ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--cpu-per-worker", type=int, default=160, help="scenarios per CPU worker process and pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the extra default-lattice / velocity microbench lines")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra lines (other lattices, stateful tick, config 5, weak)")
+    ap.add_argument("--no-peer", action="store_true", help="multi-GPU gather by point-to-point sends instead of peer stores")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -226,32 +277,31 @@ def main():
         sys.exit(subprocess.call(cmd))
 
     tag = args.lattice
-    config = {"workload": WORKLOADS[tag], "lattice": tag, "per_gpu_batch": args.batch, "seed": SEED,
+    config = {"workload": WORKLOADS[tag], "lattice": tag, "job_batch": args.batch, "seed": SEED,
               "stateless_first_tick": True, "velocity_planner": "fb"}
 
     # ------------------------------------------------------------------------------------------------------------------
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count()
-        sample = args.cpu_sample or max(cores * 8, 512)
-        arm = CpuArm(tag, cores)
-        sc = make_batch(tag, sample)
+        arm = CpuArm(tag)
+        sc = make_batch(tag, arm.cores * args.cpu_per_worker)
         for _ in range(args.warmup):
-            arm.run(sc.subset(np.arange(min(sample, cores * 2))))
-        t = [arm.run(sc) for _ in range(args.steps)]
+            arm.run(sc.subset(np.arange(min(sc.size, arm.cores * 4))))
+        t = [arm.run(sc)[0] for _ in range(args.steps)]
+        t_one = arm.run(sc.subset(np.arange(args.cpu_per_worker)), workers=1)[0]
         arm.close()
         total = float(np.sum(t))
-        value = sample * args.steps / total
-        desc = "first %d scenarios of the seeded batch per step" % sample
+        value = sc.size * args.steps / total
+        m = dict(all=value, one=args.cpu_per_worker / t_one, sample=sc.size, seconds_all=total / args.steps,
+                 seconds_one=t_one, per_worker=args.cpu_per_worker, runs=args.steps)
         emit(({
             "impl": "reference", "metric": METRIC, "value": value, "unit": "ticks/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(config, cpu_sample=sample),
-            "cpu_baseline": {"value": value, "unit": "ticks/s", "cores": cores, "kind": "port", "sample": desc,
-                             "note": "float64 NumPy restatement of the reference path (oracle/ltpl_oracle.py); the "
-                                     "reference itself needs igraph + tph which are not installable offline"},
+            "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(config, cpu_sample=sc.size, step="one pass of all host cores over the sample"),
+            "cpu_baseline": cpu_baseline_dict(arm, m),
             "e2e": {"value": value, "unit": "ticks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -259,15 +309,11 @@ def main():
     # ------------------------------------------------------------------------------------------------------------------
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:   # before CUDA is initialised in this process (spawned workers)
-        cores = os.cpu_count()
-        sample = args.cpu_sample or max(cores * 8, 512)
-        arm = CpuArm(tag, cores)
-        sc_cpu = make_batch(tag, sample)
-        arm.run(sc_cpu.subset(np.arange(min(sample, cores * 2))))
-        dt = min(arm.run(sc_cpu) for _ in range(2))
+        arm = CpuArm(tag)
+        cpu = cpu_baseline_dict(arm, arm.measure(per_worker=args.cpu_per_worker, runs=3))
         arm.close()
-        cpu = {"value": sample / dt, "unit": "ticks/s", "cores": cores, "kind": "port",
-               "sample": "first %d scenarios of the seeded batch, best of 2, %d worker processes" % (sample, cores)}
+
+    import ctypes as C
 
     import torch
     import torch.distributed as dist
@@ -292,19 +338,23 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    online = read_online_config(ONLINE_INI)
     # lattice: built on rank 0, broadcast as one byte blob (NCCL), every rank creates its own handle
     lat = get_lattice(tag) if rank == 0 or world == 1 else None
+    packed_blob = None
     if world > 1:
         header, cap, blob_t = parallel.broadcast_lattice(lat, device, src=0)
-        pl = BatchPlanner(online=read_online_config(ONLINE_INI), device=device, packed=(header, cap), blob_tensor=blob_t)
+        packed_blob = ((header, cap), blob_t)
+        pl = BatchPlanner(online=online, device=device, packed=(header, cap), blob_tensor=blob_t)
         if lat is None:
-            lat = get_lattice(tag)   # host-side stats only
+            lat = get_lattice(tag)   # host-side statistics only
     else:
-        pl = BatchPlanner(lat, online=read_online_config(ONLINE_INI), device=device)
+        pl = BatchPlanner(lat, online=online, device=device)
     pl.set_vel_params(**vel_kwargs())
 
-    # every rank plans its own batch (different seeds per rank): weak scaling, no data-path collective
-    sc = make_batch(tag, args.batch, seed=SEED + rank)
+    # the job's batch; N > 1: scenario i is planned by rank i % world
+    sc_job = make_batch(tag, args.batch, seed=SEED)
+    sc = sc_job.shard(rank, world) if world > 1 else sc_job
     pl.stage_scenarios(sc)
     pl.upload()
     pl.set_startpos()
@@ -324,8 +374,32 @@ def main():
         torch.cuda.synchronize(device)
         return sum(e0.elapsed_time(e1) for e0, e1 in evs) * 1e-3
 
-    for _ in range(args.warmup):
+    # multi-GPU: gather of all action sets into rank 0's HBM inside the timed region
+    gather, gather_kind, gather_out = None, None, [None]
+    if world > 1:
+        if not args.no_peer:
+            try:
+                gather = parallel.PeerGather(pl, dst=0)
+                gather.attach()
+                gather_kind = "peer stores: k_export writes the live rows into rank 0's HBM over NVLink (symmetric memory) " \
+                              "+ one peer copy of the per-path arrays + device-side barrier per tick"
+            except Exception as e:   # noqa: BLE001
+                gather = None
+                gather_kind = "point-to-point sends of the live rows (peer memory unavailable: %s)" % str(e)[:120]
+        else:
+            gather_kind = "point-to-point sends of the live rows (--no-peer)"
+
+    def step():
         pl.tick()
+        if world > 1:
+            if gather is not None:
+                gather.finish()
+            else:   # row count to the host, then sends of exactly the live rows + the packed per-path arrays
+                n = int(pl.t["queue_cnt"][2].item())
+                gather_out[0], _ = parallel.gather_rows(pl.t["traj"], n, dst=0, out=gather_out[0])
+
+    for _ in range(args.warmup):
+        step()
     clocks = {}
     stop_evt = threading.Event()
     ready_evt = threading.Event()
@@ -335,177 +409,210 @@ def main():
         ready_evt.wait(timeout=10.0)   # first nvidia-smi sample has arrived: the sampler covers the timed region
     barrier()
     l0 = pl.launch_count()
-    t_dev = timed_loop(pl.tick, args.steps)
+    t_dev = timed_loop(step, args.steps)
     launches = pl.launch_count() - l0
     barrier()
     t_dev = max_over_ranks(t_dev)
-    value = world * args.batch * args.steps / t_dev
+    value = args.batch * args.steps / t_dev
+    gathered_rows = None
+    if world > 1 and rank == 0 and gather is not None:   # the consumer sees every rank's rows: count them
+        gathered_rows = 0
+        for rows, meta in gather.regions():
+            v = pl._packed(pl._meta_spec, lambda n, m=meta: m)[1] if hasattr(pl, "_meta_spec") else None
+            gathered_rows += int(v["queue_cnt"][2].item()) if v is not None else 0
+    if gather is not None:
+        gather.detach()
 
-    # batch statistics for the algorithmic byte counts (rank 0's batch)
-    f = pl.fetch("sc_flags", "status", "action_id", "n_nodes", "path_len", "traj_len", "const_len")
-    found = (f["status"] & capi.ST_FOUND) != 0
-    stats = dict(batch=args.batch, n_obj_sum=float(sc.n_obj.sum()), n_actions=float(found.sum()),
-                 seg_sum=float(np.maximum(f["n_nodes"] - 2, 0)[found].sum()), nodes_sum=float(f["n_nodes"][found].sum()),
-                 pts_sum=float(f["path_len"][found].sum()),
-                 pts_follow_sum=float(f["path_len"][found & (f["action_id"] == capi.ACT_FOLLOW)].sum()),
-                 export_rows=float(f["traj_len"].sum()), p0_mean=float(f["const_len"].mean()))
-    n_bad = {name: int(((f["sc_flags"] & bit) != 0).sum()) for name, bit in (
-        ("out_of_track", capi.SC_OUT_OF_TRACK), ("heading_mismatch", capi.SC_HEADING_MISMATCH),
-        ("capacity", capi.SC_CAPACITY), ("brake_prefix", capi.SC_BRAKE_PREFIX))}
+    def batch_stats(plx, scx):
+        f = plx.fetch("sc_flags", "status", "action_id", "n_nodes", "path_len", "traj_len", "const_len")
+        found = (f["status"] & capi.ST_FOUND) != 0
+        st = dict(batch=scx.size, n_obj_sum=float(scx.n_obj.sum()), n_actions=float(found.sum()),
+                  seg_sum=float(np.maximum(f["n_nodes"] - 2, 0)[found].sum()), nodes_sum=float(f["n_nodes"][found].sum()),
+                  pts_sum=float(f["path_len"][found].sum()),
+                  pts_follow_sum=float(f["path_len"][found & (f["action_id"] == capi.ACT_FOLLOW)].sum()),
+                  export_rows=float(f["traj_len"].sum()), p0_mean=float(f["const_len"].mean()))
+        bad = {name: int(((f["sc_flags"] & bit) != 0).sum()) for name, bit in (
+            ("out_of_track", capi.SC_OUT_OF_TRACK), ("heading_mismatch", capi.SC_HEADING_MISMATCH),
+            ("capacity", capi.SC_CAPACITY), ("brake_prefix", capi.SC_BRAKE_PREFIX))}
+        return st, bad
 
-    # per-kernel device time (each kernel launched alone through ltpl_launch_stage, same buffers, L2 flushed)
-    import ctypes as C
     stage_names = {1: "k_plan", 2: "k_path", 3: "k_vel", 4: "k_export"}
-    ktime = {}
-    for stage, name in stage_names.items():
-        def one(stage=stage):
-            capi.check(pl.lib, pl.lib.ltpl_launch_stage(stage, pl.handle, C.byref(pl.params), C.byref(pl.dims),
-                                                        C.byref(pl.buf), pl.stream), name)
-        for _ in range(3):
-            one()
-        ktime[name] = timed_loop(one, args.steps) / args.steps
 
-    # ------------------------------------------------------------------------------------------------------------------
-    # e2e: public API with host buffers (pinned): H2D scenario arrays + set_startpos + tick + D2H action sets per step
-    ltpl = Graph_LTPL.__new__(Graph_LTPL)
-    ltpl._Graph_LTPL__planner = pl           # reuse the planner (same lattice handle / buffers)
-    cap_rows = (3 * args.batch) // 2   # fixed-stride all-gather capacity (mean is ~1.3 kept trajectories per scenario)
-    comm = torch.cuda.Stream(device=device) if world > 1 else None
-    gather_bufs, gather_done = [], {}
-    snap = [(torch.empty_like(pl.t["traj_len"]), torch.empty_like(pl.t["traj_id"])) for _ in range(pl.N_SETS)]
-
-    def hook(k):
-        # all-gather of the (fixed-stride) compact action sets over NVLink on a communication stream: it overlaps the
-        # kernels of the next step exactly like the D2H copy does (the small per-path arrays are snapshotted first)
-        if world == 1:
-            return
-        compute = torch.cuda.current_stream(device)
-        snap[k][0].copy_(pl.t["traj_len"])
-        snap[k][1].copy_(pl.t["traj_id"])
-        ev = torch.cuda.Event()
-        ev.record(compute)
-        with torch.cuda.stream(comm):
-            comm.wait_event(ev)
-            parallel.gather_action_sets(pl.traj_bufs[k][:cap_rows], snap[k][0], snap[k][1], out=gather_bufs)
-            done = torch.cuda.Event()
-            done.record(comm)
-        gather_done[k] = done
-
-    def hook_before(k):
-        if k in gather_done:   # buffer set k is about to be rewritten
-            torch.cuda.current_stream(device).wait_event(gather_done[k])
-    hook.before = hook_before
-
-    def feed(n):
-        for _ in range(n):
-            yield sc      # the same host-side ScenarioBatch is staged, uploaded and planned every step
-
-    for out in ltpl.plan_stream(feed(3), device_hook=hook):
-        pass
-    barrier()
-    t0 = time.perf_counter()
-    rows = 0
-    for out in ltpl.plan_stream(feed(args.steps), device_hook=hook):
-        rows += int(out["n_rows"])
-    torch.cuda.synchronize(device)
-    barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * args.batch * args.steps / t_e2e
-    assert rows > 0 and rows <= cap_rows * args.steps
-    rows_per_step = rows / args.steps
-    if rank == 0:
-        stop_evt.set()
-        th.join(timeout=3)
-
-    # third timing of SURVEY 8(d): the optional per-scenario Python view of one result (reference-style dicts)
-    t0 = time.perf_counter()
-    unpacked = Graph_LTPL.unpack_batch(out)
-    t_unpack = time.perf_counter() - t0
-    assert len(unpacked) == args.batch
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    def kernel_times(plx, steps):
+        """per-kernel device time (each kernel launched alone through ltpl_launch_stage, same buffers, L2 flushed)"""
+        kt = {}
+        for stage, name in stage_names.items():
+            def one(stage=stage, name=name):
+                capi.check(plx.lib, plx.lib.ltpl_launch_stage(stage, plx.handle, C.byref(plx.params), C.byref(plx.dims),
+                                                              C.byref(plx.buf), plx.stream), name)
+            for _ in range(3):
+                one()
+            kt[name] = timed_loop(one, steps) / steps
+        return kt
 
     peaks_path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.isfile(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    alg = algorithmic_bytes(lat, stats)
-    dom = max(ktime, key=ktime.get)
-    achieved = alg[dom] / ktime[dom] / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg[dom],
-                "kernel_ms": {k: 1e3 * v for k, v in ktime.items()},
-                "kernel_share_of_step": {k: v / sum(ktime.values()) for k, v in ktime.items()},
-                "per_kernel_gbs": {k: alg[k] / ktime[k] / 1e9 for k in ktime},
-                "note": "latency/issue-bound: the lattice (%.1f MB) is L2-resident, see DESIGN.md" % (
-                    pl.blob.numel() / 1e6)}
-    traffic_path = os.path.join(REPO, "profiles", "traffic.json")
-    if os.path.isfile(traffic_path):
-        try:
-            roofline["traffic"] = json.load(open(traffic_path)).get(tag, {}).get(dom)
-        except Exception:
-            pass
+    try:
+        traffic_tab = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+    except Exception:   # noqa: BLE001
+        traffic_tab = {}
 
+    def roofline_of(latx, tagx, stats, ktime, ms_step, blob_mb):
+        alg = algorithmic_bytes(latx, stats)
+        dom = max(ktime, key=ktime.get)
+        achieved = alg[dom] / ktime[dom] / 1e9
+        step_s = ms_step * 1e-3
+        return {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic_tab.get(tagx, {}).get(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom],
+                "algorithmic_bytes_definition": "inputs + outputs of the kernel, float64 / int32 as computed, no scratch",
+                "kernel_ms": {k: 1e3 * v for k, v in ktime.items()},
+                "kernel_share_of_step": {k: v / step_s for k, v in ktime.items()},
+                "per_kernel_gbs": {k: alg[k] / ktime[k] / 1e9 for k in ktime},
+                "per_kernel_frac": {k: alg[k] / ktime[k] / 1e9 / peak for k in ktime},
+                "k_vel_frac_fp32_element_sizes": alg["k_vel_fp32_sizes"] / ktime["k_vel"] / 1e9 / peak,
+                "k_plan_gbs_counted_as_reference_work": alg["k_plan_as_reference"] / ktime["k_plan"] / 1e9,
+                "whole_tick": {"bytes_per_tick_survey_8d": alg["tick_survey_8d"] / stats["batch"],
+                               "achieved_gbs": alg["tick_survey_8d"] / step_s / 1e9,
+                               "frac": alg["tick_survey_8d"] / step_s / 1e9 / peak,
+                               "bound_ticks_per_s": peak * 1e9 / (alg["tick_survey_8d"] / stats["batch"])},
+                "note": "latency / issue bound: the lattice (%.1f MB) is L2-resident, DRAM traffic ~ compulsory bytes "
+                        "(DESIGN.md section 5)" % blob_mb}
+
+    stats, n_bad = batch_stats(pl, sc)
+    ktime = kernel_times(pl, args.steps)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # e2e: public API with host buffers (pinned): H2D scenario arrays + set_startpos + tick + D2H action sets per step
+    ltpl = Graph_LTPL.__new__(Graph_LTPL)
+    ltpl._Graph_LTPL__planner = pl           # reuse the planner (same lattice handle / buffers)
+
+    def feed(scx, n):
+        for _ in range(n):
+            yield scx      # the same host-side ScenarioBatch is staged, uploaded and planned every step
+
+    def e2e_run(scx, steps):
+        for out in ltpl.plan_stream(feed(scx, 3)):
+            pass
+        barrier()
+        t0 = time.perf_counter()
+        rows = 0
+        for out in ltpl.plan_stream(feed(scx, steps)):
+            rows += int(out["n_rows"])
+        torch.cuda.synchronize(device)
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0), rows, out
+
+    t_e2e, rows, out = e2e_run(sc, args.steps)
+    e2e_value = args.batch * args.steps / t_e2e
+    rows_per_step = rows / args.steps
+    if rank == 0:
+        stop_evt.set()
+        th.join(timeout=3)
+
+    # third timing of SURVEY 8(d): the per-scenario Python view of one result (reference-style dicts)
+    t0 = time.perf_counter()
+    unpacked = Graph_LTPL.unpack_batch(out)
+    t_unpack = time.perf_counter() - t0
+    assert len(unpacked) == sc.size
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # weak scaling (N > 1): every rank plans its own 10 000-scenario batch, replicas, no gather
+    weak = None
+    if world > 1 and not args.no_extra:
+        pl_w = BatchPlanner(online=online, device=device, packed=packed_blob[0], blob_tensor=packed_blob[1])
+        pl_w.set_vel_params(**vel_kwargs())
+        sc_w = make_batch(tag, args.batch, seed=SEED + rank)
+        pl_w.stage_scenarios(sc_w)
+        pl_w.upload()
+        pl_w.set_startpos()
+        for _ in range(args.warmup):
+            pl_w.tick()
+        barrier()
+        tw = max_over_ranks(timed_loop(pl_w.tick, args.steps))
+        ltpl._Graph_LTPL__planner = pl_w
+        tw_e2e, _, _ = e2e_run(sc_w, args.steps)
+        ltpl._Graph_LTPL__planner = pl
+        weak = {"scaling": "weak", "per_gpu_batch": args.batch, "value": world * args.batch * args.steps / tw,
+                "ms_per_step": 1e3 * tw / args.steps, "e2e_value": world * args.batch * args.steps / tw_e2e,
+                "e2e_ms_per_step": 1e3 * tw_e2e / args.steps,
+                "mode": "replicas: every rank keeps its action sets (rank-local consumers), no gather"}
+        del pl_w
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = 1e3 * t_dev / args.steps
+    blob_mb = pl.blob.numel() / 1e6
+    # per-kernel times were taken on this rank's shard; the step of `value` additionally holds the gather (N > 1)
+    roofline = roofline_of(lat, tag, stats, ktime, 1e3 * sum(ktime.values()) if world > 1 else ms_step, blob_mb)
     result = {
         "metric": METRIC, "value": value, "unit": "ticks/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f64 (decisions, splines, arc lengths) + f32 (velocity recurrences)",
+        "data": "synthetic",
         "config": dict(config, l2="256 MiB buffer written before every timed step (L2 = 126 MB)",
-                       actions_per_tick=stats["n_actions"] / args.batch,
+                       scenarios_per_gpu=sc.size, actions_per_tick=stats["n_actions"] / sc.size,
                        path_points_per_action=stats["pts_sum"] / max(stats["n_actions"], 1),
-                       scenarios_flagged=n_bad, parallelism="%d x independent scenario shards" % world),
+                       scenarios_flagged=n_bad,
+                       parallelism="%d GPU(s): the seeded batch sharded i %% world, lattice broadcast once" % world
+                       + ("; timed region = tick of every shard + gather of all action sets into rank 0's HBM (%s)"
+                          % gather_kind if world > 1 else "")),
         "e2e": {"value": e2e_value, "unit": "ticks/s", "h2d_bytes_per_step": pl.h2d_bytes(),
                 "d2h_bytes_per_step": pl.d2h_bytes(int(rows_per_step)), "ms_per_step": 1e3 * t_e2e / args.steps,
-                "kept_trajectories_per_step": rows_per_step,
-                "facade_unpack_ms_per_batch": 1e3 * t_unpack,
+                "kept_trajectories_per_step": rows_per_step, "facade_unpack_ms_per_batch": 1e3 * t_unpack,
                 "api": "Graph_LTPL.plan_stream: per step host staging + H2D + set_startpos + calc_paths + "
                        "calc_vel_profile + D2H of the compact action sets; D2H of step i overlaps the kernels of step "
-                       "i+1 (copy stream, 3 buffer sets)" + ("; + all_gather of the action sets on a communication stream" if world > 1 else "")},
+                       "i+1 (copy stream, 3 buffer sets)" + ("; every rank stages / uploads its shard and downloads its "
+                                                              "shard's action sets (bytes per rank)" if world > 1 else "")},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if gathered_rows is not None:
+        result["config"]["rows_in_rank0_hbm_after_gather"] = gathered_rows
     if cpu is not None:
         result["cpu_baseline"] = cpu
+    extra = {}
+    if weak is not None:
+        extra["weak"] = weak
 
     if not args.no_extra and world == 1:
-        extra = {}
-        try:   # shipped default lattice (128 layers x 13-25 nodes, 14 k edges): the non-degenerate search workload
-            lat_d = get_lattice("default")
-            pl_d = BatchPlanner(lat_d, online=read_online_config(ONLINE_INI), device=device)
-            pl_d.set_vel_params(**vel_kwargs())
-            pl_d.stage_scenarios(make_batch("default", args.batch))
-            pl_d.upload()
-            pl_d.set_startpos()
-            for _ in range(args.warmup):
-                pl_d.tick()
-            td = timed_loop(pl_d.tick, args.steps)
-            extra["default_lattice_ticks_per_s"] = args.batch * args.steps / td
-            extra["default_lattice_ms_per_step"] = 1e3 * td / args.steps
-            del pl_d
-        except Exception as e:   # noqa: BLE001
-            extra["default_lattice_error"] = str(e)[:200]
-        try:   # 430 layers x 13-25 nodes (lon steps 6 m, lat_resolution 0.5), 5 objects each
-            pl_4 = BatchPlanner(get_lattice("l430"), online=read_online_config(ONLINE_INI), device=device)
-            pl_4.set_vel_params(**vel_kwargs())
-            pl_4.stage_scenarios(make_batch("l430", args.batch))
-            pl_4.upload()
-            pl_4.set_startpos()
-            for _ in range(args.warmup):
-                pl_4.tick()
-            t4 = timed_loop(pl_4.tick, args.steps)
-            extra["config4_l430_ticks_per_s"] = args.batch * args.steps / t4
-            extra["config4_l430_ms_per_step"] = 1e3 * t4 / args.steps
-            del pl_4
-        except Exception as e:   # noqa: BLE001
-            extra["config4_l430_error"] = str(e)[:200]
+        def side_line(tagx, key):
+            """another lattice as a first-class line: ticks/s, per-kernel split and roofline like the headline"""
+            try:
+                lat_x = get_lattice(tagx)
+                pl_x = BatchPlanner(lat_x, online=online, device=device)
+                pl_x.set_vel_params(**vel_kwargs())
+                sc_x = make_batch(tagx, args.batch)
+                pl_x.stage_scenarios(sc_x)
+                pl_x.upload()
+                pl_x.set_startpos()
+                for _ in range(args.warmup):
+                    pl_x.tick()
+                tx = timed_loop(pl_x.tick, args.steps)
+                st_x, bad_x = batch_stats(pl_x, sc_x)
+                kt_x = kernel_times(pl_x, args.steps)
+                extra[key] = {"workload": WORKLOADS[tagx], "ticks_per_s": args.batch * args.steps / tx,
+                              "ms_per_step": 1e3 * tx / args.steps,
+                              "actions_per_tick": st_x["n_actions"] / args.batch, "scenarios_flagged": bad_x,
+                              "lattice": {"layers": lat_x.num_layers, "nodes": lat_x.num_nodes, "edges": lat_x.num_edges},
+                              "roofline": roofline_of(lat_x, tagx, st_x, kt_x, 1e3 * tx / args.steps,
+                                                      pl_x.blob.numel() / 1e6)}
+                del pl_x
+            except Exception as e:   # noqa: BLE001
+                extra[key + "_error"] = str(e)[:300]
+        side_line("default", "default_lattice")   # shipped ini: 128 layers x 13-25 nodes, 14 k edges (the DP workload)
+        side_line("l430", "config4_l430")         # SURVEY 8(d) config 4: 430 layers, 5 objects
+
         try:   # stateful ticks (DESIGN.md section 11): closed loop of 8 ticks on the bench workload; a
             # vehicle dummy advances every scenario 0.1 s on its first kept trajectory; the loop is recorded once
             # (untimed host work between the ticks) and replayed with CUDA events around every next_tick
             from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
-            pl_s = BatchPlanner(lat, online=read_online_config(ONLINE_INI), device=device, stateful=True)
+            pl_s = BatchPlanner(lat, online=online, device=device, stateful=True)
             pl_s.set_vel_params(**vel_kwargs())
             n_loop, dt_loop = 8, 0.1
 
@@ -537,9 +644,8 @@ def main():
             rec_in = []
             pos_e, vel_e = sc.pos.copy(), sc.vel.copy()
             for _ in range(n_loop):
-                out = pl_s.download()
-                torch.cuda.synchronize(device)
-                p_new, v_new, sel_a, ok = advance(out)
+                out_s = pl_s.download()
+                p_new, v_new, sel_a, ok = advance(out_s)
                 pos_e, vel_e = np.where(ok[:, None], p_new, pos_e), np.where(ok, v_new, vel_e)
                 rec_in.append((pos_e.copy(), vel_e.copy(), sel_a.astype(np.int32)))
                 sc_k = ScenarioBatch(pos_e.copy(), sc.heading, sc.vel, sc.n_obj, sc.obj)
@@ -547,25 +653,29 @@ def main():
             torch.cuda.synchronize(device)
             flags = pl_s.fetch("sc_flags")["sc_flags"]
             first_tick()
-            t_st = 0.0
-            stream_s = torch.cuda.current_stream(device)
+            t_st, t_wall = 0.0, 0.0
             for pos_k, vel_k, sel_k in rec_in:
                 sc_k = ScenarioBatch(pos_k, sc.heading, sc.vel, sc.n_obj, sc.obj)
                 flush.fill_(1)
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream_s)
-                pl_s.next_tick(sc_k, sel_k, 2.0 * dt_loop, vel_est=vel_k)
-                e1.record(stream_s)
                 torch.cuda.synchronize(device)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                w0 = time.perf_counter()
+                e0.record(stream)
+                pl_s.next_tick(sc_k, sel_k, 2.0 * dt_loop, vel_est=vel_k)
+                e1.record(stream)
+                torch.cuda.synchronize(device)
+                t_wall += time.perf_counter() - w0
                 t_st += e0.elapsed_time(e1) * 1e-3
             extra["stateful_tick"] = {"ticks_per_s": args.batch * n_loop / t_st, "ms_per_tick": 1e3 * t_st / n_loop,
+                                      "wall_ms_per_tick_incl_host_staging": 1e3 * t_wall / n_loop,
                                       "ticks": n_loop, "scenarios_still_planned_at_the_end": int((flags == 0).sum()),
                                       "flags_at_the_end": {name: int(((flags & bit) != 0).sum()) for name, bit in (
                                           ("out_of_track", capi.SC_OUT_OF_TRACK),
                                           ("heading_mismatch", capi.SC_HEADING_MISMATCH), ("capacity", capi.SC_CAPACITY),
                                           ("brake_prefix", capi.SC_BRAKE_PREFIX),
                                           ("state_fallback", capi.SC_STATE_FALLBACK))},
-                                      "note": "closed loop, 0.1 s per tick; device time of one next_tick incl. its input upload"}
+                                      "note": "closed loop, 0.1 s per tick; device time of one next_tick incl. its ONE "
+                                              "packed input upload and the carry copy of the per-path arrays"}
             del pl_s
         except Exception as e:   # noqa: BLE001
             extra["stateful_tick_error"] = str(e)[:300]
@@ -585,11 +695,15 @@ def main():
                 vp()
             tv = timed_loop(vp, 10) / 10
             nbytes = 100000 * 500 * 4 * 8
-            extra["velprofile_100k_x_500"] = {"ms": 1e3 * tv, "paths_per_s": 100000 / tv,
-                                              "algorithmic_GBps": nbytes / tv / 1e9, "frac_of_peak": nbytes / tv / 1e9 / peak,
-                                              "dtype": "f64 (kappa, el in; vx, ax out = 32 B / point)"}
+            extra["velprofile_100k_x_500"] = {
+                "ms": 1e3 * tv, "paths_per_s": 100000 / tv, "algorithmic_GBps": nbytes / tv / 1e9,
+                "frac_of_peak": nbytes / tv / 1e9 / peak,
+                "frac_of_peak_fp32_element_sizes": nbytes / 2 / tv / 1e9 / peak,
+                "traffic": traffic_tab.get("velprofile", {}).get("k_velprofile"),
+                "dtype": "kappa, el in; vx, ax out as float64 = 32 B / point (SURVEY 8(d): 16 B / point in fp32)"}
         except Exception as e:   # noqa: BLE001
             extra["velprofile_error"] = str(e)[:200]
+    if extra:
         result["extra"] = extra
 
     emit(result)

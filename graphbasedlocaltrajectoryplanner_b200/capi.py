@@ -12,7 +12,7 @@ import os
 import subprocess
 import sys
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 NSLOT = 3
 KMAX = 16
 MAX_AXM = 32
@@ -24,6 +24,7 @@ ACTION_NAMES = {ACT_STRAIGHT: "straight", ACT_FOLLOW: "follow", ACT_LEFT: "left"
 ST_FOUND, ST_REDUCED_HORIZON, ST_TIE_AMBIGUOUS, ST_START_BLOCKED = 1, 2, 4, 8
 ST_TRAJ_VALID, ST_VEL_BOUND_VIOL, ST_TOO_CLOSE, ST_CONST_ONLY, ST_RENAMED_STRAIGHT = 16, 32, 64, 128, 256
 SC_OUT_OF_TRACK, SC_HEADING_MISMATCH, SC_CAPACITY, SC_BRAKE_PREFIX, SC_STATE_FALLBACK = 1, 2, 4, 8, 16
+SC_REASON_SHIFT = 8   # bits 8..10 of sc_flags: why SC_STATE_FALLBACK was raised (include/ltpl_b200.h)
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
@@ -69,8 +70,8 @@ class Dims(C.Structure):
 
 BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
                  "const_coeff", "action_id", "status", "n_nodes", "nodes", "node_idx", "edge_seq", "closest_obj", "cobj", "cobj_start",
-                 "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "vel_scratch", "s_vx_ax",
-                 "vel_t", "traj", "traj_len", "traj_id", "zone_bits", "zone_sel", "em_info", "obj_pred",
+                 "path_len", "path", "coeff", "queue", "queue_cnt", "exp_q", "traj_row", "s_vx_ax",
+                 "traj", "traj_len", "traj_id", "zone_bits", "zone_sel", "em_info", "obj_pred",
                  "n_pred", "prev_path", "prev_path_len", "prev_node_idx", "prev_nodes", "prev_n_nodes", "prev_coeff",
                  "prev_s_vx_ax", "prev_action_id", "prev_traj_len", "prev_trim", "sel_action", "pos_last", "t_const",
                  "st_info", "trim", "vel_plan", "course", "obj_dist", "zone_s0", "em_vx", "prev_em_vx", "prev_em_info")

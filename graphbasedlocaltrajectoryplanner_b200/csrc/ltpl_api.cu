@@ -10,58 +10,46 @@
 #include <string>
 
 #define LTPL_WARPS_PER_CTA_EXPORT 8
-#define LTPL_VEL_BLOCK 64
-#ifndef LTPL_VEL_LANES
-#define LTPL_VEL_LANES 8   // work items (paths) per warp in k_vel, see ltpl_vel.cuh
-#endif
-// threads needed so that every queued path gets a lane (both queue classes padded to LTPL_VEL_LANES)
-#define LTPL_VEL_GRID(nq) ((int)((((size_t)(nq) / LTPL_VEL_LANES + 2) * 32 + LTPL_VEL_BLOCK - 1) / LTPL_VEL_BLOCK))
 #include "ltpl_path.cuh"
 #include "ltpl_plan.cuh"
 #include "ltpl_vel.cuh"
-#include "ltpl_vel_tiled.cuh"
-#include "ltpl_vel_split.cuh"
+#include "ltpl_vel_res.cuh"
+#include "ltpl_velprofile.cuh"
 #include "ltpl_emerg.cuh"
 #include "ltpl_state.cuh"
 
-#ifndef LTPL_VEL_TILED
-#define LTPL_VEL_TILED 1   // 1: tile-streamed velocity kernel (ltpl_vel_tiled.cuh), 0: thread-per-path k_vel
-#endif
-#ifndef LTPL_VEL_SPLIT
-// 1: k_vel_sweeps + k_vel_out (ltpl_vel_split.cuh: the independent recurrences of a follow path in concurrent CTAs),
-// 0: the single k_vel_tiled kernel.  Measured on B200 (10 k scenarios): the split shortens the chain per warp from ~3 n to
-// ~2 n steps but doubles the resident warps and adds ~25 % instructions (second prologue, kappa / el tiles loaded twice):
-// 0.35 ms against 0.28 ms -- the stage is bound by issue slots as much as by latency, so the single kernel stays default.
-#define LTPL_VEL_SPLIT 0
-#endif
-
 static std::atomic<unsigned long long> g_launches{0};
 
+// velocity kernel: one CTA per VR_P queued paths of one class, the paths resident in shared memory (ltpl_vel_res.cuh)
 static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                                 cudaStream_t st, bool stateful = false) {
     const int nq = LTPL_NSLOT * dm->batch;
-#if LTPL_VEL_TILED && LTPL_VEL_SPLIT
-    // follow groups get three CTAs each (<= B follow paths: slot 0 only), every other group one
-    const int g_follow = dm->batch / VT_P + 1, g_all = nq / VT_P + 2;
-    k_vel_sweeps<<<3 * g_follow + g_all, 32, VS_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    k_vel_out<<<g_all, 32, VO_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
-#elif LTPL_VEL_TILED
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_vel_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
+    const int nmax = dm->p_max;
+    if (nmax > 32 * VR_MAXM || nmax % 4 != 0) return cudaErrorInvalidValue;
+    const size_t smem = vr_smem_bytes(nmax);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    static thread_local size_t attr_set = 0;
+    if (smem > attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_vel_res<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_vel_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM_BYTES);
+            e = cudaFuncSetAttribute(k_vel_res<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_vel_res<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(k_vel_res<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set = smem;
     }
-    if (stateful)
-        k_vel_tiled<true><<<nq / VT_P + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
+    const int grid = nq / VR_P + 2;   // >= groups of the follow queue + groups of the other queue
+    const bool exp1 = prm->dyn_model_exp == 1.0;
+    if (stateful && exp1)
+        k_vel_res<true, true><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+    else if (stateful)
+        k_vel_res<true, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+    else if (exp1)
+        k_vel_res<false, true><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
     else
-        k_vel_tiled<false><<<nq / VT_P + 2, 32, VT_SMEM_BYTES, st>>>(lat->d, *prm, *dm, *bf);
-#else
-    k_vel<<<LTPL_VEL_GRID(nq), LTPL_VEL_BLOCK, 0, st>>>(lat->d, *prm, *dm, *bf);
-#endif
+        k_vel_res<false, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
     return cudaSuccess;
 }
 
@@ -265,7 +253,7 @@ static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplD
                       cudaStream_t st) {
     const int nq = LTPL_NSLOT * dm->batch;
     if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
-    if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: cudaFuncSetAttribute failed");
+    if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
     if (int r = check_launch("k_vel")) return r;
     k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
         *dm, *bf);
@@ -314,11 +302,7 @@ static int check_stateful(const LtplLattice* lat, const LtplParams* prm, const L
     if (dm->n_zones > 0 && !bf->zone_s0) return fail("stateful tick with zones: buffers.zone_s0 must be set");
     if (prm->incl_emerg_traj && !bf->em_info) return fail("params.incl_emerg_traj needs buffers.em_info");
     if (prm->delaycomp <= 0.0) return fail("params.delaycomp must be > 0");
-#if !LTPL_VEL_TILED || LTPL_VEL_SPLIT
-    return fail("the stateful tick needs the default velocity kernel (LTPL_VEL_TILED=1, LTPL_VEL_SPLIT=0)");
-#else
     return 0;
-#endif
 }
 
 int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
@@ -365,7 +349,7 @@ int ltpl_next_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* p
     k_ref<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
     if (int r = check_launch("k_ref")) return r;
     if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
-    if (launch_k_vel(lat, prm, dm, bf, st, true) != cudaSuccess) return fail("k_vel: cudaFuncSetAttribute failed");
+    if (launch_k_vel(lat, prm, dm, bf, st, true) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
     if (int r = check_launch("k_vel")) return r;
     k_backup<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*prm, *dm, *bf);
     if (int r = check_launch("k_backup")) return r;
@@ -430,7 +414,7 @@ int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, 
         case 3:
             if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess)
                 return fail("memset(export count) failed");
-            if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: cudaFuncSetAttribute failed");
+            if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
             return check_launch("k_vel");
         case 4:
             k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT,
@@ -446,12 +430,7 @@ int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* s
     if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");
     if (prm->axm_v[prm->n_axm - 1] < prm->vel_max)
         return fail("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!");
-#if LTPL_VEL_TILED
     k_velprofile_tiled<<<(vb->n_paths + 31) / 32, 32, VD_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
-#else
-    k_velprofile_dense<<<(vb->n_paths + LTPL_VEL_BLOCK - 1) / LTPL_VEL_BLOCK, LTPL_VEL_BLOCK, 0,
-                         static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
-#endif
     return check_launch("k_velprofile");
 }
 

@@ -19,7 +19,6 @@
 #pragma once
 #include "ltpl_plan.cuh"
 
-#define LTPL_COURSE_MAX 8
 
 // get_s_coord(..., only_index=True)[1] on an OPEN polyline given by a gather pt(i), i < n (get_s_coord.py:40-58, 94-97):
 // nearest point (first minimum), then the neighbour on the side of the larger angle; returns the pair (i0, i1)
@@ -287,13 +286,18 @@ k_ref(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffer
                 break;
             }
         }
-        vel_idx = min(arg + 1, nv - 1);
-        if (vel_idx < 0) vel_idx = 0;
-        if (vel_idx > LTPL_COURSE_MAX) vel_idx = LTPL_COURSE_MAX;   // capacity of `course` (flagged below)
-        bf.vel_plan[b] = V[cut_index + vel_idx];
-        for (int i = 0; i < vel_idx; ++i) bf.course[(size_t)b * LTPL_COURSE_MAX + i] = V[cut_index + i];
+        vel_idx = min(arg + 1, nv - 1);   // -1: the cut is the LAST row of the last trajectory -- v_past is empty
+        if (vel_idx >= 0) {
+            bf.vel_plan[b] = V[cut_index + vel_idx];
+            // `course` holds n_export rows per scenario = as many as an exported trajectory has: no truncation
+            for (int i = 0; i < vel_idx; ++i) bf.course[(size_t)b * dm.n_export + i] = V[cut_index + i];
+        }
     }
     vel_idx = __shfl_sync(LTPL_FULL, vel_idx, 0);
+    if (vel_idx < 0) {   // np.argmin of an empty array raises in the reference (OTH:570): not planned, re-anchor
+        if (lane == 0) bf.sc_flags[b] = LTPL_SC_STATE_FALLBACK | (7 << LTPL_SC_REASON_SHIFT);
+        return;
+    }
     const int cut_pos = (c_p - m_p) + cut_index;     // cut_index_pos in the NEW path planes (OTH:577)
 
     // cut layer from the node index list of the first action of this tick (OTH:580-590)
@@ -357,7 +361,7 @@ k_prefix(const LtplDims dm, const LtplBuffers bf) {
         double acc = 0.0;
         for (int i = 0; i < pref; ++i) {
             S[i] = acc;
-            VX[i] = bf.course[(size_t)b * LTPL_COURSE_MAX + i];
+            VX[i] = bf.course[(size_t)b * dm.n_export + i];
             acc = __dadd_rn(acc, E[i]);
         }
         for (int i = 0; i < pref; ++i) {

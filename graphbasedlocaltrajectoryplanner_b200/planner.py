@@ -147,81 +147,117 @@ class BatchPlanner(object):
             p.axm_s[i] = (axm[i + 1, 1] - axm[i, 1]) / (axm[i + 1, 0] - axm[i, 0])
 
     # -- buffers -----------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _packed(spec, make):
+        """one raw byte buffer + named views into it (sections 256-byte aligned)"""
+        offs, total = {}, 0
+        for name, shape, dt in spec:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            offs[name] = (total, nbytes, shape, dt)
+            total += (nbytes + 255) // 256 * 256
+        raw = make(total)
+        views = {name: raw[o:o + nb].view(dt).view(shape) for name, (o, nb, shape, dt) in offs.items()}
+        return raw, views
+
+    _IN_NAMES = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "zone_sel", "n_pred", "sel_action", "t_const",
+                 "obj_pred")
+
+    def _alloc_inputs(self, batch: int, k_obj: int, k_pred: int) -> None:
+        """The scenario inputs live in ONE packed device buffer (one H2D copy per tick) with N_SETS pinned host staging
+        sets.  Only these buffers depend on the object / prediction capacities, so a batch with more objects or with
+        its first 'prediction' array re-creates them and nothing else: the memory of a stateful session stays intact.
+        Two device copies are kept and used alternately by stateful ticks: the position estimate of the previous
+        calc_vel_profile (pos_last, OTH:537, MOPG:80-84) is then simply the other copy's ``pos``."""
+        B, K, dev = int(batch), int(k_obj), self.device
+        f64, i32 = torch.float64, torch.int32
+        in_spec = [("pos", (B, 2), f64), ("heading", (B,), f64), ("vel", (B,), f64), ("vel_est", (B,), f64),
+                   ("n_obj", (B,), i32), ("obj", (B, K, 5), f64), ("zone_sel", (B,), i32), ("n_pred", (B, K), i32),
+                   ("sel_action", (B,), i32), ("t_const", (B,), f64)]
+        if k_pred > 0:
+            in_spec.append(("obj_pred", (B, K, int(k_pred), 2), f64))
+        self._k_pred_cap = int(k_pred)
+        self.d_in = []
+        for _ in range(2):
+            raw, views = self._packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
+            if k_pred == 0:
+                views["obj_pred"] = torch.zeros((1,), dtype=f64, device=dev)
+            self.d_in.append((raw, views))
+        self.h_in_raw, self.h_in_sets = [], []
+        for _ in range(self.N_SETS):
+            raw, views = self._packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
+            self.h_in_raw.append(raw)
+            self.h_in_sets.append(views)
+        self.h_in = self.h_in_sets[0]
+        self._h2d_ev = [None] * self.N_SETS
+        self.dims.k_obj = K
+        self._use_inputs(0)
+
+    def _use_inputs(self, which: int) -> None:
+        self._in_cur = which
+        self.d_in_raw, views = self.d_in[which]
+        self.t.update(views)
+        for name in self._IN_NAMES:
+            if name in views and name not in ("sel_action", "t_const"):
+                setattr(self.buf, name, views[name].data_ptr())
+
     def allocate(self, batch: int, k_obj: int = 3, k_pred: int = 0) -> None:
-        if self.dims is not None and self.dims.batch == batch and self.dims.k_obj == max(1, k_obj) \
-                and self._k_pred_cap >= k_pred:
-            return
         k_obj = max(1, int(k_obj))
         if k_obj > capi.KMAX:
             raise ValueError("at most %d objects per scenario" % capi.KMAX)
+        if self.dims is not None and self.dims.batch == batch:
+            if self.dims.k_obj >= k_obj and self._k_pred_cap >= k_pred:
+                return
+            # more object slots / prediction points than before: only the input buffers grow (see _alloc_inputs)
+            torch.cuda.current_stream(self.device).synchronize()
+            self._alloc_inputs(batch, max(k_obj, self.dims.k_obj), max(int(k_pred), self._k_pred_cap))
+            return
         d = capi.Dims()
         d.batch, d.k_obj = int(batch), k_obj
         d.p0_max, d.p_max, d.h_max = self.cap["p0_max"], self.cap["p_max"], self.cap["h_max"]
         d.n_export = int(self.online["nmbr_export_points"])
-        B, K, P0, P, H, NE = d.batch, d.k_obj, d.p0_max, d.p_max, d.h_max, d.n_export
+        B, P0, P, H, NE = d.batch, d.p0_max, d.p_max, d.h_max, d.n_export
         dev = self.device
         f64, i32, f32 = torch.float64, torch.int32, torch.float32
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)   # noqa: E731
-
-        # The scenario inputs live in ONE packed device buffer (one H2D copy per tick) and the small per-path result
-        # arrays in another (one D2H copy per tick); the named tensors below are views into them.
-        def packed(spec, make):
-            offs, total = {}, 0
-            for name, shape, dt in spec:
-                nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
-                offs[name] = (total, nbytes, shape, dt)
-                total += (nbytes + 255) // 256 * 256
-            raw = make(total)
-            views = {name: raw[o:o + nb].view(dt).view(shape) for name, (o, nb, shape, dt) in offs.items()}
-            return raw, views
-
-        in_spec = [("pos", (B, 2), f64), ("heading", (B,), f64), ("vel", (B,), f64), ("vel_est", (B,), f64),
-                   ("n_obj", (B,), i32), ("obj", (B, K, 5), f64), ("zone_sel", (B,), i32), ("n_pred", (B, K), i32)]
-        self._k_pred_cap = int(k_pred)
-        if k_pred > 0:
-            in_spec.append(("obj_pred", (B, K, int(k_pred), 2), f64))
-        meta_spec = [("exp_q", (NSLOT * B,), i32), ("traj_row", (NSLOT, B), i32), ("traj_len", (NSLOT, B), i32),
-                     ("traj_id", (NSLOT, B), i32), ("action_id", (NSLOT, B), i32), ("status", (NSLOT, B), i32),
-                     ("sc_flags", (B,), i32), ("queue_cnt", (4,), i32), ("em_info", (B, 3), i32)]
-        self.d_in_raw, t_in = packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
-        self.d_meta_raw, t_meta = packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
+        # the small per-path result arrays live in one packed buffer (one D2H copy per tick)
+        # (the first six are what a stateful tick keeps of the previous one: one contiguous block, carried by one copy)
+        meta_spec = [("action_id", (NSLOT, B), i32), ("traj_len", (NSLOT, B), i32), ("em_info", (B, 3), i32),
+                     ("path_len", (NSLOT, B), i32), ("n_nodes", (NSLOT, B), i32), ("trim", (NSLOT * B, 4), i32),
+                     ("exp_q", (NSLOT * B,), i32), ("traj_row", (NSLOT, B), i32), ("traj_id", (NSLOT, B), i32),
+                     ("status", (NSLOT, B), i32), ("sc_flags", (B,), i32), ("queue_cnt", (4,), i32)]
+        self._carry_spec = meta_spec[:6]
+        self._meta_spec = meta_spec
+        self.d_meta_raw, t_meta = self._packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
         t = dict(
             start_node=z((B, 2), i32), const_len=z((B,), i32), const_seg=z((5, B, P0), f64),
             const_coeff=z((B, 8), f64),
-            n_nodes=z((NSLOT, B), i32), nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
+            nodes=z((NSLOT, B, H, 2), i32), node_idx=z((NSLOT, B, H), i32),
             edge_seq=z((NSLOT, B, H), i32), closest_obj=z((B,), i32), cobj=z((B, 4), f64), cobj_start=z((B,), i32),
-            path_len=z((NSLOT, B), i32),
             path=z((5, NSLOT * B, P), f64), coeff=z((NSLOT * B, H, 8), f64), queue=z((2, NSLOT * B), i32),
-            vel_scratch=z((3, NSLOT * B, P), f64),
-            s_vx_ax=z((3, NSLOT * B, P), f64), vel_t=z((5, P, NSLOT * B + 64), f64),
+            s_vx_ax=z((3, NSLOT * B, P), f64),
             traj=z(((NSLOT + 1) * B, NE, 7), f32))
-        t.update(t_in)
         t.update(t_meta)
         buf = capi.Buffers()
         t["zone_bits"] = torch.zeros((1, 1), dtype=torch.int32, device=dev)   # replaced by _upload_zones()
-        if k_pred == 0:
-            t["obj_pred"] = torch.zeros((1,), dtype=f64, device=dev)
         d.k_pred = 0
         d.n_zones, d.n_zone_words = 0, (self.lattice_nodes + 31) // 32
         for name in capi.BUFFER_FIELDS:
-            if name not in capi.STATE_FIELDS:
+            if name not in capi.STATE_FIELDS and name in t:   # `trim` is a state field: NULL unless the planner is stateful
                 setattr(buf, name, t[name].data_ptr())
         self.t, self.buf, self.dims = t, buf, d
+        self._alloc_inputs(B, k_obj, k_pred)
         self._state = None   # buffers of the stateful tick, allocated by next_tick()
         # further compact export buffers: the pipelined stream planner lets the D2H of step i overlap step i + 1
         self.traj_bufs = [t["traj"]] + [z(((NSLOT + 1) * B, NE, 7), f32) for _ in range(self.N_SETS - 1)]
-        # pinned host staging for the per-tick host <-> device copies (N_SETS sets for the pipelined path)
+        # pinned host staging of the per-tick results (N_SETS sets for the pipelined path)
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()   # noqa: E731
-        self.h_in_raw, self.h_in_sets, self.h_meta_raw, self.h_out_sets = [], [], [], []
+        self.h_meta_raw, self.h_out_sets = [], []
         for _ in range(self.N_SETS):
-            raw, views = packed(in_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
-            self.h_in_raw.append(raw)
-            self.h_in_sets.append(views)
-            raw, views = packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
+            raw, views = self._packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8).pin_memory())
             views["traj"] = pin(((NSLOT + 1) * B, NE, 7), f32)
             self.h_meta_raw.append(raw)
             self.h_out_sets.append(views)
-        self.h_in, self.h_out = self.h_in_sets[0], self.h_out_sets[0]
+        self.h_out = self.h_out_sets[0]
         self._meta_names = tuple(n for n, _, _ in meta_spec)
         self._row_bytes = NE * 7 * 4
         if self._stateful:
@@ -249,6 +285,9 @@ class BatchPlanner(object):
         kp = 0 if sc.pred is None else int(sc.pred.shape[2])
         if self.dims is None or sc.size != self.dims.batch or sc.obj.shape[1] > self.dims.k_obj or kp > self._k_pred_cap:
             self.allocate(sc.size, sc.obj.shape[1], kp)
+        if self._h2d_ev[which] is not None:   # an asynchronous upload may still read this pinned set
+            self._h2d_ev[which].synchronize()
+            self._h2d_ev[which] = None
         h = self.h_in_sets[which]
         k = sc.obj.shape[1]
         h["pos"].numpy()[...] = sc.pos
@@ -290,6 +329,26 @@ class BatchPlanner(object):
 
     def upload(self, which: int = 0) -> None:
         self.d_in_raw.copy_(self.h_in_raw[which], non_blocking=True)      # one packed H2D copy
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._h2d_ev[which] = ev
+
+    def set_estimates(self, pos_est=None, vel_est=None) -> None:
+        """position / velocity estimates of calc_vel_profile (LTPL:344-346) for the staged batch: written into the pinned
+        staging set 0 and copied to the device on the current stream."""
+        if self._h2d_ev[0] is not None:
+            self._h2d_ev[0].synchronize()
+            self._h2d_ev[0] = None
+        t = self.t
+        if pos_est is not None:
+            self.h_in["pos"].numpy()[...] = np.asarray(pos_est, dtype=np.float64).reshape(-1, 2)
+            t["pos"].copy_(self.h_in["pos"], non_blocking=True)
+        if vel_est is not None:
+            self.h_in["vel_est"].numpy()[...] = np.asarray(vel_est, dtype=np.float64).reshape(-1)
+            t["vel_est"].copy_(self.h_in["vel_est"], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._h2d_ev[0] = ev
 
     def _download_meta(self, which: int) -> None:
         self.h_meta_raw[which].copy_(self.d_meta_raw, non_blocking=True)  # one packed D2H copy
@@ -298,11 +357,14 @@ class BatchPlanner(object):
         """synchronous-style download on the current stream: per-path arrays + the filled rows of the compact
         trajectory list (the row count is read back first)."""
         out = self.h_out_sets[which]
+        stream = torch.cuda.current_stream(self.device)
         self._download_meta(which)
-        torch.cuda.current_stream(self.device).synchronize()
+        stream.synchronize()
         n = int(out["queue_cnt"][2])
         if n:
-            out["traj"][:n].copy_(self.t["traj"][:n], non_blocking=True)
+            src = next(tb for tb in self.traj_bufs if tb.data_ptr() == self.buf.traj)   # the set the kernels wrote
+            out["traj"][:n].copy_(src[:n], non_blocking=True)
+            stream.synchronize()   # the caller reads pinned host memory: the copy has to be complete
         out["n_rows"] = n
         out["incl_emerg_traj"] = bool(self.params.incl_emerg_traj)
         return out
@@ -340,9 +402,19 @@ class BatchPlanner(object):
             out["incl_emerg_traj"] = bool(self.params.incl_emerg_traj)
             inflight.append(k)
 
+        try:
+            yield from self._plan_stream_loop(batches, vel_est, device_hook, ns, compute, ev_meta, ev_d2h, pending,
+                                              inflight, issue_copy)
+        finally:
+            self.buf.traj = self.traj_bufs[0].data_ptr()
+
+    def _plan_stream_loop(self, batches, vel_est, device_hook, ns, compute, ev_meta, ev_d2h, pending, inflight,
+                          issue_copy):
         i = 0
         for sc in batches:
             k = i % ns
+            if self.dims is not None and sc.size != self.dims.batch and (pending or inflight):
+                raise ValueError("plan_stream: the batch size changed while results are in flight")
             while inflight and (inflight[0] == k or ev_d2h[inflight[0]].query()):
                 # hand out finished results in order; the set about to be reused must have left the device first
                 j = inflight.pop(0)
@@ -368,7 +440,6 @@ class BatchPlanner(object):
         for j in inflight:
             ev_d2h[j].synchronize()
             yield self.h_out_sets[j]
-        self.buf.traj = self.traj_bufs[0].data_ptr()
 
     # -- kernels ---------------------------------------------------------------------------------------------------------------
     def _call(self, fn, what):
@@ -406,7 +477,7 @@ class BatchPlanner(object):
 
     # -- stateful tick (csrc/ltpl_state.cuh) ----------------------------------------------
     _BIG = ("path", "node_idx", "nodes", "coeff", "s_vx_ax", "em_vx")            # swapped by pointer
-    _SMALL = ("path_len", "n_nodes", "action_id", "traj_len", "trim", "em_info")  # copied (a few bytes per path)
+    _SMALL = ("action_id", "traj_len", "em_info", "path_len", "n_nodes", "trim")  # carried by ONE device copy
 
     def _alloc_state(self) -> None:
         dev, B = self.device, self.dims.batch
@@ -416,15 +487,13 @@ class BatchPlanner(object):
         t["em_vx"] = z((B, self.dims.n_export), f64)   # f64 velocity of the emergency trajectory (executed 'emergency')
         self.buf.em_vx = t["em_vx"].data_ptr()
         t["em_info"].fill_(-1)
-        st = dict(other={k: torch.zeros_like(t[k]) for k in self._BIG},
-                  prev_small={"path_len": torch.zeros_like(t["path_len"]), "n_nodes": torch.zeros_like(t["n_nodes"]),
-                              "action_id": z((NSLOT, B), i32), "traj_len": z((NSLOT, B), i32),
-                              "trim": z((NSLOT * B, 4), i32), "em_info": torch.full((B, 3), -1, dtype=i32, device=dev)},
-                  sel_action=z((B,), i32), pos_last=z((B, 2), f64), t_const=z((B,), f64), st_info=z((B, 8), i32),
-                  vel_plan=z((B,), f64), course=z((B, 8), f64), obj_dist=z((B,), f64))
+        prev_raw, prev_small = self._packed(self._carry_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
+        prev_small["em_info"].fill_(-1)
+        st = dict(other={k: torch.zeros_like(t[k]) for k in self._BIG}, prev_raw=prev_raw, prev_small=prev_small,
+                  st_info=z((B, 8), i32), vel_plan=z((B,), f64), course=z((B, self.dims.n_export), f64),
+                  obj_dist=z((B,), f64))
         st["zone_s0"] = torch.full((B,), -1, dtype=i32, device=dev)
         self.buf.zone_s0 = st["zone_s0"].data_ptr()
-        t["trim"] = z((NSLOT * B, 4), i32)
         self.buf.trim = t["trim"].data_ptr()
         self._state = st
 
@@ -433,20 +502,25 @@ class BatchPlanner(object):
         lists (its poses are only used by ``next_calc_vel_profile``), ``sel_action`` = action id (capi.ACT_*) every
         scenario executed since the last tick, ``t_const`` = min(average calculation time * calc_time_safety, 0.5) per
         scenario (OTH:353-375; the caller keeps the moving average).  The previous tick (tick() / calc_paths() +
-        calc_vel_profile() after set_startpos(), or a stateful tick) must have run on this planner."""
+        calc_vel_profile() after set_startpos(), or a stateful tick) must have run on this planner.
+
+        Host side of one call: pointer swaps, the host memcpy into the pinned staging set, ONE packed H2D copy (scenario
+        arrays incl. sel_action / t_const), ONE device copy (the small per-path arrays of the last tick) and the
+        library call."""
+        if sc.size != self.dims.batch:
+            raise ValueError("stateful tick: the batch size must not change within a session (re-anchor with "
+                             "set_startpos on a new batch)")
         if self._state is None:
             self._alloc_state()
         st, t, buf = self._state, self.t, self.buf
-        ps = st["prev_small"]
-        for k in self._SMALL:
-            ps[k].copy_(t[k].view(ps[k].shape))
+        n_carry = st["prev_raw"].numel()
+        st["prev_raw"].copy_(self.d_meta_raw[:n_carry])       # the last tick's small per-path arrays
         for k in self._BIG:                                   # this tick writes the other set, the last one is memory
             t[k], st["other"][k] = st["other"][k], t[k]
             setattr(buf, k, t[k].data_ptr())
             setattr(buf, "prev_" + k, st["other"][k].data_ptr())
         for k in self._SMALL:
-            setattr(buf, "prev_" + k, ps[k].data_ptr())
-        st["pos_last"].copy_(t["pos"])                        # pos_est of the previous calc_vel_profile (OTH:537)
+            setattr(buf, "prev_" + k, st["prev_small"][k].data_ptr())
         # a zone under a NEW id is a new zone object: its unblock window is evaluated at this tick (OLI:155-237, GLNT:43-77)
         zkey = sc.zone_key if sc.zone_key is not None else np.zeros(sc.size, dtype=np.int64)
         last = getattr(self, "_zone_key", None)               # of the batch staged for the previous tick
@@ -454,25 +528,27 @@ class BatchPlanner(object):
             changed = np.nonzero((zkey != last) & (zkey != 0))[0]
             if changed.size:
                 st["zone_s0"][torch.as_tensor(changed, device=self.device)] = -1
-        st["sel_action"].copy_(torch.as_tensor(np.asarray(sel_action, dtype=np.int32).reshape(-1)))
-        st["t_const"].copy_(torch.as_tensor(np.broadcast_to(np.asarray(t_const, dtype=np.float64),
-                                                            (self.dims.batch,)).copy()))
-        for k in ("sel_action", "pos_last", "t_const", "st_info", "vel_plan", "course", "obj_dist"):
-            setattr(buf, k, st[k].data_ptr())
+        # pos_est of the previous calc_vel_profile (OTH:537) = `pos` of the input copy the last tick used; this tick
+        # uploads into the other copy (a batch with more objects than before re-creates only the input buffers)
+        self._pos_last = t["pos"]
         self.stage_scenarios(sc)
+        self._use_inputs(1 - self._in_cur)
+        buf.pos_last = self._pos_last.data_ptr()
+        for k in ("st_info", "vel_plan", "course", "obj_dist"):
+            setattr(buf, k, st[k].data_ptr())
+        buf.sel_action = t["sel_action"].data_ptr()
+        buf.t_const = t["t_const"].data_ptr()
+        self.h_in["sel_action"].numpy()[...] = np.asarray(sel_action, dtype=np.int32).reshape(-1)
+        self.h_in["t_const"].numpy()[...] = np.broadcast_to(np.asarray(t_const, dtype=np.float64), (self.dims.batch,))
         self.upload()
         self._call(self.lib.ltpl_next_calc_paths_batch, "ltpl_next_calc_paths_batch")
 
     def next_calc_vel_profile(self, pos_est=None, vel_est=None) -> None:
         """calc_vel_profile of a stateful tick (OTH:518-601 + 603-1040): position / velocity estimates per
         scenario (None: the poses / velocities staged by ``next_calc_paths``)."""
-        t, buf, st = self.t, self.buf, self._state
-        if pos_est is not None:
-            self.h_in["pos"].numpy()[...] = np.asarray(pos_est, dtype=np.float64).reshape(-1, 2)
-            t["pos"].copy_(self.h_in["pos"], non_blocking=True)
-        if vel_est is not None:
-            self.h_in["vel_est"].numpy()[...] = np.asarray(vel_est, dtype=np.float64).reshape(-1)
-            t["vel_est"].copy_(self.h_in["vel_est"], non_blocking=True)
+        buf, st = self.buf, self._state
+        if pos_est is not None or vel_est is not None:
+            self.set_estimates(pos_est, vel_est)
         keep_vel = buf.vel
         buf.vel = st["vel_plan"].data_ptr()                   # the planned velocity at the cut replaces the start velocity
         try:

@@ -15,8 +15,9 @@
  *   - return value: 0 = ok, < 0 = error (message via ltpl_last_error()).
  *   - per (scenario, action slot) results carry a status bit field (LTPL_ST_*); infeasible actions are flagged, never
  *     silently dropped, mirroring "omitted from the dict" in the reference (MOPG:246-248, OTH:1007-1025).
- *   - batched ticks are STATELESS: first tick after set_startpos (the reference's multi-tick memory is wall-clock
- *     dependent, OTH:353-378).
+ *   - ltpl_tick_batch plans the stateless FIRST tick after set_startpos; ltpl_next_* plan every later tick with the
+ *     iterative memory of the reference (OTH:64-87) held in caller-owned device buffers -- the wall clock the reference
+ *     reads (OTH:353-378) is an input (t_const).
  */
 #ifndef LTPL_B200_H
 #define LTPL_B200_H
@@ -27,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 10
+#define LTPL_ABI_VERSION 11
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -63,7 +64,8 @@ extern "C" {
                                            /*   planned per OTH:393-407), 2 its trajectory has <= 2 rows, 3 fewer than  */
                                            /*   2 memory nodes, 4 the start node is the placeholder, 5 the constant     */
                                            /*   segment exceeds p_max, 6 follow / straight cannot start at the planned  */
-                                           /*   velocity and no backup plan exists                                      */
+                                           /*   velocity and no backup plan exists, 7 the position estimate lies at the */
+                                           /*   last row of the last trajectory (np.argmin of an empty array, OTH:570)  */
 #define LTPL_SC_BRAKE_PREFIX     (1 << 3)  /* vel_plan > vel_max + 0.1: the reference path raises here (OTH:747-754,   */
                                            /* 830/919 column_stack length mismatch); reported instead of planned       */
 
@@ -203,9 +205,7 @@ typedef struct LtplBuffers {
     int32_t* exp_q;           /* [NSLOT*B] path id q of every exported trajectory row (compact export list)               */
     int32_t* traj_row;        /* [NSLOT][B] row of path q in `traj`, or -1                                                 */
     /* calc_vel_profile results                                                                                          */
-    double* vel_scratch;     /* [3][NSLOT*B][p_max] brake / follow / complete profiles (CVPF:152,263,297)               */
     double* s_vx_ax;          /* [3][NSLOT*B][p_max] planes s, vx, ax                                                    */
-    double* vel_t;            /* [5][p_max][NSLOT*B + 64] transposed (point-major) scratch of the tiled velocity kernel  */
     float* traj;              /* [NSLOT*B][n_export][7] s, x, y, psi, kappa, vx, ax (OTH:941, LTPL:401-406); COMPACT: only  */
                               /* the first queue_cnt[2] rows are filled (one per kept trajectory, row -> path via exp_q)   */
     int32_t* traj_len;        /* [NSLOT][B]                                                                              */
@@ -244,7 +244,7 @@ typedef struct LtplBuffers {
                                     /*     point (path-plane indices of THIS tick, OTH:586-598, 705-731), pref = #points    */
                                     /*     of vel_course; zero on first ticks                                               */
     double* vel_plan;               /* [B] planned velocity at the cut (OTH:572); the kernels read it through `vel`        */
-    double* course;                 /* [B][8] vel_course (OTH:574)                                                         */
+    double* course;                 /* [B][n_export] vel_course (OTH:574): at most the rows of an exported trajectory      */
     double* obj_dist;               /* [B] s_obj - s_start on the cut follow path (OTH:774-784)                            */
     int32_t* zone_s0;               /* [B] start layer of the tick in which the scenario's zone was processed (GLNT:43-77:  */
                                     /*     the unblock window is evaluated once), -1: not yet; needed for zones in stateful  */

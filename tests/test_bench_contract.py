@@ -16,7 +16,7 @@ def _run(args, timeout=600):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = _run(["--impl", "reference", "--steps", "2", "--warmup", "0", "--cpu-sample", "16"])
+    r = _run(["--impl", "reference", "--steps", "2", "--warmup", "0", "--cpu-per-worker", "2"])
     assert r.returncode == 0, r.stderr[-800:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, "stdout must carry exactly one line, got %d" % len(lines)
@@ -30,6 +30,7 @@ def test_reference_arm_prints_the_contract_line():
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["unit"] == "ticks/s" and "sample" in cb
+    assert cb["ticks_per_s_cpu_1core"] > 0 and cb["ticks_per_s_cpu_allcores"] == cb["value"]
     assert abs(cb["value"] - d["value"]) <= 1e-9 * d["value"] and d["value"] > 0
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0 and e["unit"] == "ticks/s"
@@ -51,7 +52,7 @@ def test_reference_arm_under_torchrun_prints_once():
     """the driver launches the reference arm like the product arm; rank 0 alone works and prints, the others exit 0."""
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533", BENCH, "--impl", "reference", "--gpus", "2",
-                        "--steps", "1", "--warmup", "0", "--cpu-sample", "16"], cwd=H.REPO, stdout=subprocess.PIPE,
+                        "--steps", "1", "--warmup", "0", "--cpu-per-worker", "2"], cwd=H.REPO, stdout=subprocess.PIPE,
                        stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-800:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip().startswith("{")]

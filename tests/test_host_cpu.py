@@ -93,11 +93,28 @@ ref = H.lattice_for("l216")
 from graphbasedlocaltrajectoryplanner_b200.lattice_blob import pack_lattice
 h2, blob2, cap2 = pack_lattice(ref)
 assert bytes(header) == bytes(h2) and cap == cap2 and np.array_equal(blob.numpy(), blob2)
-traj = torch.full((3, 4, 5, 7), float(rank), dtype=torch.float32)
-tl = torch.full((3, 4), rank, dtype=torch.int32)
-out = parallel.gather_action_sets(traj, tl, tl.clone())
-assert out[0].shape == (world, 3, 4, 5, 7) and all(float(out[0][r].mean()) == r for r in range(world))
+# gather of the LIVE rows only: rank r holds 2 + 3 r live rows of a compact export buffer with 9 rows
+rows = torch.full((9, 5, 7), float(rank), dtype=torch.float32)
+n_live = 2 + 3 * rank
+got, counts = parallel.gather_rows(rows, n_live, dst=0)
+assert counts == [2 + 3 * r for r in range(world)]
+if rank == 0:
+    assert got.shape == (sum(counts), 5, 7)
+    off = 0
+    for r in range(world):
+        assert float(got[off:off + counts[r]].min()) == r == float(got[off:off + counts[r]].max())
+        off += counts[r]
+else:
+    assert got is None
+# a rank without live rows takes part without sending
+got, counts = parallel.gather_rows(rows, 0 if rank == 1 else 4, dst=0)
+assert counts == [4, 0] and (rank != 0 or got.shape[0] == 4)
 assert parallel.shard_indices(10, rank, world).tolist() == list(range(rank, 10, world))
+# the shards of a seeded batch: scenario i on rank (i mod world), together exactly the batch
+from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios
+sc = make_scenarios(Track(H.TRACK_CSV), 11, seed=5)
+sh = sc.shard(rank, world)
+assert sh.size == len(range(rank, 11, world)) and np.array_equal(sh.pos, sc.pos[rank::world])
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -1,5 +1,5 @@
 """debug (GPU box): build library variants with extra -D flags and time the tick kernels.
-usage: python tools/gpu_tune.py l216 "-DLTPL_VEL_LANES=4" "-DLTPL_VEL_LANES=8" ..."""
+usage: python tools/gpu_tune.py l216 "-DVR_P=8" "-DVR_P=16" ..."""
 import os, subprocess, sys, json
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)

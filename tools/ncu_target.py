@@ -1,5 +1,5 @@
 """ncu target (GPU box): set_startpos + 3 ticks of the bench workload.
-ncu --set full --clock-control none --import-source on -k regex:'k_plan|k_path|k_vel_tiled|k_export' --launch-skip 8
+ncu --set full --clock-control none --import-source on -k regex:'k_plan|k_path|k_vel_res|k_export' --launch-skip 8
     --launch-count 4 -o gpurun_out/prof python tools/ncu_target.py l216"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
