@@ -113,6 +113,30 @@ def _cpu_work(args):
     return pos.shape[0], time.perf_counter() - t0
 
 
+def usable_cores():
+    """host cores this process may use: the scheduler affinity mask, capped by the cgroup CPU quota (a container often
+    sees every core of the box in os.cpu_count() but may only run on a few of them)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, int(quota / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 class CpuArm(object):
     """`cores` worker processes, one oracle each, one BLAS thread each (main_min_example.py:8; the variables are set in
     the parent BEFORE the workers are spawned -- a child imports NumPy before its initializer runs).  A run hands every
@@ -122,7 +146,7 @@ class CpuArm(object):
         import multiprocessing as mp
         get_lattice(tag)   # make sure the cache file exists
         self.tag = tag
-        self.cores = cores or os.cpu_count()
+        self.cores = cores or usable_cores()
         keep = {k: os.environ.get(k) for k in _ONE_THREAD}
         for k in _ONE_THREAD:
             os.environ[k] = "1"
@@ -156,14 +180,17 @@ class CpuArm(object):
         return dt, sum(r[1] for r in res)
 
     def measure(self, per_worker=160, runs=2):
-        """all-core ticks/s (median of `runs` passes over cores x per_worker scenarios of the seeded batch) and the
-        single-core ticks/s (one worker, per_worker scenarios; BASELINE.md section 2 asks for both)."""
+        """single-core ticks/s (one worker, per_worker scenarios) and all-core ticks/s (median of `runs` passes over
+        cores x per_worker scenarios of the seeded batch); BASELINE.md section 2 asks for both.  When the workers
+        share fewer physical cores than reported (in-worker time far above the single-core time) that is said."""
         sc = make_batch(self.tag, self.cores * per_worker)
-        t_all = sorted(self.run(sc)[0] for _ in range(runs))[(runs - 1) // 2]
         sc1 = sc.subset(np.arange(per_worker))
         t_one = self.run(sc1, workers=1)[0]
+        passes = sorted(self.run(sc) for _ in range(runs))
+        t_all, busy = passes[(runs - 1) // 2]
         return dict(all=sc.size / t_all, one=sc1.size / t_one, sample=sc.size, seconds_all=t_all, seconds_one=t_one,
-                    per_worker=per_worker, runs=runs)
+                    per_worker=per_worker, runs=runs, parallel_efficiency=(sc.size / t_all) / (self.cores * sc1.size / t_one),
+                    in_worker_slowdown=(busy / sc.size) / (t_one / sc1.size))
 
     def close(self):
         self.pool.close()
@@ -173,6 +200,8 @@ class CpuArm(object):
 def cpu_baseline_dict(arm, m):
     return {"value": m["all"], "unit": "ticks/s", "cores": arm.cores, "kind": "port",
             "ticks_per_s_cpu_allcores": m["all"], "ticks_per_s_cpu_1core": m["one"],
+            "os_cpu_count": os.cpu_count(), "parallel_efficiency": m.get("parallel_efficiency"),
+            "in_worker_slowdown_vs_1core": m.get("in_worker_slowdown"),
             "sample": "%d scenarios of the seeded workload (%d per worker process, %d processes, 1 BLAS thread each), "
                       "median of %d passes, %.2f s per pass; single core: %d scenarios in %.2f s" % (
                           m["sample"], m["per_worker"], arm.cores, m["runs"], m["seconds_all"], m["per_worker"],

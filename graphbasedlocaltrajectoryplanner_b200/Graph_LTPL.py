@@ -191,8 +191,26 @@ class Graph_LTPL(object):
         if self.__state not in ("paths", "paths_next"):
             raise ValueError("calc_paths() must be called before calc_vel_profile()")
         pl = self.__planner
+        gg_planes = None
+        if type(local_gg) is dict:   # location dependent friction: one (P, 2) array per path of this tick (OTH:649-666)
+            n_pts = pl.dims.p_max
+            gg_planes = np.ones((2, capi.NSLOT, 1, n_pts))
+            slot_of = {"straight": 0, "follow": 0, "left": 1, "right": 2}
+            for action, paths in self.__records["paths"].items():
+                if action not in local_gg:   # the reference indexes local_gg[action_id] for every action (OTH:708)
+                    raise KeyError(action)
+                arr = np.asarray(local_gg[action][0], dtype=np.float64)
+                if arr.ndim != 2 or arr.shape != (paths[0].shape[0], 2):
+                    raise ValueError("local_gg['%s'][0] must have the shape (%d, 2) of the action's path" % (
+                        action, paths[0].shape[0]))
+                gg_planes[:, slot_of[action], 0, :arr.shape[0]] = arr.T
+            local_gg = None
         pl.set_vel_params(vel_max=vel_max, gg_scale=gg_scale, local_gg=local_gg, ax_max_machines=ax_max_machines,
                           safety_d=safety_d, incl_emerg_traj=incl_emerg_traj)
+        if gg_planes is not None:
+            pl.set_local_gg_planes(gg_planes[0], gg_planes[1])
+        else:
+            pl.set_local_gg_planes(None)
         pos = np.asarray(pos_est, dtype=np.float64).reshape(2)
         if self.__state == "paths_next":
             pl.next_calc_vel_profile(pos_est=[pos], vel_est=[float(vel_est)])

@@ -26,30 +26,32 @@ static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, c
     const int nq = LTPL_NSLOT * dm->batch;
     const int nmax = dm->p_max;
     if (nmax > 32 * VR_MAXM || nmax % 4 != 0) return cudaErrorInvalidValue;
-    const size_t smem = vr_smem_bytes(nmax);
+    const bool gg = bf->gg != nullptr;   // location dependent local_gg: the general-exponent variant carries it
+    const size_t smem = vr_smem_bytes(nmax, gg);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     static thread_local size_t attr_set = 0;
     if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_vel_res<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_vel_res<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_vel_res<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_vel_res<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        const void* fns[6] = {(const void*)k_vel_res<false, true, false>, (const void*)k_vel_res<true, true, false>,
+                              (const void*)k_vel_res<false, false, false>, (const void*)k_vel_res<true, false, false>,
+                              (const void*)k_vel_res<false, false, true>, (const void*)k_vel_res<true, false, true>};
+        for (const void* f : fns)
+            if (cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) return e;
         attr_set = smem;
     }
     const int grid = nq / VR_P + 2;   // >= groups of the follow queue + groups of the other queue
-    const bool exp1 = prm->dyn_model_exp == 1.0;
-    if (stateful && exp1)
-        k_vel_res<true, true><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+    const bool exp1 = prm->dyn_model_exp == 1.0 && !gg;
+    if (gg && stateful)
+        k_vel_res<true, false, true><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+    else if (gg)
+        k_vel_res<false, false, true><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+    else if (stateful && exp1)
+        k_vel_res<true, true, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
     else if (stateful)
-        k_vel_res<true, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+        k_vel_res<true, false, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
     else if (exp1)
-        k_vel_res<false, true><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+        k_vel_res<false, true, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
     else
-        k_vel_res<false, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
+        k_vel_res<false, false, false><<<grid, VR_THREADS, smem, st>>>(lat->d, *prm, *dm, *bf, nmax);
     return cudaSuccess;
 }
 
@@ -69,6 +71,37 @@ static int check_launch(const char* name) {
         return -2;
     }
     return 0;
+}
+
+
+// k_plan<ZONE, STATE>: one warp per scenario (ltpl_plan.cuh)
+static const char* launch_k_plan(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                                 cudaStream_t st, bool stateful) {
+    const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
+    const int hl = dm->h_max;
+    const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
+    const size_t smem = plan_smem_bytes_per_warp(maxn, hl, mask_words) * LTPL_WARPS_PER_CTA;
+    if (smem > 200 * 1024) return "lattice window too large for shared memory";
+    static thread_local size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        if (cudaFuncSetAttribute(k_plan<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_plan<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_plan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(k_plan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return "cudaFuncSetAttribute(k_plan) failed";
+        attr = smem;
+    }
+    const int grid = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, thr = LTPL_WARPS_PER_CTA * 32;
+    const bool zone = dm->n_zones > 0;
+    if (zone && stateful)
+        k_plan<true, true><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    else if (zone)
+        k_plan<true, false><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    else if (stateful)
+        k_plan<false, true><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    else
+        k_plan<false, false><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    return nullptr;
 }
 
 extern "C" {
@@ -217,31 +250,16 @@ int ltpl_set_startpos_batch(const LtplLattice* lat, const LtplParams* prm, const
 
 static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                         cudaStream_t st) {
-    const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
-    const int hl = dm->h_max;
-    const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
-    const size_t smem_plan = plan_smem_bytes_per_warp(maxn, hl, mask_words) * LTPL_WARPS_PER_CTA;
     const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
-    if (smem_plan > 200 * 1024 || smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
-    static thread_local size_t attr_plan = 0, attr_path = 0;
-    if (smem_plan > 48 * 1024 && smem_plan > attr_plan) {
-        if (cudaFuncSetAttribute(k_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
-                cudaSuccess ||
-            cudaFuncSetAttribute(k_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) != cudaSuccess)
-            return fail("cudaFuncSetAttribute(k_plan) failed");
-        attr_plan = smem_plan;
-    }
+    if (smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
+    static thread_local size_t attr_path = 0;
     if (smem_path > 48 * 1024 && smem_path > attr_path) {
         if (cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
             return fail("cudaFuncSetAttribute(k_path) failed");
         attr_path = smem_path;
     }
     if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
-    const int grid_plan = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    if (dm->n_zones > 0)
-        k_plan<true><<<grid_plan, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
-    else
-        k_plan<false><<<grid_plan, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    if (const char* e = launch_k_plan(lat, prm, dm, bf, st, false)) return fail(e);
     if (int r = check_launch("k_plan")) return r;
     const int nq = LTPL_NSLOT * dm->batch;
     const int grid_path = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
@@ -309,18 +327,8 @@ int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, co
                                void* stream) {
     if (int r = check_stateful(lat, prm, dm, bf)) return r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
-    const int hl = dm->h_max;
-    const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
-    const size_t smem_plan = plan_smem_bytes_per_warp(maxn, hl, mask_words) * LTPL_WARPS_PER_CTA;
     const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
-    if (smem_plan > 200 * 1024 || smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
-    if (smem_plan > 48 * 1024 &&
-        (cudaFuncSetAttribute(k_plan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
-             cudaSuccess ||
-         cudaFuncSetAttribute(k_plan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan) !=
-             cudaSuccess))
-        return fail("cudaFuncSetAttribute(k_plan) failed");
+    if (smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
     if (smem_path > 48 * 1024 &&
         cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
         return fail("cudaFuncSetAttribute(k_path) failed");
@@ -329,10 +337,7 @@ int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, co
     const int grid_q = (LTPL_NSLOT * dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
     k_state<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
     if (int r = check_launch("k_state")) return r;
-    if (dm->n_zones > 0)
-        k_plan<true, true><<<grid_b, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
-    else
-        k_plan<false, true><<<grid_b, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    if (const char* e = launch_k_plan(lat, prm, dm, bf, st, true)) return fail(e);
     if (int r = check_launch("k_plan")) return r;
     k_path<true><<<grid_q, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
     return check_launch("k_path");
@@ -384,25 +389,10 @@ int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, 
     switch (stage) {
         case 0: return ltpl_set_startpos_batch(lat, prm, dm, bf, stream);
         case 1:
+            if (const char* e = launch_k_plan(lat, prm, dm, bf, st, false)) return fail(e);
+            return check_launch("k_plan");
         case 2: {
-            const int maxn = ((lat->h.max_nodes_per_layer + 31) / 32) * 32;
-            const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
-            const size_t smem_plan = plan_smem_bytes_per_warp(maxn, dm->h_max, mask_words) * LTPL_WARPS_PER_CTA;
             const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
-            if (stage == 1) {
-                if (smem_plan > 48 * 1024) {
-                    cudaFuncSetAttribute(k_plan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
-                    cudaFuncSetAttribute(k_plan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_plan);
-                }
-                const int grid = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-                if (dm->n_zones > 0)
-                    k_plan<true><<<grid, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn,
-                                                                                   dm->h_max, mask_words);
-                else
-                    k_plan<false><<<grid, LTPL_WARPS_PER_CTA * 32, smem_plan, st>>>(lat->d, *prm, *dm, *bf, maxn,
-                                                                                    dm->h_max, mask_words);
-                return check_launch("k_plan");
-            }
             if (smem_path > 48 * 1024)
                 cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path);
             if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess)

@@ -60,6 +60,8 @@ k_emergency(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     if (lane == 0) {
         const double dmq = LTPL_EM_DRAG / LTPL_EM_MASS;
         const double inv_ay = 1.0 / prm.gg_ay;
+        // location dependent local_gg: the rows of the base trajectory, cut at its start (action_set_path_param_gg, OTH:1030)
+        const double* ggr = bf.gg ? bf.gg + (size_t)q * dm.p_max + cut : nullptr;
         double v0 = vx_row[0];
         if (v0 < 0.0) v0 = 0.0;
         double w = v0 * v0;
@@ -68,7 +70,8 @@ k_emergency(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
         #pragma unroll 1
         for (int i = 0; i + 1 < m; ++i) {
             if (!stopped) {
-                const double a = acc_brake(w, sk[i], prm.gg_ax, inv_ay, 1.0, dmq);
+                const double a = ggr ? acc_brake(w, sk[i], ggr[i], 1.0 / ggr[pplane + i], 1.0, dmq)
+                                     : acc_brake(w, sk[i], prm.gg_ax, inv_ay, 1.0, dmq);
                 const double nx = fma(2.0 * a, ss[i + 1] - ss[i], w);
                 if (nx < 0.0) {   // tph.calc_vel_profile_brake: negative radicand -> the rest of the profile stays 0
                     stopped = true;

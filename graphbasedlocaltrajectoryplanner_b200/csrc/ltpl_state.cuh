@@ -427,6 +427,8 @@ k_backup(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
         double* VX = S + pplane;
         double* AX = VX + pplane;
         const double dmq = prm.drag_coeff / prm.m_veh, inv_ay = 1.0 / prm.gg_ay;
+        // location dependent local_gg of the LAST tick along the backup path (__backup_path_gg, OTH:970-975), raw
+        const double* ggr = bf.prev_gg ? bf.prev_gg + (size_t)q * dm.p_max + m_b + cut + pref : nullptr;
         double v0 = bf.vel[b];                                  // == vel_plan (the host points `vel` at it)
         if (v0 < 0.0) v0 = 0.0;
         double w = v0 * v0, s = 0.0;
@@ -437,7 +439,8 @@ k_backup(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
             double wn = 0.0;
             if (i + 1 < n_p) {
                 if (!stopped) {
-                    const double a = acc_brake(w, fabs(K[i]), prm.gg_ax, inv_ay, prm.dyn_model_exp, dmq);
+                    const double a = ggr ? acc_brake(w, fabs(K[i]), ggr[i], 1.0 / ggr[pplane + i], prm.dyn_model_exp, dmq)
+                                         : acc_brake(w, fabs(K[i]), prm.gg_ax, inv_ay, prm.dyn_model_exp, dmq);
                     const double nx = fma(2.0 * a, E[i], w);
                     if (nx < 0.0)
                         stopped = true;

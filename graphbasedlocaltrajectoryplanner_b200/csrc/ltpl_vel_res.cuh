@@ -28,7 +28,11 @@
 #define VR_THREADS 64
 #define VR_MAXM 16                   // points per lane in the arc-length scan: nmax <= 32 * VR_MAXM = 512
 
-__host__ __device__ inline size_t vr_smem_bytes(int nmax) { return (size_t)VR_P * 5 * nmax * sizeof(float); }
+// per path and point: E2, W, K', SRC, S (+ AX, IAY: longitudinal tyre limit and 1 / lateral limit per point when a location
+// dependent local_gg is given)
+__host__ __device__ inline size_t vr_smem_bytes(int nmax, bool gg) {
+    return (size_t)VR_P * (gg ? 7 : 5) * nmax * sizeof(float);
+}
 
 // ---- TMA bulk copy + mbarrier (PTX) ---------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned vr_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -119,10 +123,11 @@ __device__ __noinline__ float vr_tire_pow(float ratio, float ax_max, float e, fl
     return (rad > 0.0f) ? ax_max * powf(rad, inv_e) : 0.0f;
 }
 // available longitudinal tyre acceleration at w = v^2 with K = |kappa| / ay_max (tph.calc_ax_poss)
+// ax: ax_max of the point (location dependent local_gg, OTH:649-666) or the constant c.ax_max
 template <bool EXP1>
-__device__ __forceinline__ float vr_tire(const VRCfg& c, float w, float K) {
-    if (EXP1) return c.ax_max * fmaxf(fmaf(-w, K, 1.0f), 0.0f);
-    return vr_tire_pow(w * K, c.ax_max, c.exp_, c.inv_exp);
+__device__ __forceinline__ float vr_tire(const VRCfg& c, float w, float K, float ax) {
+    if (EXP1) return ax * fmaxf(fmaf(-w, K, 1.0f), 0.0f);
+    return vr_tire_pow(w * K, ax, c.exp_, c.inv_exp);
 }
 
 // Forward sweep of one lane's profile on points [lo, hi] of its path (K, E2, W: the path's shared-memory rows).
@@ -133,10 +138,11 @@ __device__ __forceinline__ float vr_tire(const VRCfg& c, float w, float K) {
 // limit is a table segment cached in registers; v moves slowly, and when a lane leaves its segment the WHOLE warp takes
 // one step to the neighbouring segment (warp-uniform branch: a miss never serialises lanes).
 // BRAKE: the warp also carries brake lanes (follow, warp 0); without them the step has no brake selects at all.
-template <bool EXP1, bool BRAKE>
+// GG: per-point longitudinal tyre limit AX[] (location dependent local_gg), else the constant c.ax_max
+template <bool EXP1, bool BRAKE, bool GG>
 __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane, const float* __restrict__ K,
-                                        const float* __restrict__ E2, float* __restrict__ W, int lo, int hi, float wcap,
-                                        float we, float wmax, int nmax) {
+                                        const float* __restrict__ E2, const float* __restrict__ AX, float* __restrict__ W,
+                                        int lo, int hi, float wcap, float we, float wmax, int nmax) {
     const bool brake = BRAKE && brake_lane;
     const int len = (on && hi >= lo) ? hi - lo : -1;
     int lmax = len;
@@ -144,7 +150,7 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
     for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(LTPL_FULL, lmax, o));
     if (lmax < 0) return;
     if (len < 0) lo = 0;
-    float k_prev = K[lo];
+    float k_prev = K[lo], ax_prev = GG ? AX[lo] : c.ax_max;
     float cur = brake ? wcap : fminf(fminf(vr_rcp(k_prev), wmax), wcap);
     if (len >= 0) W[lo] = cur;
     float o_prev = cur;
@@ -174,7 +180,7 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
             sl = c.sl[sg];
             miss = need && !(v >= xlo && v < xhi);
         }
-        const float a_t = vr_tire<EXP1>(c, cur, k_prev);
+        const float a_t = vr_tire<EXP1>(c, cur, k_prev, ax_prev);
         const float a_m = fmaf(sl, v - x0, f0);                              // mode 'accel_forw': min(tyre, machine(v))
         const float a_sel = brake ? -a_t : fminf(a_t, a_m);
         const float wn = fmaf(fmaf(-cur, c.dm, a_sel), e2, cur);             // + drag
@@ -186,27 +192,37 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
         prev_rise = rise;
         o_prev = o_n;
         k_prev = kq;
+        if (GG) ax_prev = AX[p];
     }
     if (len >= 0 && we >= 0.0f && W[hi] > we) W[hi] = we;
 }
 // Backward sweep (flipped arrays, mode 'decel_backw', one look-ahead correction); returns w[lo] afterwards.
-template <bool EXP1>
+// GG (location dependent local_gg): tph flips radii, el_lengths and the profile for this sweep but NOT the per-point ggv
+// (oracle/tph_port.py:463-538: p_ggv[i] is indexed with the flipped counter), so the point p of the profile [lo, hi] takes
+// the tyre limits of its mirror point lo + hi - p -- reproduced here: K'(p) = |kappa(p)| / ay(mirror), ax(mirror).
+template <bool EXP1, bool GG>
 __device__ __noinline__ float vr_backward(const VRCfg c, bool on, const float* __restrict__ K,
-                                          const float* __restrict__ E2, float* __restrict__ W, int lo, int hi,
+                                          const float* __restrict__ E2, const float* __restrict__ AX,
+                                          const float* __restrict__ IAY, float* __restrict__ W, int lo, int hi,
                                           float wmax) {
     float cur = 0.0f;
     if (on && hi >= lo) {
         cur = W[hi];
-        float o_prev = cur, k_p = K[hi];
+        const int mir = lo + hi;
+        float o_prev = cur;
+        float k_p = GG ? K[hi] * vr_rcp(IAY[hi]) * IAY[mir - hi] : K[hi];
+        float ax_p = GG ? AX[mir - hi] : c.ax_max;
         bool prev_rise = false, active = false;
 #pragma unroll 2
         for (int p = hi - 1; p >= lo; --p) {
-            const float o_n = W[p], kq = K[p], e2 = E2[p];
+            const float o_n = W[p], e2 = E2[p];
+            const float kq = GG ? K[p] * vr_rcp(IAY[p]) * IAY[mir - p] : K[p];
+            const float axq = GG ? AX[mir - p] : c.ax_max;
             const bool rise = o_n > o_prev;
             active = active || (rise && !prev_rise);
-            const float a = fmaf(cur, c.dm, vr_tire<EXP1>(c, cur, k_p));
+            const float a = fmaf(cur, c.dm, vr_tire<EXP1>(c, cur, k_p, ax_p));
             float wn = fmaf(a, e2, cur);
-            const float a2 = fmaf(wn, c.dm, vr_tire<EXP1>(c, wn, kq));
+            const float a2 = fmaf(wn, c.dm, vr_tire<EXP1>(c, wn, kq, axq));
             const float wt = fmaf(a2, e2, cur);
             wn = fminf(wn, wt);
             const float nxt = active ? fminf(wn, o_n) : o_n;
@@ -216,6 +232,7 @@ __device__ __noinline__ float vr_backward(const VRCfg c, bool on, const float* _
             prev_rise = rise;
             o_prev = o_n;
             k_p = kq;
+            ax_p = axq;
         }
     }
     return cur;
@@ -277,14 +294,23 @@ __device__ __forceinline__ double vr_s_coord_from_nb(const double* x, const doub
 
 // kappa row (float64, staged at X2 | X3 with `sh` leading junk elements) -> K' (fp32) in place at X2: batches of 32
 // points in ascending order; a batch's writes only cover sources of earlier batches
-__device__ __forceinline__ void vr_convert_kappa(float* X2, int n, int sh, double inv_ay, int lane) {
+// gg_row: the path's rows of the local_gg planes (ax at gg_row, ay at gg_row + gg_plane; NULL: constant local_gg): K' uses
+// the lateral limit of its point, AX gets the longitudinal one (both times gg_scale, VPFB:213-214)
+__device__ __forceinline__ void vr_convert_kappa(float* X2, float* AX, float* IAY, int n, int sh, double inv_ay,
+                                                 const double* gg_row, size_t gg_plane, double gg_scale, int lane) {
     const double* src = reinterpret_cast<const double*>(X2) + sh;
 #pragma unroll 1
     for (int p0 = 0; p0 < n; p0 += 32) {
         const int p = p0 + lane;
         const double k = (p < n) ? src[p] : 0.0;
+        double iay = inv_ay;
+        if (gg_row && p < n) {
+            iay = 1.0 / (gg_row[gg_plane + p] * gg_scale);
+            AX[p] = (float)(gg_row[p] * gg_scale);
+            IAY[p] = (float)iay;
+        }
         __syncwarp();
-        if (p < n) X2[p] = (float)(fabs(k) * inv_ay);
+        if (p < n) X2[p] = (float)(fabs(k) * iay);
     }
     __syncwarp();
 }
@@ -338,7 +364,8 @@ __device__ __forceinline__ void vr_convert_el(float* X0, float* X4, double* s_ou
 // Every device function with a long body has ONE call site (the sweeps are out of line on top): the rounds of the three
 // warp roles (other class | follow warp 0 | follow warp 1) share one loop, so the kernel stays small in the instruction
 // cache although six different profiles pass through it.
-template <bool STATE, bool EXP1>
+// GG: location dependent local_gg (buffers.gg, OTH:649-666): one more row per path (AX)
+template <bool STATE, bool EXP1, bool GG>
 __global__ void __launch_bounds__(VR_THREADS, 7)
 k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf, const int nmax) {
     extern __shared__ __align__(16) unsigned char vr_smem[];
@@ -406,7 +433,7 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     const bool any_red = s_any_red != 0;
 
     // ---- one round of TMA bulk copies: el row -> X0 | X1, kappa row -> X2 | X3 of every path --------------------------
-    const size_t rowf = (size_t)5 * nmax;   // floats per path block
+    const size_t rowf = (size_t)(GG ? 7 : 5) * nmax;   // floats per path block
     float* blk = reinterpret_cast<float*>(vr_smem);
     if (tid == 0) {
         unsigned total = 0;
@@ -443,6 +470,8 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     const float* Kp = X + 2 * (size_t)nmax;
     float* SRC = X + 3 * (size_t)nmax;
     const float* S32 = X + 4 * (size_t)nmax;
+    const float* AXp = X + 5 * (size_t)nmax;   // only with GG
+    const float* IAYp = X + 6 * (size_t)nmax;  // only with GG
     const double* sg = s_pl + s_out[pl];
     const double vel_plan = mine ? bf.vel[b] : 0.0;
     const double vs_f = fmax(vel_plan, 0.0);
@@ -498,7 +527,9 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
         const int nr = s_n[r];
         if (nr <= 0) continue;
         float* Xr = blk + rowf * r;
-        if (!fw0) vr_convert_kappa(Xr + 2 * (size_t)nmax, nr, s_sh[r], inv_ay, lane);
+        if (!fw0)
+            vr_convert_kappa(Xr + 2 * (size_t)nmax, Xr + 5 * (size_t)nmax, Xr + 6 * (size_t)nmax, nr, s_sh[r], inv_ay,
+                             GG ? bf.gg + s_in[r] : nullptr, pplane, prm.gg_scale, lane);
         if (!fw1) vr_convert_el(Xr, Xr + 4 * (size_t)nmax, s_pl + s_out[r], nr, s_sh[r], lane);
     }
     LTPL_PH(1)
@@ -717,13 +748,13 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
         }
 
         if (fw0 && round == 0) {
-            vr_forward<EXP1, true>(c, on, brake, Kp, E2, W, lo, hi, wcap, we, wmx, nmax);
+            vr_forward<EXP1, true, GG>(c, on, brake, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
             LTPL_PH(3)
             vr_bar_arrive(2);
         } else {
-            vr_forward<EXP1, false>(c, on, false, Kp, E2, W, lo, hi, wcap, we, wmx, nmax);
+            vr_forward<EXP1, false, GG>(c, on, false, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
         }
-        const float w_first = vr_backward<EXP1>(c, on && !brake, Kp, E2, W, lo, hi, wmx);
+        const float w_first = vr_backward<EXP1, GG>(c, on && !brake, Kp, E2, AXp, IAYp, W, lo, hi, wmx);
 
         if (!follow_cls || (fw0 && round == 1)) {
             if (on) {

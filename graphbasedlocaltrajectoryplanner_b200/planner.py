@@ -113,7 +113,9 @@ class BatchPlanner(object):
                        ax_max_machines=np.atleast_2d([100.0, 5.0]), safety_d: float = 30.0,
                        incl_emerg_traj: bool = False) -> None:
         """per-call arguments of Graph_LTPL.calc_vel_profile (LTPL:344-352)."""
-        if type(local_gg) is not tuple or len(local_gg) != 2:   # OTH:651-653 (location dependent dicts: not batched)
+        if local_gg is None:        # location dependent friction: the planes of set_local_gg_planes() are used
+            local_gg = (1.0, 1.0)
+        if type(local_gg) is not tuple or len(local_gg) != 2:   # OTH:651-653 (dict form: Graph_LTPL / set_local_gg_planes)
             raise ValueError("Provided local_gg does not satisfy requested format! Read parameter documentation.")
         axm = np.atleast_2d(np.asarray(ax_max_machines, dtype=np.float64))
         if axm.shape[1] != 2:
@@ -262,6 +264,29 @@ class BatchPlanner(object):
         self._row_bytes = NE * 7 * 4
         if self._stateful:
             self._alloc_state()   # incl. zone_s0, which the FIRST tick has to fill
+
+    def set_local_gg_planes(self, ax=None, ay=None) -> None:
+        """location dependent friction (calc_vel_profile(local_gg={action: [ndarray(P, 2)]}), OTH:649-666) for the batch:
+        ``ax``, ``ay`` [NSLOT][B][P] (P <= p_max) = longitudinal / lateral limit at every point of every path (slot 0:
+        straight | follow, 1: left, 2: right), aligned with the paths of the last calc_paths; None: back to the constant
+        tuple of set_vel_params().  The values are taken without gg_scale (VPFB:213-214 applies it)."""
+        if ax is None:
+            self.buf.gg = None
+            self._gg_active = False
+            return
+        ax = np.asarray(ax, dtype=np.float64)
+        ay = np.asarray(ay, dtype=np.float64)
+        B, P = self.dims.batch, self.dims.p_max
+        if ax.shape != ay.shape or ax.ndim != 3 or ax.shape[:2] != (NSLOT, B) or ax.shape[2] > P:
+            raise ValueError("local_gg planes must have the shape [NSLOT][B][P <= p_max]")
+        if "gg" not in self.t:
+            self.t["gg"] = torch.ones((2, NSLOT * B, P), dtype=torch.float64, device=self.device)
+        host = np.ones((2, NSLOT * B, P))
+        host[0, :, :ax.shape[2]] = ax.reshape(NSLOT * B, -1)
+        host[1, :, :ay.shape[2]] = ay.reshape(NSLOT * B, -1)
+        self.t["gg"].copy_(torch.from_numpy(host))
+        self.buf.gg = self.t["gg"].data_ptr()
+        self._gg_active = True
 
     def device_bytes(self) -> int:
         return int(sum(v.numel() * v.element_size() for v in self.t.values()) + self.blob.numel())
@@ -521,6 +546,16 @@ class BatchPlanner(object):
             setattr(buf, "prev_" + k, st["other"][k].data_ptr())
         for k in self._SMALL:
             setattr(buf, "prev_" + k, st["prev_small"][k].data_ptr())
+        # location dependent local_gg of the last tick = backup for a brake on the old plan (__backup_path_gg, OTH:970)
+        if getattr(self, "_gg_active", False):
+            if "gg" not in st["other"]:
+                st["other"]["gg"] = torch.ones_like(t["gg"])
+            t["gg"], st["other"]["gg"] = st["other"]["gg"], t["gg"]
+            buf.prev_gg = st["other"]["gg"].data_ptr()
+        else:
+            buf.prev_gg = None
+        buf.gg = None            # this tick's local_gg arrives with its calc_vel_profile
+        self._gg_active = False
         # a zone under a NEW id is a new zone object: its unblock window is evaluated at this tick (OLI:155-237, GLNT:43-77)
         zkey = sc.zone_key if sc.zone_key is not None else np.zeros(sc.size, dtype=np.int64)
         last = getattr(self, "_zone_key", None)               # of the batch staged for the previous tick

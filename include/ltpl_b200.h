@@ -254,6 +254,10 @@ typedef struct LtplBuffers {
     double* em_vx;                  /* [B][n_export] f64 velocity of this tick's emergency trajectory (k_emergency)        */
     const double* prev_em_vx;       /* [B][n_export] the previous tick's                                                   */
     const int32_t* prev_em_info;    /* [B][3] the previous tick's em_info (all -1 when it had no emergency trajectory)     */
+    /* location dependent friction: calc_vel_profile(local_gg={action: [ndarray(P, 2)]}) (OTH:649-666, VPFB:194-227).     */
+    /* NULL: the constant params.gg_ax / gg_ay of the tuple form.  Rows are aligned with the path planes.                 */
+    const double* gg;               /* [2][NSLOT*B][p_max] planes ax_max, ay_max per path point (without gg_scale)         */
+    const double* prev_gg;          /* the previous tick's `gg` (brake on the backup plan, OTH:970-975); NULL: constant     */
 } LtplBuffers;
 
 /* stand-alone forward/backward ggv velocity profile over dense path arrays (BASELINE.json config 5).                   */

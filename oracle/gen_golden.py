@@ -98,8 +98,9 @@ def ax_max_machines_table():
     return np.vstack((tab, [100.0, tab[-1, 1]]))
 
 
-def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False, blocked_zones=None, vel_est=None):
-    """one stateless planning tick through the reference's public API (main_min_example.py:69-104 flow)."""
+def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False, blocked_zones=None, vel_est=None, gg_fn=None):
+    """one stateless planning tick through the reference's public API (main_min_example.py:69-104 flow).
+    gg_fn: location dependent friction -- local_gg = {action: [gg_fn(path[:, 0:2])]} (OTH:649-666)."""
     name = '_Graph_LTPL__nmbr_export_points'
     keep = getattr(ltpl, name)
     if full:
@@ -124,6 +125,8 @@ def run_tick(ltpl, pos, heading, vel, object_list, vel_kwargs, full=False, block
         rec['red_len'] = {k: list(v) for k, v in oth._OnlineTrajectoryHandler__last_action_set_red_len.items()}
         rec['closest_obj_index'] = oth._OnlineTrajectoryHandler__closest_obj_index
         rec['start_node'] = list(oth._OnlineTrajectoryHandler__start_node)
+        if gg_fn is not None:
+            vel_kwargs = dict(vel_kwargs, local_gg={k: [gg_fn(v[0][:, 0:2])] for k, v in path_dict.items()})
         traj, ids, _ = ltpl.calc_vel_profile(pos_est=np.array(pos), vel_est=float(vel if vel_est is None else vel_est),
                                              **vel_kwargs)
         rec['traj'] = {k: [np.array(a) for a in v] for k, v in traj.items()}
@@ -292,7 +295,8 @@ def advance_on_traj(traj, dt):
 
 
 def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=None, seed=31337, gg_drop=None,
-                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None, s_max=None, hmax=40, s_min=0.0):
+                      em_select=None, bad_select=None, n_obj=(0, 2), zone_swap=None, s_max=None, hmax=40, s_min=0.0,
+                      gg_fn=None):
     """closed-loop sequences through the unmodified reference with a scripted clock: per tick the inputs (clock step,
     selected action, object list, position / velocity estimate) and the outputs (node sequences, trajectories, ids).
     em_select=(k0, k1): the odd sequences execute the 'emergency' trajectory of ticks k0 .. k1 (OTH:307-309; code 4).
@@ -376,6 +380,8 @@ def multitick_fixture(graph_ltpl, ltpl, track, n_seq, n_ticks, vel_kwargs, lat=N
                 if gg_drop is not None and q % 2 == 1 and k >= gg_drop[0]:
                     vk['gg_scale'] = gg_drop[1]       # grip drops: profiles can no longer start at the planned velocity
                 out['gg_scale'][q, k] = vk.get('gg_scale', 1.0)
+                if gg_fn is not None:                 # location dependent friction along this tick's paths (OTH:649-666)
+                    vk['local_gg'] = {a: [gg_fn(p[0][:, 0:2])] for a, p in paths.items()}
                 traj_set, ids, _ = ltpl.calc_vel_profile(pos_est=pos_est, vel_est=vel_est, **vk)
                 for a, act in enumerate(ACTIONS):
                     if act in traj_set and len(traj_set[act]):
@@ -485,6 +491,7 @@ def main():
     ap.add_argument('--n-open', type=int, default=64)
     ap.add_argument('--variants-only', action='store_true', help='only the parameter-variant fixture')
     ap.add_argument('--n-variant', type=int, default=24)
+    ap.add_argument('--ggpp-only', action='store_true', help='only the location dependent local_gg fixtures')
     args = ap.parse_args()
 
     graph_ltpl = load_reference()
@@ -494,6 +501,36 @@ def main():
     vel_kwargs = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=ax_max_machines_table(),
                       safety_d=30.0, incl_emerg_traj=False)
 
+    if args.ggpp_only:
+        # location dependent friction: local_gg = {action: [ndarray(P, 2)]} (OTH:649-666, VPFB:194-227), emergency
+        # trajectory on (its brake profile takes the raw local_gg of the base trajectory, OTH:1030); closed loop with a grip
+        # drop on the odd sequences (the brake on the backup plan takes the LAST tick's local_gg, OTH:970-975)
+        sys.path.insert(0, REPO)
+        from tests.helpers import local_gg_field
+        ltpl, _ = make_ltpl(graph_ltpl, "default", {})
+        vk = dict(vel_kwargs, incl_emerg_traj=True)
+        sc = make_scenarios(track, 32, seed=2468, n_obj_min=0, n_obj_max=3)
+        recs = [run_tick(ltpl, sc.pos[b], sc.heading[b], sc.vel[b], sc.object_list(b), vk, full=True, gg_fn=local_gg_field)
+                for b in range(sc.size)]
+        pk = pack_ticks(recs)
+        n, pmax = sc.size, pk['path'].shape[2]
+        em, em_len, em_id = np.zeros((n, pmax, 7)), np.zeros(n, dtype=np.int32), np.full(n, -1, dtype=np.int32)
+        for i, r in enumerate(recs):
+            if 'traj' in r and 'emergency' in r['traj']:
+                t = r['traj']['emergency'][0]
+                em[i, :t.shape[0]] = t
+                em_len[i] = t.shape[0]
+                em_id[i] = r['ids']['emergency']
+        payload = {('full_' + k): v for k, v in pk.items()}
+        payload.update(em_traj=em, em_len=em_len, em_id=em_id, sc_pos=sc.pos, sc_heading=sc.heading, sc_vel=sc.vel, sc_n_obj=sc.n_obj,
+                       sc_obj=sc.obj, ax_max_machines=vel_kwargs['ax_max_machines'], overrides=np.array(repr([])))
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_ggpp_default.npz'), **payload)
+        print("[ggpp] action paths %s; emergency %d" % (
+            {a: int((pk['path_len'][:, i] > 0).sum()) for i, a in enumerate(ACTIONS)}, int((em_len > 0).sum())))
+        np.savez_compressed(os.path.join(GOLDEN, 'ticks_multitick_ggpp_default.npz'),
+                            **multitick_fixture(graph_ltpl, ltpl, track, 12, 8, vk, seed=1357, gg_drop=(3, 0.45),
+                                                n_obj=(0, 3), gg_fn=local_gg_field))
+        return
     if args.open_only or args.mt_open_only or not (args.quick or args.variants_only or args.ext_only or args.only or args.pred_only
                               or args.multitick_only or args.emsel_only or args.invalid_only or args.mt_l216_only
                               or args.zswap_only or args.mt_l430_only or args.mt_variant_only):

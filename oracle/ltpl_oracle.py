@@ -790,7 +790,7 @@ class OracleLTPL(object):
         # get_ref_idx, never planned before (OTH:590-599)
         vel_plan = st['v_start']
         vel_course = np.array([])
-        if type(local_gg) is not tuple or len(local_gg) != 2:
+        if type(local_gg) is not dict and (type(local_gg) is not tuple or len(local_gg) != 2):   # OTH:649-653
             raise ValueError("Provided local_gg does not satisfy requested format! Read parameter documentation.")
         traj_base_id = 10                                      # OTH:669
         closest_obj_index = res['closest_obj_index']
@@ -798,9 +798,14 @@ class OracleLTPL(object):
         out_traj = {}
         out_ids = {}
         vel_bound_flags = {}
+        gg_used = {}
         for action_id in list(res['path_param'].keys()):
             pp = res['path_param'][action_id][0]
-            gg = np.ones((pp.shape[0], 2)) * tuple(local_gg)  # OTH:665-666
+            if type(local_gg) is dict:                         # location dependent friction, aligned with the path
+                gg = np.asarray(local_gg[action_id][0], dtype=np.float64)
+            else:
+                gg = np.ones((pp.shape[0], 2)) * tuple(local_gg)  # OTH:665-666
+            gg_used[action_id] = gg
             out_ids[action_id] = traj_base_id + ACTION_ID_MAP.get(action_id, 9)
             red_len = res['red_len'][action_id][0]
             bp_out, vel_bound = self.vel_one(action_id, pp, gg, res['nodes'][action_id][0][-1], red_len, vel_plan,
@@ -816,7 +821,7 @@ class OracleLTPL(object):
             traj = out_traj[em_base][0]
             el = np.diff(traj[:, 0])
             v_brake = tph.calc_vel_profile_brake(kappa=traj[:, 4], el_lengths=el, v_start=traj[0, 5], drag_coeff=0.854,
-                                                 m_veh=1160.0, loc_gg=np.ones((traj.shape[0], 2)) * tuple(local_gg))
+                                                 m_veh=1160.0, loc_gg=gg_used[em_base][:traj.shape[0]])   # OTH:1030
             idx_em = len(v_brake)
             a_brake = tph.calc_ax_profile(vx_profile=v_brake, el_lengths=el[:idx_em], eq_length_output=True)
             out_traj['emergency'] = [np.column_stack((traj[:idx_em, 0:5], v_brake, a_brake))]
@@ -829,7 +834,8 @@ class OracleLTPL(object):
     # ----------------------------------------------------------------------------------------------------------------------
     # one stateless tick = set_startpos -> calc_paths -> calc_vel_profile  (main_min_example.py:69-104)
     # ----------------------------------------------------------------------------------------------------------------------
-    def tick(self, pos, heading, vel, object_list, vel_kwargs=None, blocked_zones=None, vel_est=None):
+    def tick(self, pos, heading, vel, object_list, vel_kwargs=None, blocked_zones=None, vel_est=None, gg_fn=None):
+        """gg_fn: location dependent friction, local_gg = {action: [gg_fn(path[:, 0:2])]} (OTH:649-666)."""
         vel_kwargs = dict(vel_kwargs or {})
         self.old_gg_scale = None
         st = self.set_startpos(np.asarray(pos, dtype=np.float64), float(heading), float(vel))
@@ -837,6 +843,8 @@ class OracleLTPL(object):
             return dict(out_of_track=True)
         obj_veh = self.process_object_list(object_list)
         res = self.calc_paths(st, obj_veh, blocked_zones)
+        if gg_fn is not None:
+            vel_kwargs['local_gg'] = {k: [gg_fn(v[0][:, 0:2])] for k, v in res['path_param'].items()}
         vp = self.calc_vel_profile(st, res, obj_veh, np.asarray(pos, dtype=np.float64),
                                    float(vel if vel_est is None else vel_est), **vel_kwargs)
         return dict(out_of_track=False, start_node=st['start_node'], paths=res['path_param'], nodes=res['nodes'],

@@ -239,7 +239,7 @@ class OracleSession(object):
         orc = self.orc
         pos_est = np.asarray(pos_est, dtype=np.float64)
         cut_index_pos, cut_layer, vel_plan, vel_course = self.get_ref_idx(self.prev_action_id, 0, pos_est)
-        if type(local_gg) is not tuple or len(local_gg) != 2:
+        if type(local_gg) is not dict and (type(local_gg) is not tuple or len(local_gg) != 2):   # OTH:649-653
             raise ValueError("Provided local_gg does not satisfy requested format! Read parameter documentation.")
         vk = dict(vel_max=vel_max, gg_scale=gg_scale, ax_max_machines=np.asarray(ax_max_machines, dtype=np.float64))
         self.traj_base_id += 10
@@ -254,7 +254,10 @@ class OracleSession(object):
             self.m_gg[action_id] = []
             ids[action_id] = self.traj_base_id + ACTION_ID_MAP.get(action_id, 9)
             full = self.m_path[action_id][0]
-            gg_full = np.ones((full.shape[0], 2)) * tuple(local_gg)
+            if type(local_gg) is dict:                     # location dependent friction, aligned with the path (OTH:708)
+                gg_full = np.asarray(local_gg[action_id][0], dtype=np.float64)
+            else:
+                gg_full = np.ones((full.shape[0], 2)) * tuple(local_gg)
             pp = full[cut_index_pos:, :]                       # OTH:700-706
             gg = gg_full[cut_index_pos:, :]
             gg_vel[action_id] = gg

@@ -130,6 +130,22 @@ def compare_records(got, want, ctx=""):
                      ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
 
 
+def local_gg_field(xy):
+    """location dependent friction of the per-point local_gg fixtures: (ax_max, ay_max) as a smooth function of the
+    position, one row per path point -- calc_vel_profile(local_gg={action: [local_gg_field(path[:, 0:2])]}) (OTH:649-666)."""
+    xy = np.asarray(xy, dtype=np.float64)
+    return np.column_stack((4.2 + 1.1 * np.sin(0.011 * xy[:, 0] + 0.5), 4.6 + 0.9 * np.cos(0.013 * xy[:, 1] - 0.3)))
+
+
+def local_gg_planes(pl):
+    """[NSLOT][B][p_max] planes (ax, ay) of local_gg_field along the paths a BatchPlanner just planned (calc_paths)."""
+    f = pl.fetch("path")
+    path = f["path"]                                   # [5][NSLOT * B][p_max]
+    gg = local_gg_field(np.column_stack((path[0].ravel(), path[1].ravel())))
+    shape = (path.shape[1] // pl.dims.batch, pl.dims.batch, path.shape[2])
+    return gg[:, 0].reshape(shape), gg[:, 1].reshape(shape)
+
+
 def zone_of(g, b, tick=0):
     """blocked_zones dict of scenario b of the zone / emergency fixture (None: no zone); fixtures with a zone swap pass
     another zone under a new id from tick `zone_swap_tick` on."""

@@ -43,7 +43,9 @@ class _Rows(object):
                                                      ("ticks_multitick_invalid_default.npz", False, None, "default"),
                                                      ("ticks_multitick_openend.npz", False, None, "open"),
                                                      ("ticks_multitick_pdtan_default.npz", False, None,
-                                                      "default:pdtan_exp15")])
+                                                      "default:pdtan_exp15"),
+                                                     ("ticks_multitick_ggpp_default.npz", True, 0, "default:ggpp"),
+                                                     ("ticks_multitick_ggpp_default.npz", True, 1, "default:ggpp")])
 def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
     """second fixture: a blocked zone on every second sequence + the emergency trajectory in every tick; third fixture:
     the grip (gg_scale) drops on the odd sequences from tick 3 on -> brake on the backup plan (OTH:950-1006); fourth
@@ -58,6 +60,9 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
     n_done = g["n_done"]                                   # open track: sequences end when no trajectory is left
     tag, _, variant = tag.partition(":")
     pl_kw, vel = {}, dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), safety_d=30.0)
+    ggpp = variant == "ggpp"   # location dependent local_gg = H.local_gg_field along every path (OTH:649-666), grip drop
+    if ggpp:
+        variant = ""
     if variant:                                            # other controller / vehicle / velocity parameters (H.VARIANTS)
         online, veh, vel_v, _ = H.VARIANTS[variant]
         pl_kw = dict(online=online, **veh)
@@ -80,7 +85,16 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
             pl.stage_scenarios(sc, vel_est=g["vel_est"][:, k])
             pl.upload()
             pl.set_startpos()
-            pl.tick()
+            if ggpp:
+                pl.calc_paths()
+                pl.set_local_gg_planes(*H.local_gg_planes(pl))
+                pl.calc_vel_profile()
+            else:
+                pl.tick()
+        elif ggpp:
+            pl.next_calc_paths(sc, sel_action=g["sel"][:, k], t_const=tc[:, k - 1])
+            pl.set_local_gg_planes(*H.local_gg_planes(pl))
+            pl.next_calc_vel_profile(vel_est=g["vel_est"][:, k])
         else:
             pl.next_tick(sc, sel_action=g["sel"][:, k], t_const=tc[:, k - 1], vel_est=g["vel_est"][:, k])
         recs = pl.records()

@@ -209,3 +209,61 @@ def test_explicit_predictions_match_reference_golden_and_oracle():
     for b in range(0, sc3.size, 4):
         want = orc.tick(sc3.pos[b], sc3.heading[b], sc3.vel[b], sc3.object_list(b), vel)
         H.compare_records(recs3[b], want, ctx="no-pred after pred %d" % b)
+
+
+def test_location_dependent_local_gg_matches_reference_golden():
+    """calc_vel_profile(local_gg={action: [ndarray(P, 2)]}) (OTH:649-666, VPFB:194-227) against the reference: friction
+    as a function of the position along every path (buffers.gg planes, k_vel_res<.., GG>), emergency trajectory on
+    (raw local_gg of its base trajectory, OTH:1030); batch API and the facade's dict form."""
+    from graphbasedlocaltrajectoryplanner_b200.Graph_LTPL import Graph_LTPL
+    from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch
+    g = H.golden("ticks_ggpp_default.npz")
+    sc = ScenarioBatch(g["sc_pos"], g["sc_heading"], g["sc_vel"], g["sc_n_obj"], g["sc_obj"])
+    pl = BatchPlanner(H.lattice_for("default"), device="cuda:0")
+    pl.set_vel_params(vel_max=100.0, gg_scale=1.0, local_gg=None, ax_max_machines=g["ax_max_machines"], safety_d=30.0,
+                      incl_emerg_traj=True)
+    pl.stage_scenarios(sc)
+    pl.upload()
+    pl.set_startpos()
+    pl.calc_paths()
+    pl.set_local_gg_planes(*H.local_gg_planes(pl))
+    pl.calc_vel_profile()
+    recs = pl.records()
+    n_em = 0
+    for b in range(sc.size):
+        H.compare_record(recs[b], g, b, ctx="ggpp")
+        n = min(int(g["em_len"][b]), 115)
+        assert ("emergency" in recs[b].get("traj", {})) == (n > 0), "scenario %d emergency presence" % b
+        if n:
+            H.assert_close("traj[emergency]", recs[b]["traj"]["emergency"][0], g["em_traj"][b, :n],
+                           ("s", "x", "y", "psi", "kappa", "vx", "ax"), "ggpp scenario %d" % b)
+            n_em += 1
+    assert n_em >= sc.size // 2
+    # the facade takes the reference's dict form
+    pd = {'globtraj_input_path': H.TRACK_CSV, 'graph_store_path': "/tmp/_lat_default_test.npz",
+          'ltpl_offline_param_path': H.OFFLINE_INI, 'ltpl_online_param_path': H.ONLINE_INI}
+    ltpl = Graph_LTPL(path_dict=pd, visual_mode=False, log_to_file=False, device="cuda:0")
+    ltpl.graph_init()
+    done = 0
+    for b in range(sc.size):
+        if bool(g["full_out_of_track"][b]) or done >= 6:
+            continue
+        assert ltpl.set_startpos(pos_est=sc.pos[b], heading_est=sc.heading[b], vel_est=sc.vel[b]) is False
+        paths = ltpl.calc_paths(prev_action_id="straight", object_list=sc.object_list(b))
+        gg = {a: [H.local_gg_field(p[0][:, 0:2])] for a, p in paths.items()}
+        traj, ids, _ = ltpl.calc_vel_profile(pos_est=sc.pos[b], vel_est=float(sc.vel[b]), local_gg=gg,
+                                             ax_max_machines=g["ax_max_machines"])
+        for a, act in enumerate(H.ACTIONS):
+            t_want = int(g["full_traj_len"][b, a])
+            assert (act in traj) == (t_want > 0), "facade scenario %d %s" % (b, act)
+            if t_want:
+                H.assert_close("traj[%s]" % act, traj[act][0], g["full_traj"][b, a, :min(t_want, 115)],
+                               ("s", "x", "y", "psi", "kappa", "vx", "ax"), "facade ggpp scenario %d" % b)
+        with pytest.raises(ValueError):   # an array that does not match its path
+            bad = {a: [v[0][:-1]] for a, v in gg.items()}
+            ltpl.set_startpos(pos_est=sc.pos[b], heading_est=sc.heading[b], vel_est=sc.vel[b])
+            ltpl.calc_paths(prev_action_id="straight", object_list=sc.object_list(b))
+            ltpl.calc_vel_profile(pos_est=sc.pos[b], vel_est=float(sc.vel[b]), local_gg=bad)
+        done += 1
+    assert done >= 4

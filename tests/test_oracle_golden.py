@@ -80,3 +80,19 @@ def test_oracle_explicit_predictions():
     for b in range(g["sc_pos"].shape[0]):
         rec = orc.tick(g["sc_pos"][b], g["sc_heading"][b], g["sc_vel"][b], H.object_list(g, b), vk)
         H.compare_record(rec, g, b, prefix="", ctx="pred")
+
+
+def test_oracle_location_dependent_local_gg():
+    """calc_vel_profile(local_gg={action: [ndarray(P, 2)]}) (OTH:649-666, VPFB:194-227): friction as a function of the
+    position along every path, emergency trajectory on (raw local_gg of its base trajectory, OTH:1030)."""
+    from oracle.ltpl_oracle import OracleLTPL
+    g = H.golden("ticks_ggpp_default.npz")
+    orc = OracleLTPL(H.lattice_for("default"))
+    vk = dict(vel_max=100.0, gg_scale=1.0, ax_max_machines=g["ax_max_machines"], safety_d=30.0, incl_emerg_traj=True)
+    n = g["sc_pos"].shape[0]
+    assert int((g["em_len"] > 0).sum()) >= n // 2 and int((g["full_traj_len"][:, 1] > 0).sum()) >= 4
+    for b in range(n):
+        rec = orc.tick(g["sc_pos"][b], g["sc_heading"][b], g["sc_vel"][b], H.object_list(g, b), vk,
+                       gg_fn=H.local_gg_field)
+        H.compare_record(rec, g, b, ctx="ggpp")
+        H.compare_emergency(rec, g, b, ctx="ggpp")

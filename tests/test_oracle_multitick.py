@@ -27,7 +27,8 @@ import pytest
                                                ("ticks_multitick_open.npz", False, "open"),
                                                ("ticks_multitick_openend.npz", False, "open"),
                                                ("ticks_multitick_l430.npz", False, "l430"),
-                                               ("ticks_multitick_pdtan_default.npz", False, "default:pdtan_exp15")])
+                                               ("ticks_multitick_pdtan_default.npz", False, "default:pdtan_exp15"),
+                                               ("ticks_multitick_ggpp_default.npz", True, "default:ggpp")])
 def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
     """second fixture: a blocked zone on every second sequence (processed once, GLNT:43-99) + emergency trajectory; third:
     grip drop -> brake on the backup plan; fourth: the odd sequences execute the 'emergency' trajectory for three ticks; fifth: the odd sequences name an action
@@ -44,6 +45,10 @@ def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
     vk = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0,
               incl_emerg_traj=emerg)
     orc_kw = {}
+    ggpp = variant == "ggpp"                                # location dependent local_gg (+ grip drop, emergency trajectory)
+    if ggpp:
+        variant = ""
+        vk.pop("local_gg")
     if variant:                                            # other controller / vehicle / velocity parameters (H.VARIANTS)
         online, veh, vel, _ = H.VARIANTS[variant]
         orc_kw = dict(online=online, **veh)
@@ -72,8 +77,10 @@ def test_session_oracle_matches_reference_sequences(fixture, emerg, tag):
                     assert paths[act][0].shape[0] == n_want, ctx + " path length " + act
                     nd = [[-1 if v is None else int(v) for v in p] for p in ses.m_nodes[act][0]]
                     assert nd == g["nodes"][q, k, a, :int(g["nodes_len"][q, k, a])].tolist(), ctx + " nodes " + act
-            traj, ids = ses.calc_vel_profile(g["pos_est"][q, k], float(g["vel_est"][q, k]),
-                                             **dict(vk, gg_scale=float(g["gg_scale"][q, k])))   # third fixture: grip drop
+            kw = dict(vk, gg_scale=float(g["gg_scale"][q, k]))   # third fixture: grip drop
+            if ggpp:
+                kw["local_gg"] = {a: [H.local_gg_field(p[0][:, 0:2])] for a, p in paths.items()}
+            traj, ids = ses.calc_vel_profile(g["pos_est"][q, k], float(g["vel_est"][q, k]), **kw)
             for a, act in enumerate(H.ACTIONS):
                 t_want = int(g["traj_len"][q, k, a])
                 assert (act in traj) == (t_want > 0), "%s: trajectory %s present=%s, golden %d" % (ctx, act, act in traj,
