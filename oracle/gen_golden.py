@@ -29,11 +29,12 @@ GOLDEN = os.path.join(REPO, 'tests', 'golden')
 ACTIONS = ("straight", "follow", "left", "right")
 
 
-def load_reference():
-    """import the reference package on top of the shims; returns the `graph_ltpl` module."""
+def load_reference(use_shims=True):
+    """import the reference package on top of the shims (use_shims=False: on REAL python-igraph /
+    trajectory_planning_helpers installs, tests/test_against_reference.py); returns the `graph_ltpl` module."""
     if not os.path.isdir(REF):
         raise RuntimeError("/root/reference is not available on this box")
-    for p in (REPO, os.path.join(REPO, 'oracle', 'shims'), REF):
+    for p in ((REPO, os.path.join(REPO, 'oracle', 'shims'), REF) if use_shims else (REPO, REF)):
         if p not in sys.path:
             sys.path.insert(0, p)
     if not hasattr(np, 'object'):

@@ -139,12 +139,13 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
     assert compared > (30 if (group is not None or n_seq < 12) else (80 if (emerg or n_seq < 16) else 150))
 
 
-@pytest.mark.parametrize("tag,n_seq,omin,omax", [("default", 96, 0, 2), ("l216", 64, 1, 3)])
+@pytest.mark.parametrize("tag,n_seq,omin,omax", [("default", 96, 0, 2), ("l216", 64, 1, 3), ("open", 48, 0, 2)])
 def test_closed_loop_matches_session_oracle(tag, n_seq, omin, omax):
     """larger closed loop driven by the DEVICE results (vehicle dummy on the selected trajectory, moving opponents,
     changing action preference); the stateful oracle (oracle/ltpl_session.py, pinned against the reference) replays the
     same inputs tick by tick.  Sequences the device flags (memory not usable, capacity) leave the loop -- at most 5 %.
-    Second case: BASELINE's ~200 x 11 lattice, whose node lists exceed 32 entries."""
+    Second case: BASELINE's ~200 x 11 lattice, whose node lists exceed 32 entries.  Third case: the OPEN track, seeded
+    over its whole length -- the vehicles near the end plan reduced horizons, shrinking trajectories and stop."""
     from graphbasedlocaltrajectoryplanner_b200 import capi
     from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
     from graphbasedlocaltrajectoryplanner_b200.scenarios import ScenarioBatch, Track, make_scenarios
@@ -155,7 +156,9 @@ def test_closed_loop_matches_session_oracle(tag, n_seq, omin, omax):
     lat = H.lattice_for(tag)
     n_ticks = 8
     vel = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"], safety_d=30.0)
-    sc0 = make_scenarios(Track(H.track_csv_for(tag)), n_seq, seed=2718, n_obj_min=omin, n_obj_max=omax)
+    trk = Track(H.track_csv_for(tag))
+    sc0 = make_scenarios(trk, n_seq, seed=2718, n_obj_min=omin, n_obj_max=omax,
+                         s_max=(trk.length - 10.0) if tag == "open" else None)
     rng = np.random.default_rng(2719)
     prefer = (("right", "left", "straight", "follow"), ("follow", "straight", "left", "right"),
               ("left", "right", "follow", "straight"), ("straight", "follow", "right", "left"))
