@@ -420,7 +420,10 @@ int ltpl_velprofile_batch(const LtplParams* prm, const LtplVelBatch* vb, void* s
     if (prm->n_axm < 1 || prm->n_axm > LTPL_MAX_AXM) return fail("params.n_axm out of range");
     if (prm->axm_v[prm->n_axm - 1] < prm->vel_max)
         return fail("ax_max_machines has to cover the entire velocity range of the car (i.e. >= v_max)!");
-    k_velprofile_tiled<<<(vb->n_paths + 31) / 32, 32, VD_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
+    if (prm->dyn_model_exp == 1.0)
+        k_velprofile<true><<<(vb->n_paths + 31) / 32, 32, VD_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
+    else
+        k_velprofile<false><<<(vb->n_paths + 31) / 32, 32, VD_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(*prm, *vb);
     return check_launch("k_velprofile");
 }
 
