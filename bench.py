@@ -5,7 +5,7 @@ bench.py -- planning ticks/s of the batched online planning path (BASELINE.json 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                     (CPU arm: oracle port on all host cores)
 
-A "step" = one planning tick (calc_paths + calc_vel_profile, 4 kernels) over one batch of 10 000 synthetic scenarios
+A "step" = one planning tick (calc_paths + calc_vel_profile, 3 kernels) over one batch of 10 000 synthetic scenarios
 (SURVEY 8(d) config 2: Monteblanco lattice with lat_resolution=1.0, lon_straight_step=12.0 -> 216 layers x 7..12 nodes;
 random ego arc length + 1..3 dynamic obstacles, seed 20260924).  set_startpos is setup.
   value : device-timed (CUDA events on the launching stream), inputs resident in HBM, L2 flushed between steps
@@ -270,14 +270,14 @@ def algorithmic_bytes(lat, stats):
     plan = plan_io + discs * s_l * (16 + 4) + ah * (1 + 4)          # one shared sweep per object, table row per step
     plan_ref = plan_io + discs * 2 * s_l * (16 + 4) + ah * e_l * (8 + 4 + 0.125) + ah * n_l * 1
     path = pts * (5 * 8 + 8) + ah * (8 * 8 + 16 + 8 + 8 + 4) + acts * stats["p0_mean"] * 5 * 8 * 2
-    vel = pts * (2 * 8 + 3 * 8) + pts_follow * (2 * 8)             # kappa, el in; s, vx, ax out; x, y in (follow)
-    vel_fp32 = pts * (2 * 4 + 3 * 4) + pts_follow * (2 * 4)        # SURVEY 8(d) element sizes
-    export = stats["export_rows"] * (7 * 8 + 7 * 4)
+    # kappa, el in; s, vx, ax out; x, y in (follow); exported rows (first ticks: fused): x, y, psi, kappa in, 7 fp32 out
+    vel = pts * (2 * 8 + 3 * 8) + pts_follow * (2 * 8) + stats["export_rows"] * (4 * 8 + 7 * 4)
+    vel_fp32 = pts * (2 * 4 + 3 * 4) + pts_follow * (2 * 4) + stats["export_rows"] * (4 * 4 + 7 * 4)   # SURVEY 8(d) sizes
     # SURVEY 8(d) B_tick (fp32 / int32 element sizes, lattice gathers included), with the batch's own H, K, A, P
     s_e = lat.num_samples / max(1, lat.num_edges)
     b_tick = discs * 2 * e_l * s_e * 8 + ah * e_l * (4 + 4 + 0.125) + ah * n_l * 4 + pts * 20 \
         + (pts * 28 + (ah + acts) * 8 + ah * 32) + discs * 12 + B * 64
-    return dict(k_plan=plan, k_path=path, k_vel=vel, k_export=export, k_plan_as_reference=plan_ref,
+    return dict(k_plan=plan, k_path=path, k_vel=vel, k_plan_as_reference=plan_ref,
                 k_vel_fp32_sizes=vel_fp32, tick_survey_8d=b_tick)
 
 
@@ -465,7 +465,7 @@ def main():
             ("capacity", capi.SC_CAPACITY), ("brake_prefix", capi.SC_BRAKE_PREFIX))}
         return st, bad
 
-    stage_names = {1: "k_plan", 2: "k_path", 3: "k_vel", 4: "k_export"}
+    stage_names = {1: "k_plan", 2: "k_path", 3: "k_vel"}   # first tick: the export is fused into k_vel (k_vel_res)
 
     def kernel_times(plx, steps):
         """per-kernel device time (each kernel launched alone through ltpl_launch_stage, same buffers, L2 flushed)"""

@@ -272,10 +272,7 @@ static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplD
     const int nq = LTPL_NSLOT * dm->batch;
     if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
     if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
-    if (int r = check_launch("k_vel")) return r;
-    k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
-        *dm, *bf);
-    if (int r = check_launch("k_export")) return r;
+    if (int r = check_launch("k_vel")) return r;   // first ticks: the export of the kept rows is fused into k_vel_res
     if (prm->incl_emerg_traj) {
         if (!bf->em_info) return fail("params.incl_emerg_traj needs buffers.em_info");
         const size_t smem = emerg_smem_bytes_per_warp(dm->n_export) * LTPL_WARPS_PER_CTA;

@@ -371,7 +371,7 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     extern __shared__ __align__(16) unsigned char vr_smem[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ float s_tab[4 * VR_TAB];
-    __shared__ int s_q[VR_P], s_n[VR_P], s_sh[VR_P], s_nb1[VR_P], s_nb2[VR_P], s_use_src[VR_P], s_any_red;
+    __shared__ int s_q[VR_P], s_n[VR_P], s_sh[VR_P], s_nb1[VR_P], s_nb2[VR_P], s_use_src[VR_P], s_row[VR_P], s_any_red;
     __shared__ long long s_in[VR_P], s_out[VR_P];
     __shared__ float s_wf0[VR_P];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -420,6 +420,7 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
         s_out[tid] = (long long)max(q, 0) * dm.p_max + pref;
         s_sh[tid] = (int)(ib & 1);   // bulk copies start at an even element (16-byte source alignment)
         s_use_src[tid] = 0;
+        s_row[tid] = -1;
         s_wf0[tid] = 0.0f;
         if (follow_cls && n > 0 && (bf.status[q] & LTPL_ST_REDUCED_HORIZON)) s_any_red = 1;
     }
@@ -792,34 +793,8 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
         }
     }
 
-    // ---- element-wise end: min(src, complete) (CVPF:297-310), vx = sqrt(w), ax = (w1 - w0) / (2 ds), standstill fix-up
-    //      (OTH:926-941); follow: all 64 threads over all paths, other class: every warp over its own paths ----
-    {
-        const int t0 = follow_cls ? tid : lane, tstep = follow_cls ? VR_THREADS : 32;
-        for (int r = follow_cls ? 0 : warp; r < VR_P; r += (follow_cls ? 1 : 2)) {
-            const int nr = s_n[r];
-            if (nr <= 0) continue;
-            const float* Er = blk + rowf * r;
-            const float* Wr = Er + nmax;
-            const float* Sr = Er + 3 * (size_t)nmax;
-            // 0: min(SRC, W) (follow), 1: W (other class; follow after the merge of round 1), 2: SRC (q1 took the second)
-            const int mode = !follow_cls ? 1 : (any_red ? (s_use_src[r] ? 2 : 1) : 0);
-            for (int p = t0; p < nr; p += tstep) {
-                const float w0 = (mode == 0) ? fminf(Sr[p], Wr[p]) : ((mode == 1) ? Wr[p] : Sr[p]);
-                float a = 0.0f;
-                if (p < nr - 1) {
-                    const float w1 = (mode == 0) ? fminf(Sr[p + 1], Wr[p + 1]) : ((mode == 1) ? Wr[p + 1] : Sr[p + 1]);
-                    a = (w1 - w0) * vr_rcp(Er[p]);
-                    if (w0 <= 1e-16f && fabsf(a) <= 1e-8f) a = -5.0f;
-                }
-                vx_pl[s_out[r] + p] = (double)vr_sqrt(w0);
-                ax_pl[s_out[r] + p] = (double)a;
-            }
-        }
-    }
-    LTPL_PH(13)
-
-    // ---- acceptance (OTH:943-1025; no backup plan exists on the first tick) ----
+    // ---- acceptance (OTH:943-1025; no backup plan exists on the first tick); the compact export row of a kept trajectory
+    //      is taken here so that the element-wise end can write it ----
     if (mine && !fw0) {
         if (follow_cls && red) vel_bound = fabs(sqrt((double)s_wf0[pl]) - vel_plan) < prm.v_max_offset;
         if (!vel_bound) st |= LTPL_ST_VEL_BOUND_VIOL;
@@ -835,7 +810,80 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
             const int e = atomicAdd(&bf.queue_cnt[2], 1);
             bf.exp_q[e] = q;
             bf.traj_row[q] = e;
+            s_row[pl] = e;
         }
         bf.status[q] = st;
     }
+    if (follow_cls)
+        __syncthreads();
+    else
+        __syncwarp();
+
+    // ---- element-wise end: min(src, complete) (CVPF:297-310), vx = sqrt(w), ax = (w1 - w0) / (2 ds), standstill fix-up
+    //      (OTH:926-941); follow: all 64 threads over all paths, other class: every warp over its own paths.
+    //      First ticks also write the exported rows (s, x, y, psi, kappa, vx, ax as fp32, cut to nmbr_export_points:
+    //      OTH:941 + LTPL:401-406) of the kept trajectories here -- no separate export kernel, s / vx / ax go out from
+    //      shared memory; stateful ticks export behind k_prefix (vel_course rows in front, ltpl_state.cuh) ----
+    {
+        const int t0 = follow_cls ? tid : lane, tstep = follow_cls ? VR_THREADS : 32;
+        for (int r = follow_cls ? 0 : warp; r < VR_P; r += (follow_cls ? 1 : 2)) {
+            const int nr = s_n[r];
+            if (nr <= 0) continue;
+            const float* Er = blk + rowf * r;
+            const float* Wr = Er + nmax;
+            const float* Sr = Er + 3 * (size_t)nmax;
+            const float* S32r = Er + 4 * (size_t)nmax;
+            // 0: min(SRC, W) (follow), 1: W (other class; follow after the merge of round 1), 2: SRC (q1 took the second)
+            const int mode = !follow_cls ? 1 : (any_red ? (s_use_src[r] ? 2 : 1) : 0);
+            for (int p = t0; p < nr; p += tstep) {
+                const float w0 = (mode == 0) ? fminf(Sr[p], Wr[p]) : ((mode == 1) ? Wr[p] : Sr[p]);
+                float a = 0.0f;
+                if (p < nr - 1) {
+                    const float w1 = (mode == 0) ? fminf(Sr[p + 1], Wr[p + 1]) : ((mode == 1) ? Wr[p + 1] : Sr[p + 1]);
+                    a = (w1 - w0) * vr_rcp(Er[p]);
+                    if (w0 <= 1e-16f && fabsf(a) <= 1e-8f) a = -5.0f;
+                }
+                vx_pl[s_out[r] + p] = (double)vr_sqrt(w0);
+                ax_pl[s_out[r] + p] = (double)a;
+            }
+            // exported rows: four points of a thread in flight (16 independent loads), then their 28 stores
+            const int er = STATE ? -1 : s_row[r];
+            const int ne = (er >= 0) ? min(nr, dm.n_export) : 0;
+            float* __restrict__ out = bf.traj + (size_t)max(er, 0) * dm.n_export * 7;
+            const double* __restrict__ ppr = bf.path + s_in[r];
+#pragma unroll 1
+            for (int p0 = t0; p0 < ne; p0 += 4 * tstep) {
+                double g[4][4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int p = min(p0 + u * tstep, ne - 1);
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) g[u][cc] = ppr[cc * pplane + p];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int p = p0 + u * tstep;
+                    if (p < ne) {
+                        const float w0 = (mode == 0) ? fminf(Sr[p], Wr[p]) : ((mode == 1) ? Wr[p] : Sr[p]);
+                        float a = 0.0f;
+                        if (p < nr - 1) {
+                            const float w1 = (mode == 0) ? fminf(Sr[p + 1], Wr[p + 1])
+                                                         : ((mode == 1) ? Wr[p + 1] : Sr[p + 1]);
+                            a = (w1 - w0) * vr_rcp(Er[p]);
+                            if (w0 <= 1e-16f && fabsf(a) <= 1e-8f) a = -5.0f;
+                        }
+                        float* o = out + (size_t)p * 7;
+                        o[0] = S32r[p];
+                        o[1] = (float)g[u][0];
+                        o[2] = (float)g[u][1];
+                        o[3] = (float)g[u][2];
+                        o[4] = (float)g[u][3];
+                        o[5] = vr_sqrt(w0);
+                        o[6] = a;
+                    }
+                }
+            }
+        }
+    }
+    LTPL_PH(13)
 }

@@ -24,7 +24,7 @@ if len(sys.argv) > 2 and sys.argv[1] == "--child":
         return tot / steps
     for _ in range(3): pl.tick()
     res = {"tick_ms": timed(pl.tick)}
-    for stage, name in {1: "k_plan", 2: "k_path", 3: "k_vel", 4: "k_export"}.items():
+    for stage, name in {1: "k_plan", 2: "k_path", 3: "k_vel"}.items():
         def one(stage=stage):
             capi.check(pl.lib, pl.lib.ltpl_launch_stage(stage, pl.handle, C.byref(pl.params), C.byref(pl.dims), C.byref(pl.buf), pl.stream), name)
         one(); res[name] = timed(one)
