@@ -83,6 +83,19 @@ __device__ __forceinline__ double dist2_rn(double ax, double ay, double bx, doub
     return __dadd_rn(sq_rn(__dsub_rn(ax, bx)), sq_rn(__dsub_rn(ay, by)));
 }
 
+// 1 / sqrt(q) and 1 / x for VALUES (never for decisions): fp32 seed + two Newton steps in float64 (~2e-16 relative)
+// instead of the emulated float64 rsqrt / division (~30-40 instructions each).  q, x > 0 and inside the fp32 range.
+__device__ __forceinline__ double fast_rsqrt(double q) {
+    double r = (double)rsqrtf((float)q);
+    r = r * (1.5 - 0.5 * q * r * r);
+    return r * (1.5 - 0.5 * q * r * r);
+}
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r = (double)__frcp_rn((float)x);
+    r = r * (2.0 - x * r);
+    return r * (2.0 - x * r);
+}
+
 // get_s_coord.py:102-121
 __device__ __forceinline__ double angle3pt(double ax, double ay, double bx, double by, double cx, double cy) {
     double ang = atan2(cy - by, cx - bx) - atan2(ay - by, ax - bx);
@@ -115,7 +128,8 @@ __device__ __forceinline__ AngCmp angle_cmp(double2 pn, double px, double py, do
     const double un = ux * ux + uy * uy, n1 = v1x * v1x + v1y * v1y, n2 = v2x * v2x + v2y * v2y;
     AngCmp r;
     if (un > 0.0 && n1 > 0.0 && n2 > 0.0) {
-        const double c1 = (ux * v1x + uy * v1y) * rsqrt(n1), c2 = (ux * v2x + uy * v2y) * rsqrt(n2);
+        // (the cosines only have to be good to ~1e-12: the margin below is 1e-9)
+        const double c1 = (ux * v1x + uy * v1y) * fast_rsqrt(n1), c2 = (ux * v2x + uy * v2y) * fast_rsqrt(n2);
         const double d = c1 - c2;
         if (d * d > 1e-18 * un) {
             r.gt = r.ge = (c1 < c2);

@@ -139,10 +139,13 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     // rows k = 1 .. nseg-1:  (2/el[k-1]) m[k-1] + 4 (1/el[k-1] + 1/el[k]) m[k] + (2/el[k]) m[k+1] = r[k]
     // The rows themselves (lo, r_x, r_y; di and up follow from lo) do not depend on the elimination: all lanes build
     // them in parallel, so that the serial Thomas sweep on lanes 0 / 1 is left with one reciprocal per row.
-    const double m0x = cos(psi_s + LTPL_PI / 2), m0y = sin(psi_s + LTPL_PI / 2);
-    const double mex = cos(psi_e + LTPL_PI / 2), mey = sin(psi_e + LTPL_PI / 2);
+    // tangents (cos, sin)(psi + pi / 2) = (-sin psi, cos psi): one sincos per heading
+    double sn_s, cs_s, sn_e, cs_e;
+    sincos(psi_s, &sn_s, &cs_s);
+    sincos(psi_e, &sn_e, &cs_e);
+    const double m0x = -sn_s, m0y = cs_s, mex = -sn_e, mey = cs_e;
     for (int k = 1 + lane; k < nseg; k += 32) {
-        const double i0 = 1.0 / kel[k - 1], i1 = 1.0 / kel[k];
+        const double i0 = fast_rcp(kel[k - 1]), i1 = fast_rcp(kel[k]);
         const double lo = 2.0 * i0, up = 2.0 * i1;
         double rx = 6.0 * ((kx[k] - kx[k - 1]) * (i0 * i0) + (kx[k + 1] - kx[k]) * (i1 * i1));
         double ry = 6.0 * ((ky[k] - ky[k - 1]) * (i0 * i0) + (ky[k + 1] - ky[k]) * (i1 * i1));
@@ -173,9 +176,9 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         double cprev = 0.0, dprev = 0.0;
         double lo = cp[1];
         for (int k = 1; k < nseg; ++k) {
-            const double up = (k + 1 < nseg) ? cp[k + 1] : 2.0 / kel[k];
+            const double up = (k + 1 < nseg) ? cp[k + 1] : 2.0 * fast_rcp(kel[k]);
             const double di = 2.0 * (lo + up);
-            const double inv = 1.0 / ((k == 1) ? di : (di - lo * cprev));
+            const double inv = fast_rcp((k == 1) ? di : (di - lo * cprev));
             const double cc = (k == nseg - 1) ? 0.0 : up * inv;
             const double dd = ((k == 1) ? dp[k] : (dp[k] - lo * dprev)) * inv;
             __syncwarp(0x3);
@@ -244,7 +247,7 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             x = ((a0x + a1x) + a2x) + a3x;
             y = ((a0y + a1y) + a2y) + a3y;
         } else {
-            t = k * (1.0 / (double)(n_i - 1));  // np.linspace(0, 1, n_i)[k]
+            t = k * fast_rcp((double)(n_i - 1));  // np.linspace(0, 1, n_i)[k] (2e-16 relative)
             x = cubic_rn(a0x, a1x, a2x, a3x, t);
             y = cubic_rn(a0y, a1y, a2y, a3y, t);
         }

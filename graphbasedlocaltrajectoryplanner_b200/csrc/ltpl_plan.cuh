@@ -27,11 +27,14 @@ __device__ __forceinline__ void head_curv(double ax1, double ax2, double ax3, do
     double ydd = 2 * ay2 + 6 * ay3 * t;
     // tph.normalize_psi(atan2(y', x') - pi/2): the argument lies in [-3 pi / 2, pi / 2], where the modulo of the
     // reference is the identity and only the "< -pi -> + 2 pi" branch can fire
+    // (the heading stays a float64 atan2: it becomes the boundary condition of the next spline, whose coefficients are
+    // compared at 1e-6; q^-1.5 comes from a Newton-refined reciprocal square root instead of a float64 sqrt and division)
     double h = atan2(yd, xd) - LTPL_PI / 2;
     if (h < -LTPL_PI) h += 2 * LTPL_PI;
     *psi = h;
-    double q = xd * xd + yd * yd;
-    *kappa = (xd * ydd - yd * xdd) / (q * sqrt(q));
+    const double q = xd * xd + yd * yd;
+    const double r = fast_rsqrt(q);
+    *kappa = (xd * ydd - yd * xdd) * (r * r * r);
 }
 
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
