@@ -25,7 +25,8 @@ for r in rows[2:]:
     for k in KEYS:
         if k in hdr:
             out.append("   %-82s %18s %s" % (k, r[hdr.index(k)], units[hdr.index(k)]))
-    rd, wr = float(r[hdr.index('dram__bytes_read.sum')]), float(r[hdr.index('dram__bytes_write.sum')])
-    out.append("   %-82s %18.3f %s" % ("traffic = dram read + write", rd + wr, units[hdr.index('dram__bytes_read.sum')]))
+    mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = sum(float(r[hdr.index(c)]) * mul[units[hdr.index(c)]] for c in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+    out.append("   %-82s %18.3f %s" % ("traffic = dram read + write", tot / 1e6, "Mbyte"))
 open(sys.argv[2], 'w').write("\n".join(out) + "\n")
 print("\n".join(out))
