@@ -44,6 +44,45 @@ REQ_PATH_DICT_ENTRIES = ['globtraj_input_path', 'graph_store_path', 'ltpl_offlin
                          'graph_log_id', 'log_path']
 
 
+class ActionSetView(object):
+    """Lazy sequence over the scenarios of a batched result (Graph_LTPL.unpack_batch): ``view[b]`` ->
+    ({action: [ndarray(rows, 7)]}, {action: trajectory id}) exactly as the reference's calc_vel_profile returns them
+    (LTPL:344-408), incl. the 'emergency' entry when it was requested."""
+
+    def __init__(self, out: dict):
+        self._rows, self._lens, self._ids, self._acts = (out[k].numpy() for k in ("traj_row", "traj_len", "traj_id",
+                                                                                  "action_id"))
+        self._traj = out["traj"].numpy()
+        self._em = out["em_info"].numpy() if out.get("incl_emerg_traj") else None
+
+    def __len__(self) -> int:
+        return int(self._rows.shape[1])
+
+    def __getitem__(self, b: int) -> tuple:
+        if b < 0:
+            b += len(self)
+        if not 0 <= b < len(self):
+            raise IndexError(b)
+        t, i = {}, {}
+        for s in range(self._rows.shape[0]):
+            r = self._rows[s, b]
+            if r >= 0:
+                name = capi.ACTION_NAMES[int(self._acts[s, b])]
+                t[name] = [self._traj[r, :self._lens[s, b]]]
+                i[name] = int(self._ids[s, b])
+        if self._em is not None and t and self._em[b, 0] >= 0:
+            t["emergency"] = [self._traj[self._em[b, 0], :self._em[b, 1]]]
+            i["emergency"] = int(self._em[b, 2])
+        return t, i
+
+    def __iter__(self):
+        return (self[b] for b in range(len(self)))
+
+    def kept(self) -> np.ndarray:
+        """[NSLOT][B] bool: which (slot, scenario) holds a trajectory -- vectorised access without building dicts"""
+        return self._rows >= 0
+
+
 class Graph_LTPL(object):
     def __init__(self, path_dict: dict, visual_mode: bool = False, log_to_file: bool = True, device=None) -> None:
         for entry in REQ_PATH_DICT_ENTRIES:   # LTPL:62-68
@@ -292,28 +331,12 @@ class Graph_LTPL(object):
         return out
 
     @staticmethod
-    def unpack_batch(out: dict) -> list:
+    def unpack_batch(out: dict) -> "ActionSetView":
         """per-scenario view of a plan_batch / plan_stream result in the reference's return structure of
-        calc_vel_profile (LTPL:344-408): a list of ({action: [ndarray(rows, 7)]}, {action: id}) -- the arrays are views of
-        the pinned host buffer (fp32), nothing is copied."""
-        names = capi.ACTION_NAMES
-        rows, lens, ids, acts = (out[k].numpy() for k in ("traj_row", "traj_len", "traj_id", "action_id"))
-        traj = out["traj"].numpy()
-        em = out["em_info"].numpy() if out.get("incl_emerg_traj") else None
-        res = []
-        for b in range(rows.shape[1]):
-            t, i = {}, {}
-            for s in range(rows.shape[0]):
-                r = rows[s, b]
-                if r >= 0:
-                    name = names[int(acts[s, b])]
-                    t[name] = [traj[r, :lens[s, b]]]
-                    i[name] = int(ids[s, b])
-            if em is not None and t and em[b, 0] >= 0:
-                t["emergency"] = [traj[em[b, 0], :em[b, 1]]]
-                i["emergency"] = int(em[b, 2])
-            res.append((t, i))
-        return res
+        calc_vel_profile (LTPL:344-408): a sequence of ({action: [ndarray(rows, 7)]}, {action: id}), one entry per
+        scenario.  The sequence is LAZY: it keeps the packed index arrays and builds a scenario's two dicts when it is
+        indexed or iterated; the arrays are views of the pinned host buffer (fp32), nothing is copied."""
+        return ActionSetView(out)
 
     def plan_stream(self, batches, vel_est=None, device_hook=None):
         """Pipelined variant of ``plan_batch`` over an iterable of ScenarioBatch objects: yields one result dict per

@@ -152,6 +152,10 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
     if (len < 0) lo = 0;
     float k_prev = K[lo], ax_prev = GG ? AX[lo] : c.ax_max;
     float cur = brake ? wcap : fminf(fminf(vr_rcp(k_prev), wmax), wcap);
+    // A brake profile approaches w = 0 from large values: the absolute rounding of an fp32 accumulator (1e-3 after 100
+    // steps from 60 m/s) would be several mm/s in v just before standstill.  Brake lanes therefore ACCUMULATE in
+    // float64 (the acceleration itself stays fp32: its error enters scaled by the step).
+    double cur64 = (double)cur;
     if (len >= 0) W[lo] = cur;
     float o_prev = cur;
     bool prev_rise = false, active = brake;
@@ -183,9 +187,13 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
         const float a_t = vr_tire<EXP1>(c, cur, k_prev, ax_prev);
         const float a_m = fmaf(sl, v - x0, f0);                              // mode 'accel_forw': min(tyre, machine(v))
         const float a_sel = brake ? -a_t : fminf(a_t, a_m);
-        const float wn = fmaf(fmaf(-cur, c.dm, a_sel), e2, cur);             // + drag
+        const float a = fmaf(-cur, c.dm, a_sel);                             // + drag
+        const float wn = fmaf(a, e2, cur);
         float nxt = active ? fminf(wn, o_n) : o_n;
-        if (brake) nxt = fmaxf(wn, 0.0f);   // negative radicand: standstill, the rest of the profile stays 0
+        if (BRAKE && brake) {   // negative radicand: standstill, the rest of the profile stays 0
+            cur64 = fmax(cur64 + (double)a * (double)e2, 0.0);
+            nxt = (float)cur64;
+        }
         active = active && !(wn > wmax);
         if (live) W[p] = nxt;
         cur = nxt;
@@ -373,7 +381,8 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     __shared__ float s_tab[4 * VR_TAB];
     __shared__ int s_q[VR_P], s_n[VR_P], s_sh[VR_P], s_nb1[VR_P], s_nb2[VR_P], s_use_src[VR_P], s_row[VR_P], s_any_red;
     __shared__ long long s_in[VR_P], s_out[VR_P];
-    __shared__ float s_wf0[VR_P];
+    __shared__ float s_wf0[VR_P], s_wcap[VR_P];
+    __shared__ double s_v0[VR_P];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int B = dm.batch;
     const int nq = LTPL_NSLOT * B;
@@ -457,12 +466,11 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
 
     // ---- follow, warp 1: opponent brake distance on the global race line, ggv = [100, 14, 14] (CVPF:134, 166-199);
     //      needs no path array and overlaps the bulk copies ----
-    // the path a lane's chain works on: other class -> path 2 lane + warp (lanes < P / 2);  follow warp 0 -> path lane
-    // (complete profile, lanes < P) and path lane - P (ego brake profile, lanes P .. 2P-1);  follow warp 1 -> path lane
+    // the path a lane's chain works on: other class -> path 2 lane + warp (lanes < P / 2);  follow -> path lane (lanes < P;
+    // warp 0: complete profile, warp 1: ego brake profile, then the control profile)
     const int pl = follow_cls ? lane % VR_P : min(2 * lane + warp, VR_P - 1);
-    const bool lane_has = follow_cls ? (lane < (fw0 ? 2 * VR_P : VR_P)) : (lane < VR_P / 2);
+    const bool lane_has = follow_cls ? (lane < VR_P) : (lane < VR_P / 2);
     const bool mine = lane_has && s_n[pl] > 0;
-    const bool brake = fw0 && lane >= VR_P;
     const int q = s_q[pl], n = s_n[pl];
     const int b = mine ? q % B : 0;
     float* X = blk + rowf * pl;
@@ -477,8 +485,12 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     const double vel_plan = mine ? bf.vel[b] : 0.0;
     const double vs_f = fmax(vel_plan, 0.0);
     const float wcap_m = (float)(vs_f * vs_f);
-    int st = (mine && !brake) ? bf.status[q] : 0;
-    const int action = (mine && !brake) ? bf.action_id[q] : LTPL_ACT_NONE;
+    if (mine) {   // first row: a profile that starts at the planned velocity returns it exactly (see the end)
+        s_wcap[pl] = wcap_m;
+        s_v0[pl] = vs_f;
+    }
+    int st = mine ? bf.status[q] : 0;
+    const int action = mine ? bf.action_id[q] : LTPL_ACT_NONE;
     const bool red = (st & LTPL_ST_REDUCED_HORIZON) != 0;
     bool vel_bound = true;
 
@@ -593,7 +605,8 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
         }
         LTPL_PH(8)
     } else if (fw0) {
-        vr_bar_sync(1);   // K' of warp 1 has landed
+        vr_bar_arrive(2);   // E2 and the arc lengths are ready for warp 1
+        vr_bar_sync(1);     // K' of warp 1 has landed
     } else {
         __threadfence_block();
         __syncwarp();
@@ -602,22 +615,24 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     // ==================================================================================================================
     // rounds of (forward sweep, backward sweep):
     //   other class        round 0: v_end rule + one profile (OTH:834-923)
-    //   follow, warp 0     round 0: complete profile (lanes < P) with the ego brake profile riding along (lanes P..2P-1);
-    //                      round 1 (a reduced-horizon path in the group): second profile with v_end = 0 (OTH:846-923)
-    //   follow, warp 1     round 0: follow scalars (CVPF:139-247) behind the brake profile, then the control profile
+    //   follow, warp 0     round 0: complete profile (CVPF:296);  round 2 (a reduced-horizon path in the group): second
+    //                      profile with v_end = 0 (OTH:846-923)
+    //   follow, warp 1     round 0: ego brake profile (CVPF:152-165, forward only, float64 accumulator);  round 1: follow
+    //                      scalars (CVPF:139-247), then the control profile -- both warps' chains advance concurrently
     // ==================================================================================================================
     int flags = 0, idx_c = 0, stop_idx = 0, hi = -1;
     bool use_prof = false, has_ctrl = false;
     double vcs = 0.0;
-    const int rounds = (follow_cls && any_red) ? 2 : 1;
+    const int rounds = follow_cls ? (any_red ? 3 : 2) : 1;
 #pragma unroll 1
     for (int round = 0; round < rounds; ++round) {
         bool on = false;
         int lo = 0;
         float wcap = wcap_m, we = -1.0f, wmx = wmax;
         float* W = WM;
+        bool brake = false;
         hi = -1;
-        if (round == 1) {   // materialise min(profile, complete) first: quirk q1 compares it with the second profile
+        if (round == 2) {   // materialise min(profile, complete) first: quirk q1 compares it with the second profile
             for (int r = 0; r < VR_P; ++r) {
                 float* Wr = blk + rowf * r + nmax;
                 const float* Sr = blk + rowf * r + 3 * (size_t)nmax;
@@ -625,9 +640,9 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
             }
             __syncthreads();
         }
-        if (!follow_cls || (fw0 && round == 1)) {
+        if (!follow_cls || (fw0 && round == 2)) {
             // ---- single profile: all actions but follow, and follow with a reduced horizon ----
-            on = mine && !brake && (!follow_cls || red);
+            on = mine && (!follow_cls || red);
             if (on) {
                 double v_end;
                 int v_idx;
@@ -657,16 +672,21 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
                 }
                 if (follow_cls) W = SRC;   // second profile of a follow path: SRC is free after the merge above
             }
-        } else if (fw0) {
-            // ---- complete profile on [0, n-1] (CVPF:296) | ego brake profile (CVPF:152-165) into SRC ----
+        } else if (fw0 && round == 0) {
+            // ---- complete profile on [0, n-1] (CVPF:296) ----
             on = mine;
             hi = n - 1;
-            if (brake) W = SRC;
-        } else if (round == 0) {
-            // ---- follow scalars (CVPF:139-247), then the control profile on [idx_c, stop_idx] into SRC ----
+        } else if (fw1 && round == 0) {
+            // ---- ego brake profile on [0, n-1] into SRC (CVPF:152-165) ----
             LTPL_PH(7)
-            vr_bar_sync(2);   // brake profile, E2 and arc lengths of warp 0 are ready
+            vr_bar_sync(2);   // E2 and the arc lengths of warp 0 are ready
             LTPL_PH(9)
+            on = mine;
+            brake = true;
+            hi = n - 1;
+            W = SRC;
+        } else if (fw1 && round == 1) {
+            // ---- follow scalars (CVPF:139-247), then the control profile on [idx_c, stop_idx] into SRC ----
             double v_end_c = 0.0, v_control = 0.0;
             if (mine) {
                 double obj_dist;
@@ -748,16 +768,17 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
             LTPL_PH(10)
         }
 
-        if (fw0 && round == 0) {
-            vr_forward<EXP1, true, GG>(c, on, brake, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
-            LTPL_PH(3)
-            vr_bar_arrive(2);
+        if (fw1 && round == 0) {
+            vr_forward<EXP1, true, GG>(c, on, true, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
         } else {
             vr_forward<EXP1, false, GG>(c, on, false, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
+            if (fw0 && round == 0) {
+                LTPL_PH(3)
+            }
         }
         const float w_first = vr_backward<EXP1, GG>(c, on && !brake, Kp, E2, AXp, IAYp, W, lo, hi, wmx);
 
-        if (!follow_cls || (fw0 && round == 1)) {
+        if (!follow_cls || (fw0 && round == 2)) {
             if (on) {
                 for (int p = hi + 1; p < n; ++p) W[p] = 0.0f;   // zeros behind the reduced horizon (OTH:900-903)
                 const float wf0 = (hi >= 0) ? w_first : 0.0f;
@@ -768,7 +789,7 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
                     vel_bound = fabs(sqrt((double)wf0) - vel_plan) < prm.v_max_offset;
                 }
             }
-        } else if (fw1 && round == 0) {
+        } else if (fw1 && round == 1) {
             if (mine && use_prof) {
                 const double vcs_p = fmax(vcs, 0.0);
                 if (!has_ctrl) SRC[idx_c] = (float)(vcs_p * vcs_p);
@@ -784,11 +805,11 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
         } else if (fw0 && round == 0) {
             LTPL_PH(4)
         }
-        if (follow_cls)
+        if (follow_cls && round >= 1)   // (round 0 -> 1: warp 1 only depends on its own brake profile)
             __syncthreads();
         else
             __syncwarp();
-        if (follow_cls && round == 0) {
+        if (follow_cls && round == 1) {
             LTPL_PH(5 + 7 * warp)
         }
     }
@@ -843,7 +864,9 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
                     a = (w1 - w0) * vr_rcp(Er[p]);
                     if (w0 <= 1e-16f && fabsf(a) <= 1e-8f) a = -5.0f;
                 }
-                vx_pl[s_out[r] + p] = (double)vr_sqrt(w0);
+                // v[0] = min(v[0], v_start) (tph): an unchanged first value IS the planned velocity, bit for bit
+                const double v = (p == 0 && w0 == s_wcap[r]) ? s_v0[r] : (double)sqrtf(w0);
+                vx_pl[s_out[r] + p] = v;
                 ax_pl[s_out[r] + p] = (double)a;
             }
             // exported rows: four points of a thread in flight (16 independent loads), then their 28 stores
@@ -878,7 +901,7 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
                         o[2] = (float)g[u][1];
                         o[3] = (float)g[u][2];
                         o[4] = (float)g[u][3];
-                        o[5] = vr_sqrt(w0);
+                        o[5] = (p == 0 && w0 == s_wcap[r]) ? (float)s_v0[r] : sqrtf(w0);
                         o[6] = a;
                     }
                 }

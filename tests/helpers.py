@@ -44,7 +44,14 @@ def object_list(g, b):
     return out
 
 
-def assert_close(name, got, want, cols, ctx=""):
+W_REL_BRAKE = 2e-5   # see assert_close(w_rel=...)
+
+
+def assert_close(name, got, want, cols, ctx="", w_rel=None):
+    """w_rel: a brake-to-standstill profile (the 'emergency' trajectory) is integrated in w = v^2 from its start
+    velocity v0; a relative difference eps in v0 (1e-6 from the fp32 velocity recurrences, against a tolerance of 1e-4)
+    becomes eps v0^2 / v in v just before standstill.  Such profiles are therefore ALSO accepted where
+    |v_got^2 - v_want^2| <= w_rel * v0^2 (the same tolerance, stated in the quantity the profile is integrated in)."""
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, "%s %s: shape %s vs %s" % (ctx, name, got.shape, want.shape)
@@ -53,6 +60,11 @@ def assert_close(name, got, want, cols, ctx=""):
         if key == "psi":   # headings are compared modulo 2 pi
             d = np.abs(np.mod(got[:, c] - want[:, c] + np.pi, 2 * np.pi) - np.pi)
         lim = ATOL[key] + RTOL * np.abs(want[:, c])
+        if w_rel is not None and key == "vx":
+            lim = np.where(np.abs(got[:, c] ** 2 - want[:, c] ** 2) <= w_rel * want[0, c] ** 2, np.inf, lim)
+        if w_rel is not None and key == "ax":   # ax = d(v^2) / (2 ds): the same band, ds >= 0.5 m
+            w0 = want[0, cols.index("vx")] ** 2
+            lim = np.maximum(lim, 2.0 * w_rel * w0)
         bad = np.nonzero(d > lim)[0]
         assert bad.size == 0, "%s %s col %s: %d/%d rows off, worst |d|=%.3e at row %d (want %.6e got %.6e)" % (
             ctx, name, key, bad.size, d.size, d.max(), int(np.argmax(d)), want[int(np.argmax(d)), c],
@@ -168,7 +180,7 @@ def compare_emergency(rec, g, b, ctx=""):
     if has:
         assert int(rec["ids"]["emergency"]) % 10 == int(g["em_id"][b]) % 10, "%s scenario %d emergency id" % (ctx, b)
         assert_close("traj[emergency]", rec["traj_full"]["emergency"][0], g["em_traj"][b, :n],
-                     ("s", "x", "y", "psi", "kappa", "vx", "ax"), "%s scenario %d" % (ctx, b))
+                     ("s", "x", "y", "psi", "kappa", "vx", "ax"), "%s scenario %d" % (ctx, b), w_rel=W_REL_BRAKE)
 
 
 VARIANTS = {   # oracle/gen_golden.py VARIANTS: online overrides, vehicle parameters, velocity arguments, vel_est offset

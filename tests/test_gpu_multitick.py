@@ -130,7 +130,7 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
                     assert ("emergency" in rec["traj"]) == (n_em > 0), ctx + " emergency presence"
                     if n_em:
                         H.assert_close("traj[emergency]", rec["traj"]["emergency"][0], g["em_traj"][q, k, :n_em],
-                                       ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+                                       ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx, w_rel=H.W_REL_BRAKE)
             except AssertionError as e:
                 fails.append(str(e).split("\\n")[0][:400] if "nodes of" not in str(e) else str(e)[:700])
                 alive[q] = False            # later ticks of this sequence depend on this one
@@ -305,5 +305,5 @@ def test_facade_runs_closed_loop_like_the_reference(fixture, seqs, emerg):
                     compared += 1
             if emerg and int(g["em_len"][q, k]):
                 H.assert_close("traj[emergency]", traj["emergency"][0], g["em_traj"][q, k, :int(g["em_len"][q, k])],
-                               ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx)
+                               ("s", "x", "y", "psi", "kappa", "vx", "ax"), ctx, w_rel=H.W_REL_BRAKE)
     assert compared > (20 if emerg else 40)

@@ -37,7 +37,7 @@ def _work(args):
                 if em_w is not None:
                     assert id_w % 10 == id_g % 10
                     H.assert_close("traj[emergency]", em_g[0], em_w[0], ("s", "x", "y", "psi", "kappa", "vx", "ax"),
-                                   "scenario %d" % idx[i])
+                                   "scenario %d" % idx[i], w_rel=H.W_REL_BRAKE)
             H.compare_records(got, want, ctx="scenario %d" % idx[i])
         except AssertionError as e:
             bad.append(str(e).split("\n")[0][:300])
@@ -90,7 +90,7 @@ def main():
             chunks.append((list(range(a, b)), sc.pos[a:b], sc.heading[a:b], sc.vel[a:b],
                            [sc.object_list(i) for i in range(a, b)], recs[a:b], zones[a:b], features))
         ctx = mp.get_context("spawn")
-        with ctx.Pool(min(os.cpu_count(), 96), initializer=_init, initargs=(tag,)) as pool:
+        with ctx.Pool(min(bench.usable_cores(), 96), initializer=_init, initargs=(tag,)) as pool:
             res = pool.map(_work, chunks)
         bad = [m for r in res for m in r[0]]
         ties = sum(r[1] for r in res)
