@@ -269,7 +269,6 @@ static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const Ltp
 
 static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                       cudaStream_t st) {
-    const int nq = LTPL_NSLOT * dm->batch;
     if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
     if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
     if (int r = check_launch("k_vel")) return r;   // first ticks: the export of the kept rows is fused into k_vel_res

@@ -2,7 +2,7 @@
 repo's NumPy port, measured in the build container (the reference checkout does not exist on the GPU box, and its two
 third-party dependencies are restated by oracle/shims -- kind "reference+shims").  Writes one JSON object:
 
-    python tools/cpu_reference_shims.py [n_scenarios] > profiles/r2_cpu_reference_shims.json
+    python oracle/time_reference_shims.py [n_scenarios] > profiles/r2_cpu_reference_shims.json
 
 Per scenario, as BASELINE.md section 2 asks: set_startpos -> calc_paths -> calc_vel_profile, visual_mode=False,
 log_to_file=False, one BLAS thread (main_min_example.py:8)."""

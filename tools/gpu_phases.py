@@ -23,14 +23,16 @@ pl.lib.ltpl_debug_phases(out, 0)
 cnt = pl.t["queue_cnt"].cpu().numpy()
 P = int(os.environ.get("VR_P", "8"))
 gf = (cnt[0] + P - 1) // P
-names = {0: "w0 wait TMA", 1: "w0 el -> E2, s (scan)", 2: "w0 wait K'", 3: "w0 forward complete + brake", 4: "w0 backward",
-         5: "w0 wait warp 1", 6: "w1 opponent brake distance", 7: "w1 wait TMA + kappa -> K'", 8: "w1 nearest points",
-         9: "w1 wait brake profile", 10: "w1 follow scalars", 11: "w1 control profile fwd + bwd", 12: "w1 wait warp 0",
-         13: "element-wise end (both warps)"}
+# time since the previous marker of the same warp, summed over both warps of every CTA (all classes)
+names = {6: "setup + (w1) opponent brake distance", 0: "wait for the bulk copies", 1: "rows -> fp32 (w0: el, s scan; w1: kappa)",
+         8: "w1 nearest path points", 7: "w1 up to the brake chain", 9: "w1 wait for E2 / arc lengths (bar 2)",
+         10: "w1 ego brake chain + follow scalars", 11: "w1 control profile fwd + bwd, acceptance",
+         3: "w0 forward sweep (complete profile)", 4: "w0 backward sweep", 5: "w0 wait for warp 1", 12: "w1 wait for warp 0",
+         13: "element-wise end + export rows"}
 print("queue counts", cnt[:2], "follow CTAs", gf)
 pn = {16: "plan: defaults+object filter", 17: "plan: planning range", 18: "plan: blocked edges+closest", 19: "plan: const-seg objects",
       20: "plan: glob match", 21: "plan: DP", 22: "plan: goal+backtrack"}
 for k in range(16, 23):
     print("%-30s %10.0f cycles/scenario" % (pn[k], out[k] / 10000.0))
-for k in range(14):
-    print("%-34s %10.0f cycles per follow CTA" % (names.get(k, k), out[k] / max(gf * (2 if k == 13 else 1), 1)))
+for k in (6, 0, 1, 8, 7, 9, 10, 11, 3, 4, 5, 12, 13):
+    print("%-44s %10.0f cycles per follow CTA" % (names[k], out[k] / max(gf, 1)))
