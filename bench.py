@@ -687,7 +687,13 @@ def main():
             torch.cuda.synchronize(device)
             flags = pl_s.fetch("sc_flags")["sc_flags"]
             first_tick()
-            t_st, t_wall = 0.0, 0.0
+            t_st, t_wall, t_dev = 0.0, 0.0, 0.0
+            e_dev = [None]
+
+            def mark_device_start():
+                e_dev[0] = torch.cuda.Event(enable_timing=True)
+                e_dev[0].record(stream)
+            pl_s.on_device_start = mark_device_start
             for pos_k, vel_k, sel_k in rec_in:
                 sc_k = ScenarioBatch(pos_k, sc.heading, sc.vel, sc.n_obj, sc.obj)
                 flush.fill_(1)
@@ -700,8 +706,11 @@ def main():
                 torch.cuda.synchronize(device)
                 t_wall += time.perf_counter() - w0
                 t_st += e0.elapsed_time(e1) * 1e-3
+                t_dev += e_dev[0].elapsed_time(e1) * 1e-3
+            pl_s.on_device_start = None
             extra["stateful_tick"] = {"ticks_per_s": args.batch * n_loop / t_st, "ms_per_tick": 1e3 * t_st / n_loop,
                                       "wall_ms_per_tick_incl_host_staging": 1e3 * t_wall / n_loop,
+                                      "device_ms_per_tick_after_host_staging": 1e3 * t_dev / n_loop,
                                       "ticks": n_loop, "scenarios_still_planned_at_the_end": int((flags == 0).sum()),
                                       "flags_at_the_end": {name: int(((flags & bit) != 0).sum()) for name, bit in (
                                           ("out_of_track", capi.SC_OUT_OF_TRACK),

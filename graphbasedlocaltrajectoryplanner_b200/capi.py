@@ -12,7 +12,8 @@ import os
 import subprocess
 import sys
 
-ABI_VERSION = 11
+ABI_VERSION = 12
+MAX_SUB = 8
 NSLOT = 3
 KMAX = 16
 MAX_AXM = 32
@@ -65,7 +66,7 @@ class Params(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "k_obj", "p0_max", "p_max", "h_max", "n_export", "n_zone_words",
-                                            "n_zones", "k_pred", "pad0")]
+                                            "n_zones", "k_pred", "sub_id", "sub_off", "sub_cnt")]
 
 
 BUFFER_FIELDS = ("pos", "heading", "vel", "vel_est", "n_obj", "obj", "sc_flags", "start_node", "const_len", "const_seg",
@@ -91,7 +92,7 @@ class VelBatch(C.Structure):
 EXPORTS = ("ltpl_version", "ltpl_last_error", "ltpl_sizeof", "ltpl_lattice_create", "ltpl_lattice_destroy",
            "ltpl_set_startpos_batch", "ltpl_calc_paths_batch", "ltpl_calc_vel_profile_batch", "ltpl_tick_batch",
            "ltpl_velprofile_batch", "ltpl_launch_count", "ltpl_launch_stage", "ltpl_next_tick_batch",
-           "ltpl_next_calc_paths_batch", "ltpl_next_calc_vel_profile_batch")
+           "ltpl_next_calc_paths_batch", "ltpl_next_calc_vel_profile_batch", "ltpl_set_subbatches")
 
 
 def build_library(verbose: bool = False) -> str:
@@ -133,6 +134,8 @@ def load_library():
     lib.ltpl_launch_count.restype = C.c_uint64
     lib.ltpl_lattice_create.argtypes = [C.POINTER(LatticeHeader), C.c_void_p, C.POINTER(C.c_void_p)]
     lib.ltpl_lattice_destroy.argtypes = [C.c_void_p]
+    lib.ltpl_set_subbatches.argtypes = [C.c_void_p, C.c_int]
+    lib.ltpl_set_subbatches.restype = C.c_int
     for fn in (lib.ltpl_set_startpos_batch, lib.ltpl_calc_paths_batch, lib.ltpl_calc_vel_profile_batch,
                lib.ltpl_tick_batch, lib.ltpl_next_tick_batch, lib.ltpl_next_calc_paths_batch,
                lib.ltpl_next_calc_vel_profile_batch):

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -23,7 +24,7 @@ static std::atomic<unsigned long long> g_launches{0};
 // velocity kernel: one CTA per VR_P queued paths of one class, the paths resident in shared memory (ltpl_vel_res.cuh)
 static cudaError_t launch_k_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                                 cudaStream_t st, bool stateful = false) {
-    const int nq = LTPL_NSLOT * dm->batch;
+    const int nq = LTPL_NSLOT * dm->sub_cnt;   // paths of this launch's scenario window
     const int nmax = dm->p_max;
     if (nmax > 32 * VR_MAXM || nmax % 4 != 0) return cudaErrorInvalidValue;
     const bool gg = bf->gg != nullptr;   // location dependent local_gg: the general-exponent variant carries it
@@ -91,7 +92,7 @@ static const char* launch_k_plan(const LtplLattice* lat, const LtplParams* prm, 
             return "cudaFuncSetAttribute(k_plan) failed";
         attr = smem;
     }
-    const int grid = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, thr = LTPL_WARPS_PER_CTA * 32;
+    const int grid = (dm->sub_cnt + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, thr = LTPL_WARPS_PER_CTA * 32;
     const bool zone = dm->n_zones > 0;
     if (zone && stateful)
         k_plan<true, true><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
@@ -209,14 +210,97 @@ int ltpl_lattice_create(const LtplLatticeHeader* h, void* dev_blob, LtplLattice*
         }
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
+    {   // internal streams / events of the scenario windows (ltpl_set_subbatches)
+        cudaError_t e = cudaEventCreateWithFlags(&lat->ev_fork, cudaEventDisableTiming);
+        for (int i = 0; i < LTPL_MAX_SUB - 1 && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&lat->aux[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&lat->ev_join[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) {
+            g_err = std::string("ltpl_lattice_create: streams: ") + cudaGetErrorString(e);
+            ltpl_lattice_destroy(lat);
+            return -2;
+        }
+        lat->n_sub = LTPL_DEFAULT_SUB;
+        lat->sub_min = LTPL_SUB_MIN;
+        if (const char* env = getenv("LTPL_SUBBATCHES")) {
+            const int n = atoi(env);
+            if (n >= 1 && n <= LTPL_MAX_SUB) lat->n_sub = n;
+        }
+    }
     *out = lat;
     return 0;
 }
 
 int ltpl_lattice_destroy(LtplLattice* lat) {
+    if (!lat) return 0;
+    for (int i = 0; i < LTPL_MAX_SUB - 1; ++i) {
+        if (lat->aux[i]) cudaStreamDestroy(lat->aux[i]);
+        if (lat->ev_join[i]) cudaEventDestroy(lat->ev_join[i]);
+    }
+    if (lat->ev_fork) cudaEventDestroy(lat->ev_fork);
     delete lat;
     return 0;
 }
+
+int ltpl_set_subbatches(LtplLattice* lat, int n) {
+    if (!lat) return fail("null argument");
+    if (n < 1 || n > LTPL_MAX_SUB) return fail("ltpl_set_subbatches: n must be in [1, LTPL_MAX_SUB]");
+    lat->n_sub = n;
+    lat->sub_min = 1;   // an explicit request is taken literally (windows of at least one scenario)
+    return 0;
+}
+
+// ---- scenario windows: the launches of one call run per window, window 0 on the caller's stream, the others on the
+// handle's internal streams between an event fork and an event join (also valid under stream capture) ----
+static LtplDims window_dims(const LtplDims* dm, int s, int n) {
+    LtplDims w = *dm;
+    const int per = (dm->batch + n - 1) / n;
+    w.sub_id = s;
+    w.sub_off = s * per;
+    w.sub_cnt = dm->batch - s * per < per ? dm->batch - s * per : per;
+    if (w.sub_cnt < 0) w.sub_cnt = 0;
+    return w;
+}
+
+static int window_count(const LtplLattice* lat, const LtplDims* dm) {
+    int n = lat->n_sub;
+    while (n > 1 && (dm->batch + n - 1) / n < lat->sub_min) --n;
+    if (n > dm->batch) n = dm->batch;
+    return n < 1 ? 1 : n;
+}
+
+extern "C++" {
+template <class Body>
+static int for_windows(const LtplLattice* lat, const LtplDims* dm, cudaStream_t st, Body body) {
+    const int n = window_count(lat, dm);
+    if (n == 1) {
+        const LtplDims w = window_dims(dm, 0, 1);
+        return body(&w, st);
+    }
+    if (cudaEventRecord(lat->ev_fork, st) != cudaSuccess) return fail("event record (fork) failed");
+    int rc = 0;
+    {
+        const LtplDims w = window_dims(dm, 0, n);
+        rc = body(&w, st);
+    }
+    int forked = 0;
+    for (int s = 1; s < n && rc == 0; ++s, ++forked) {
+        cudaStream_t a = lat->aux[s - 1];
+        if (cudaStreamWaitEvent(a, lat->ev_fork, 0) != cudaSuccess) {
+            rc = fail("stream wait (fork) failed");
+            break;
+        }
+        const LtplDims w = window_dims(dm, s, n);
+        const int r = (w.sub_cnt > 0) ? body(&w, a) : 0;
+        if (cudaEventRecord(lat->ev_join[s - 1], a) != cudaSuccess && r == 0) rc = fail("event record (join) failed");
+        if (r) rc = r;
+    }
+    for (int s = 1; s <= forked; ++s)   // join whatever was forked, also after an error
+        if (cudaStreamWaitEvent(st, lat->ev_join[s - 1], 0) != cudaSuccess && rc == 0) rc = fail("stream wait (join) failed");
+    return rc;
+}
+}  // extern "C++"
 
 static int check_common(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf) {
     if (!lat || !prm || !dm || !bf) return fail("null argument");
@@ -248,63 +332,141 @@ int ltpl_set_startpos_batch(const LtplLattice* lat, const LtplParams* prm, const
     return check_launch("k_startpos");
 }
 
-static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
-                        cudaStream_t st) {
+static const int kCntInts = 4 + 4 * LTPL_MAX_SUB;   // buffers.queue_cnt
+
+static int prepare_path_attr(const LtplDims* dm, bool stateful, size_t* smem_out) {
     const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
     if (smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
-    static thread_local size_t attr_path = 0;
-    if (smem_path > 48 * 1024 && smem_path > attr_path) {
-        if (cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
-            return fail("cudaFuncSetAttribute(k_path) failed");
-        attr_path = smem_path;
+    static thread_local size_t attr_path[2] = {0, 0};
+    if (smem_path > 48 * 1024 && smem_path > attr_path[stateful]) {
+        const cudaError_t e = stateful ? cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path)
+                                       : cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path);
+        if (e != cudaSuccess) return fail("cudaFuncSetAttribute(k_path) failed");
+        attr_path[stateful] = smem_path;
     }
-    if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
-    if (const char* e = launch_k_plan(lat, prm, dm, bf, st, false)) return fail(e);
+    *smem_out = smem_path;
+    return 0;
+}
+
+// one scenario window of calc_paths: (k_state ->) k_plan -> k_path
+static int paths_window(const LtplLattice* lat, const LtplParams* prm, const LtplDims* w, const LtplBuffers* bf,
+                        cudaStream_t st, bool stateful, size_t smem_path) {
+    const int grid_b = (w->sub_cnt + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    const int grid_q = (LTPL_NSLOT * w->sub_cnt + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    if (stateful) {
+        k_state<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *w, *bf);
+        if (int r = check_launch("k_state")) return r;
+    }
+    if (const char* e = launch_k_plan(lat, prm, w, bf, st, stateful)) return fail(e);
     if (int r = check_launch("k_plan")) return r;
-    const int nq = LTPL_NSLOT * dm->batch;
-    const int grid_path = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    k_path<false><<<grid_path, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
+    if (stateful)
+        k_path<true><<<grid_q, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *w, *bf);
+    else
+        k_path<false><<<grid_q, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *w, *bf);
     return check_launch("k_path");
 }
 
-static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
-                      cudaStream_t st) {
-    if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
-    if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
-    if (int r = check_launch("k_vel")) return r;   // first ticks: the export of the kept rows is fused into k_vel_res
-    if (prm->incl_emerg_traj) {
-        if (!bf->em_info) return fail("params.incl_emerg_traj needs buffers.em_info");
-        const size_t smem = emerg_smem_bytes_per_warp(dm->n_export) * LTPL_WARPS_PER_CTA;
-        if (smem > 48 * 1024) return fail("n_export too large for k_emergency");
-        k_emergency<<<(dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem, st>>>(
-            *prm, *dm, *bf);
-        return check_launch("k_emergency");
+static int launch_emergency(const LtplParams* prm, const LtplDims* w, const LtplBuffers* bf, cudaStream_t st) {
+    const size_t smem = emerg_smem_bytes_per_warp(w->n_export) * LTPL_WARPS_PER_CTA;
+    if (smem > 48 * 1024) return fail("n_export too large for k_emergency");
+    k_emergency<<<(w->sub_cnt + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem, st>>>(
+        *prm, *w, *bf);
+    return check_launch("k_emergency");
+}
+
+static const char* kVelCapacity =
+    "k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)";
+
+// one scenario window of calc_vel_profile.  First tick: k_vel_res (exports its rows itself) (-> k_emergency).
+// Stateful tick: k_ref -> k_vel_res -> k_backup -> k_prefix -> k_export (-> k_emergency)
+static int vel_window(const LtplLattice* lat, const LtplParams* prm, const LtplDims* w, const LtplBuffers* bf,
+                      cudaStream_t st, bool stateful) {
+    const int grid_b = (w->sub_cnt + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    const int nq = LTPL_NSLOT * w->sub_cnt;
+    const int grid_q = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
+    if (stateful) {
+        k_ref<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *w, *bf);
+        if (int r = check_launch("k_ref")) return r;
     }
+    if (launch_k_vel(lat, prm, w, bf, st, stateful) != cudaSuccess) return fail(kVelCapacity);
+    if (int r = check_launch("k_vel")) return r;
+    if (stateful) {
+        k_backup<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*prm, *w, *bf);
+        if (int r = check_launch("k_backup")) return r;
+        k_prefix<<<grid_q, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*w, *bf);
+        if (int r = check_launch("k_prefix")) return r;
+        k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0,
+                   st>>>(*w, *bf);
+        if (int r = check_launch("k_export")) return r;
+    }
+    if (prm->incl_emerg_traj) return launch_emergency(prm, w, bf, st);
+    return 0;
+}
+
+static int launch_paths(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                        cudaStream_t st, bool stateful) {
+    size_t smem_path = 0;
+    if (int r = prepare_path_attr(dm, stateful, &smem_path)) return r;
+    if (cudaMemsetAsync(bf->queue_cnt, 0, kCntInts * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
+    return for_windows(lat, dm, st, [&](const LtplDims* w, cudaStream_t s) {
+        return paths_window(lat, prm, w, bf, s, stateful, smem_path);
+    });
+}
+
+static int launch_vel(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                      cudaStream_t st, bool stateful) {
+    if (prm->incl_emerg_traj && !bf->em_info) return fail("params.incl_emerg_traj needs buffers.em_info");
+    if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
+    if (int r = for_windows(lat, dm, st, [&](const LtplDims* w, cudaStream_t s) {
+            return vel_window(lat, prm, w, bf, s, stateful);
+        }))
+        return r;
+    // stateful tick without an emergency trajectory: the next one must not take a stale one for executed (k_state)
+    if (stateful && !prm->incl_emerg_traj && bf->em_info &&
+        cudaMemsetAsync(bf->em_info, 0xFF, sizeof(int) * 3 * (size_t)dm->batch, st) != cudaSuccess)
+        return fail("memset(em_info) failed");
+    return 0;
+}
+
+// calc_paths + calc_vel_profile of one tick: every window runs its whole chain on its stream, one fork / join
+static int launch_tick(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
+                       cudaStream_t st, bool stateful) {
+    size_t smem_path = 0;
+    if (int r = prepare_path_attr(dm, stateful, &smem_path)) return r;
+    if (prm->incl_emerg_traj && !bf->em_info) return fail("params.incl_emerg_traj needs buffers.em_info");
+    if (cudaMemsetAsync(bf->queue_cnt, 0, kCntInts * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
+    if (int r = for_windows(lat, dm, st, [&](const LtplDims* w, cudaStream_t s) {
+            if (int r2 = paths_window(lat, prm, w, bf, s, stateful, smem_path)) return r2;
+            return vel_window(lat, prm, w, bf, s, stateful);
+        }))
+        return r;
+    if (stateful && !prm->incl_emerg_traj && bf->em_info &&
+        cudaMemsetAsync(bf->em_info, 0xFF, sizeof(int) * 3 * (size_t)dm->batch, st) != cudaSuccess)
+        return fail("memset(em_info) failed");
     return 0;
 }
 
 int ltpl_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                           void* stream) {
     if (int r = check_common(lat, prm, dm, bf)) return r;
-    return launch_paths(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
+    return launch_paths(lat, prm, dm, bf, static_cast<cudaStream_t>(stream), false);
 }
 
 int ltpl_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,
                                 const LtplBuffers* bf, void* stream) {
     if (int r = check_common(lat, prm, dm, bf)) return r;
-    return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
+    return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream), false);
 }
 
 int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                     void* stream) {
     if (int r = check_common(lat, prm, dm, bf)) return r;
-    if (int r = launch_paths(lat, prm, dm, bf, static_cast<cudaStream_t>(stream))) return r;
-    return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream));
+    return launch_tick(lat, prm, dm, bf, static_cast<cudaStream_t>(stream), false);
 }
 
 // stateful tick (ltpl_state.cuh):
 //   ltpl_next_calc_paths_batch        k_state -> k_plan<.., true> -> k_path<true>
-//   ltpl_next_calc_vel_profile_batch  k_ref -> k_vel_tiled<true> -> k_prefix -> k_export
+//   ltpl_next_calc_vel_profile_batch  k_ref -> k_vel_res<true> -> k_backup -> k_prefix -> k_export
 static int check_stateful(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf) {
     if (int r = check_common(lat, prm, dm, bf)) return r;
     if (!bf->prev_path || !bf->prev_path_len || !bf->prev_node_idx || !bf->prev_nodes || !bf->prev_n_nodes ||
@@ -322,89 +484,51 @@ static int check_stateful(const LtplLattice* lat, const LtplParams* prm, const L
 int ltpl_next_calc_paths_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                                void* stream) {
     if (int r = check_stateful(lat, prm, dm, bf)) return r;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
-    if (smem_path > 200 * 1024) return fail("lattice window too large for shared memory");
-    if (smem_path > 48 * 1024 &&
-        cudaFuncSetAttribute(k_path<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path) != cudaSuccess)
-        return fail("cudaFuncSetAttribute(k_path) failed");
-    if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess) return fail("memset(queue_cnt) failed");
-    const int grid_b = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    const int grid_q = (LTPL_NSLOT * dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    k_state<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
-    if (int r = check_launch("k_state")) return r;
-    if (const char* e = launch_k_plan(lat, prm, dm, bf, st, true)) return fail(e);
-    if (int r = check_launch("k_plan")) return r;
-    k_path<true><<<grid_q, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(lat->d, *prm, *dm, *bf);
-    return check_launch("k_path");
+    return launch_paths(lat, prm, dm, bf, static_cast<cudaStream_t>(stream), true);
 }
 
 int ltpl_next_calc_vel_profile_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,
                                      const LtplBuffers* bf, void* stream) {
     if (int r = check_stateful(lat, prm, dm, bf)) return r;
     if (bf->vel != bf->vel_plan) return fail("stateful tick: buffers.vel must point at buffers.vel_plan");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid_b = (dm->batch + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    const int nq = LTPL_NSLOT * dm->batch;
-    const int grid_q = (nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA;
-    k_ref<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(lat->d, *prm, *dm, *bf);
-    if (int r = check_launch("k_ref")) return r;
-    if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess) return fail("memset(export count) failed");
-    if (launch_k_vel(lat, prm, dm, bf, st, true) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
-    if (int r = check_launch("k_vel")) return r;
-    k_backup<<<grid_b, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*prm, *dm, *bf);
-    if (int r = check_launch("k_backup")) return r;
-    k_prefix<<<grid_q, LTPL_WARPS_PER_CTA * 32, 0, st>>>(*dm, *bf);
-    if (int r = check_launch("k_prefix")) return r;
-    k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT, LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(
-        *dm, *bf);
-    if (int r = check_launch("k_export")) return r;
-    if (prm->incl_emerg_traj) {
-        const size_t smem = emerg_smem_bytes_per_warp(dm->n_export) * LTPL_WARPS_PER_CTA;
-        if (smem > 48 * 1024) return fail("n_export too large for k_emergency");
-        k_emergency<<<grid_b, LTPL_WARPS_PER_CTA * 32, smem, st>>>(*prm, *dm, *bf);
-        return check_launch("k_emergency");
-    }
-    // no emergency trajectory in this tick: the next one must not take a stale one for executed (k_state)
-    if (bf->em_info && cudaMemsetAsync(bf->em_info, 0xFF, sizeof(int) * 3 * (size_t)dm->batch, st) != cudaSuccess)
-        return fail("memset(em_info) failed");
-    return 0;
+    return launch_vel(lat, prm, dm, bf, static_cast<cudaStream_t>(stream), true);
 }
 
 int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm, const LtplBuffers* bf,
                          void* stream) {
-    if (int r = ltpl_next_calc_paths_batch(lat, prm, dm, bf, stream)) return r;
-    return ltpl_next_calc_vel_profile_batch(lat, prm, dm, bf, stream);
+    if (int r = check_stateful(lat, prm, dm, bf)) return r;
+    if (bf->vel != bf->vel_plan) return fail("stateful tick: buffers.vel must point at buffers.vel_plan");
+    return launch_tick(lat, prm, dm, bf, static_cast<cudaStream_t>(stream), true);
 }
 
 int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, const LtplDims* dm,
                       const LtplBuffers* bf, void* stream) {
     if (int r = check_common(lat, prm, dm, bf)) return r;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LtplDims w = window_dims(dm, 0, 1);   // the whole batch as ONE window: this call times a kernel alone
     const int nq = LTPL_NSLOT * dm->batch;
     switch (stage) {
         case 0: return ltpl_set_startpos_batch(lat, prm, dm, bf, stream);
         case 1:
-            if (const char* e = launch_k_plan(lat, prm, dm, bf, st, false)) return fail(e);
+            if (const char* e = launch_k_plan(lat, prm, &w, bf, st, false)) return fail(e);
             return check_launch("k_plan");
         case 2: {
-            const size_t smem_path = path_smem_bytes_per_warp(dm->h_max) * LTPL_WARPS_PER_CTA;
-            if (smem_path > 48 * 1024)
-                cudaFuncSetAttribute(k_path<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_path);
-            if (cudaMemsetAsync(bf->queue_cnt, 0, 4 * sizeof(int), st) != cudaSuccess)
+            size_t smem_path = 0;
+            if (int r = prepare_path_attr(dm, false, &smem_path)) return r;
+            if (cudaMemsetAsync(bf->queue_cnt, 0, kCntInts * sizeof(int), st) != cudaSuccess)
                 return fail("memset(queue_cnt) failed");
             k_path<false><<<(nq + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, LTPL_WARPS_PER_CTA * 32, smem_path, st>>>(
-                lat->d, *prm, *dm, *bf);
+                lat->d, *prm, w, *bf);
             return check_launch("k_path");
         }
         case 3:
             if (cudaMemsetAsync(bf->queue_cnt + 2, 0, sizeof(int), st) != cudaSuccess)
                 return fail("memset(export count) failed");
-            if (launch_k_vel(lat, prm, dm, bf, st) != cudaSuccess) return fail("k_vel: dims.p_max exceeds the shared-memory capacity of the velocity kernel (<= 512, % 4 == 0)");
+            if (launch_k_vel(lat, prm, &w, bf, st) != cudaSuccess) return fail(kVelCapacity);
             return check_launch("k_vel");
         case 4:
             k_export<<<(nq + LTPL_WARPS_PER_CTA_EXPORT - 1) / LTPL_WARPS_PER_CTA_EXPORT,
-                       LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(*dm, *bf);
+                       LTPL_WARPS_PER_CTA_EXPORT * 32, 0, st>>>(w, *bf);
             return check_launch("k_export");
         default: return fail("ltpl_launch_stage: unknown stage");
     }

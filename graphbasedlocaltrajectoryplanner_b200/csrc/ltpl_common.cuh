@@ -68,10 +68,33 @@ struct LatDev {
     int tab_stride;
 };
 
+#ifndef LTPL_DEFAULT_SUB
+#define LTPL_DEFAULT_SUB 4     // scenario windows per tick
+#endif
+#ifndef LTPL_SUB_MIN
+#define LTPL_SUB_MIN 512       // ... but no window below this many scenarios unless ltpl_set_subbatches asks for it
+#endif
 struct LtplLattice {
     LtplLatticeHeader h;
     LatDev d;
+    // a tick runs as n_sub scenario windows: window 0 on the caller's stream, window s > 0 on aux[s - 1], forked from and
+    // joined into the caller's stream with events (ltpl_set_subbatches)
+    int n_sub = 1, sub_min = LTPL_SUB_MIN;
+    cudaStream_t aux[LTPL_MAX_SUB - 1] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[LTPL_MAX_SUB - 1] = {};
 };
+
+// scenario of a one-warp-per-scenario kernel inside the launch's sub-batch window (-1: none)
+__device__ __forceinline__ int sub_scenario(const LtplDims& dm, int warps_per_cta) {
+    const int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    return (i < dm.sub_cnt) ? dm.sub_off + i : -1;
+}
+// path id q = slot * B + b of a one-warp-per-path kernel inside the window (-1: none)
+__device__ __forceinline__ int sub_path(const LtplDims& dm, int warps_per_cta) {
+    const int i = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+    if (i >= LTPL_NSLOT * dm.sub_cnt) return -1;
+    return (i / dm.sub_cnt) * dm.batch + dm.sub_off + i % dm.sub_cnt;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // float64 helpers with NumPy operation order

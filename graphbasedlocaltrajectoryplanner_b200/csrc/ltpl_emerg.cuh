@@ -26,8 +26,8 @@ k_emergency(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     extern __shared__ __align__(16) unsigned char em_smem[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + wib;
-    if (b >= dm.batch) return;
+    const int b = sub_scenario(dm, LTPL_WARPS_PER_CTA);
+    if (b < 0) return;
     const int B = dm.batch;
     int* info = bf.em_info + 3 * (size_t)b;
     int q = -1;

@@ -13,10 +13,11 @@ __host__ __device__ inline size_t path_smem_bytes_per_warp(int h_max) {
 
 // append path q to the dense work queue of its class (0: follow, 1: straight / left / right) for k_vel
 __device__ __forceinline__ void enqueue_path(const LtplBuffers& bf, const LtplDims& dm, int q) {
-    const int nq = LTPL_NSLOT * dm.batch;
+    const int nq = LTPL_NSLOT * dm.sub_cnt;   // the window's own [2][nq] part of the queue buffer
     const int cls = (bf.action_id[q] == LTPL_ACT_FOLLOW) ? 0 : 1;
-    const int pos = atomicAdd(&bf.queue_cnt[cls], 1);
-    if (pos < nq) bf.queue[cls * nq + pos] = q;
+    const int pos = atomicAdd(&bf.queue_cnt[4 + 4 * dm.sub_id + cls], 1);
+    if (pos < nq) bf.queue[2 * LTPL_NSLOT * dm.sub_off + cls * nq + pos] = q;
+    atomicAdd(&bf.queue_cnt[cls], 1);         // totals over all windows (statistics)
 }
 
 #ifndef LTPL_PATH_MINB
@@ -30,8 +31,8 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int B = dm.batch;
-    const int q = blockIdx.x * LTPL_WARPS_PER_CTA + wib;
-    if (q >= LTPL_NSLOT * B) return;
+    const int q = sub_path(dm, LTPL_WARPS_PER_CTA);
+    if (q < 0) return;
     const int b = q % B;
     const int st = bf.status[q];
     if (!(st & LTPL_ST_FOUND)) return;

@@ -436,8 +436,8 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + wib;
-    if (b >= dm.batch) return;
+    const int b = sub_scenario(dm, LTPL_WARPS_PER_CTA);
+    if (b < 0) return;
     unsigned char* base = smem_raw + plan_smem_bytes_per_warp(maxn, hl, mask_words) * wib;
     PlanSmem* ps = reinterpret_cast<PlanSmem*>(base);
     double* dist = reinterpret_cast<double*>(base + sizeof(PlanSmem));

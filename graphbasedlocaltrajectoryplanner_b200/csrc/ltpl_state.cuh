@@ -55,8 +55,8 @@ __device__ __forceinline__ int find_edge(const LatDev& lt, int layer, int src, i
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
 k_state(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (b >= dm.batch) return;
+    const int b = sub_scenario(dm, LTPL_WARPS_PER_CTA);
+    if (b < 0) return;
     const int B = dm.batch;
     int* info = bf.st_info + 8 * (size_t)b;
     // a scenario whose start pose was rejected (set_startpos returned True, LTPL:268-298) stays so until it is re-anchored
@@ -228,8 +228,8 @@ __device__ __forceinline__ void ref_obj_dist(const LtplDims& dm, const LtplBuffe
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
 k_ref(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (b >= dm.batch) return;
+    const int b = sub_scenario(dm, LTPL_WARPS_PER_CTA);
+    if (b < 0) return;
     const int B = dm.batch;
     if (bf.sc_flags[b] != 0) return;
     const int* info = bf.st_info + 8 * (size_t)b;
@@ -342,8 +342,8 @@ __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
 k_prefix(const LtplDims dm, const LtplBuffers bf) {
     const int lane = threadIdx.x & 31;
     const int B = dm.batch;
-    const int q = blockIdx.x * LTPL_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (q >= LTPL_NSLOT * B) return;
+    const int q = sub_path(dm, LTPL_WARPS_PER_CTA);
+    if (q < 0) return;
     if (!(bf.status[q] & LTPL_ST_TRAJ_VALID)) return;
     const int b = q % B;
     const int cut = bf.trim[4 * q + 2], pref = bf.trim[4 * q + 3];
@@ -385,8 +385,8 @@ k_prefix(const LtplDims dm, const LtplBuffers bf) {
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32)
 k_backup(const LtplParams prm, const LtplDims dm, const LtplBuffers bf) {
     const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * LTPL_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (b >= dm.batch) return;
+    const int b = sub_scenario(dm, LTPL_WARPS_PER_CTA);
+    if (b < 0) return;
     const int B = dm.batch;
     const int q = b;   // slot 0: follow / straight
     const int st = bf.status[q];

@@ -33,9 +33,10 @@ __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA_EXPORT * 32)
 k_export(const LtplDims dm, const LtplBuffers bf) {
     const int B = dm.batch;
     const int lane = threadIdx.x & 31;
-    const int e = blockIdx.x * LTPL_WARPS_PER_CTA_EXPORT + (threadIdx.x >> 5);  // row of the compact export list
-    if (e >= bf.queue_cnt[2]) return;
-    const int q = bf.exp_q[e];
+    const int q = sub_path(dm, LTPL_WARPS_PER_CTA_EXPORT);   // a path of this launch's window ...
+    if (q < 0) return;
+    const int e = bf.traj_row[q];                            // ... and its row of the compact export list
+    if (e < 0) return;
     const int n = bf.traj_len[q];
     const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
     const int cut = bf.trim ? bf.trim[4 * q + 2] : 0;   // stateful tick: the trajectory starts at the cut index (OTH:700)

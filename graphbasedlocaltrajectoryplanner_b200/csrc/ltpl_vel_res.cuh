@@ -386,7 +386,9 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int B = dm.batch;
     const int nq = LTPL_NSLOT * B;
-    const int n_follow = bf.queue_cnt[0], n_other = bf.queue_cnt[1];
+    const int nq_sub = LTPL_NSLOT * dm.sub_cnt;   // this launch's window: its own queues and fill counts
+    const int* queue = bf.queue + 2 * LTPL_NSLOT * dm.sub_off;
+    const int n_follow = bf.queue_cnt[4 + 4 * dm.sub_id], n_other = bf.queue_cnt[4 + 4 * dm.sub_id + 1];
     const int gf = (n_follow + VR_P - 1) / VR_P, go = (n_other + VR_P - 1) / VR_P;
     const int g = blockIdx.x;
     if (g >= gf + go) return;
@@ -406,7 +408,7 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
     if (tid < VR_P) {
         const int t = (follow_cls ? g : g - gf) * VR_P + tid;
         const bool live = t < (follow_cls ? n_follow : n_other);
-        const int q = live ? bf.queue[(follow_cls ? 0 : nq) + t] : -1;
+        const int q = live ? queue[(follow_cls ? 0 : nq_sub) + t] : -1;
         int n = live ? bf.path_len[q] : 0;
         int off_in = 0, pref = 0;
         if (STATE && live) {

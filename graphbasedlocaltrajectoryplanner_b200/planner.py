@@ -98,6 +98,7 @@ class BatchPlanner(object):
         self.t = {}
         self.params = capi.Params()
         self._tick_count = 0
+        self.on_device_start = None   # optional callable, called where a stateful tick's host staging ends (timing)
         self.set_vel_params()
 
     def __del__(self):
@@ -107,6 +108,12 @@ class BatchPlanner(object):
                 self.handle = None
         except Exception:
             pass
+
+    def set_subbatches(self, n: int) -> None:
+        """number of scenario windows a tick is split into inside the library (1 .. capi.MAX_SUB; default 4 for windows
+        of >= 512 scenarios): window s runs on an internal stream, so kernels of different stages overlap.  The results
+        do not depend on it (only the unspecified order of the compact export rows)."""
+        capi.check(self.lib, self.lib.ltpl_set_subbatches(self.handle, int(n)), "ltpl_set_subbatches")
 
     # -- parameters ------------------------------------------------------------------------------------------------------
     def set_vel_params(self, vel_max: float = 100.0, gg_scale: float = 1.0, local_gg=(5.0, 5.0),
@@ -226,7 +233,7 @@ class BatchPlanner(object):
         meta_spec = [("action_id", (NSLOT, B), i32), ("traj_len", (NSLOT, B), i32), ("em_info", (B, 3), i32),
                      ("path_len", (NSLOT, B), i32), ("n_nodes", (NSLOT, B), i32), ("trim", (NSLOT * B, 4), i32),
                      ("exp_q", (NSLOT * B,), i32), ("traj_row", (NSLOT, B), i32), ("traj_id", (NSLOT, B), i32),
-                     ("status", (NSLOT, B), i32), ("sc_flags", (B,), i32), ("queue_cnt", (4,), i32)]
+                     ("status", (NSLOT, B), i32), ("sc_flags", (B,), i32), ("queue_cnt", (4 + 4 * capi.MAX_SUB,), i32)]
         self._carry_spec = meta_spec[:6]
         self._meta_spec = meta_spec
         self.d_meta_raw, t_meta = self._packed(meta_spec, lambda n: torch.zeros(n, dtype=torch.uint8, device=dev))
@@ -522,7 +529,7 @@ class BatchPlanner(object):
         self.buf.trim = t["trim"].data_ptr()
         self._state = st
 
-    def next_calc_paths(self, sc: ScenarioBatch, sel_action, t_const) -> None:
+    def next_calc_paths(self, sc: ScenarioBatch, sel_action, t_const, vel_est=None) -> None:
         """calc_paths of a stateful tick (OTH:289-516 with the iterative memory): ``sc`` carries the object
         lists (its poses are only used by ``next_calc_vel_profile``), ``sel_action`` = action id (capi.ACT_*) every
         scenario executed since the last tick, ``t_const`` = min(average calculation time * calc_time_safety, 0.5) per
@@ -566,7 +573,7 @@ class BatchPlanner(object):
         # pos_est of the previous calc_vel_profile (OTH:537) = `pos` of the input copy the last tick used; this tick
         # uploads into the other copy (a batch with more objects than before re-creates only the input buffers)
         self._pos_last = t["pos"]
-        self.stage_scenarios(sc)
+        self.stage_scenarios(sc, vel_est=vel_est)
         self._use_inputs(1 - self._in_cur)
         buf.pos_last = self._pos_last.data_ptr()
         for k in ("st_info", "vel_plan", "course", "obj_dist"):
@@ -575,6 +582,8 @@ class BatchPlanner(object):
         buf.t_const = t["t_const"].data_ptr()
         self.h_in["sel_action"].numpy()[...] = np.asarray(sel_action, dtype=np.int32).reshape(-1)
         self.h_in["t_const"].numpy()[...] = np.broadcast_to(np.asarray(t_const, dtype=np.float64), (self.dims.batch,))
+        if self.on_device_start is not None:   # measurement hook: the host staging ends here, the device work begins
+            self.on_device_start()
         self.upload()
         self._call(self.lib.ltpl_next_calc_paths_batch, "ltpl_next_calc_paths_batch")
 
@@ -595,8 +604,8 @@ class BatchPlanner(object):
 
     def next_tick(self, sc: ScenarioBatch, sel_action, t_const, vel_est=None) -> None:
         """One stateful tick for the whole batch: ``sc.pos`` = position estimates."""
-        self.next_calc_paths(sc, sel_action, t_const)
-        self.next_calc_vel_profile(vel_est=vel_est)
+        self.next_calc_paths(sc, sel_action, t_const, vel_est=vel_est)   # vel_est travels in the packed upload
+        self.next_calc_vel_profile()
 
     def launch_count(self) -> int:
         return int(self.lib.ltpl_launch_count())

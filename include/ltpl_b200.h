@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LTPL_ABI_VERSION 11
+#define LTPL_ABI_VERSION 12
 
 /* action ids (OTH:14-17 ACTION_ID_MAP) */
 #define LTPL_ACT_NONE (-1)
@@ -168,8 +168,12 @@ typedef struct LtplDims {
     int32_t n_zone_words; /* 32-bit words of one zone bitmask = ceil(num_nodes / 32)   */
     int32_t n_zones;      /* zone bitmasks in LtplBuffers.zone_bits (0: no zones)      */
     int32_t k_pred;       /* prediction points per object slot in obj_pred (0: built-in 0.2 s prediction only) */
-    int32_t pad0;
+    /* sub-batch window of ONE launch, filled by the library itself (callers pass 0): a tick runs as n independent     */
+    /* scenario windows [sub_off, sub_off + sub_cnt) on n internal streams, so that the kernels of different stages     */
+    /* overlap (ltpl_set_subbatches)                                                                                     */
+    int32_t sub_id, sub_off, sub_cnt;
 } LtplDims;
+#define LTPL_MAX_SUB 8
 
 /* Caller-owned device buffers.  q = slot * B + b indexes a path ("action major").                                      */
 typedef struct LtplBuffers {
@@ -199,8 +203,10 @@ typedef struct LtplBuffers {
     int32_t* path_len;        /* [NSLOT][B]                                                                              */
     double* path;             /* [5][NSLOT*B][p_max] planes x, y, psi, kappa, el  (path_dict of calc_paths)              */
     double* coeff;            /* [NSLOT*B][h_max][8] (MOPG:305-309 spline_coeff_mat, stitched OTH:470-472)               */
-    int32_t* queue;           /* [2][NSLOT*B] dense work queues of path ids q: class 0 follow, class 1 other (k_path->k_vel) */
-    int32_t* queue_cnt;       /* [4] fill counts of the two queues ([0], [1]) and number of exported trajectories ([2]);   */
+    int32_t* queue;           /* [2][NSLOT*B] dense work queues of path ids q: class 0 follow, class 1 other (k_path->k_vel); */
+                              /*     sub-batch window [o, o + n) owns the entries [6 o, 6 (o + n)) as its own [2][NSLOT n]   */
+    int32_t* queue_cnt;       /* [4 + 4 LTPL_MAX_SUB]: total fill counts of the two queue classes ([0], [1]), number of    */
+                              /*     exported trajectories ([2]); [4 + 4 s + c] = fill count of class c in sub-batch s;     */
                               /*     zeroed by the library before k_plan / k_path / k_vel                                 */
     int32_t* exp_q;           /* [NSLOT*B] path id q of every exported trajectory row (compact export list)               */
     int32_t* traj_row;        /* [NSLOT][B] row of path q in `traj`, or -1                                                 */
@@ -303,6 +309,11 @@ int ltpl_next_tick_batch(const LtplLattice* lat, const LtplParams* params, const
                          const LtplBuffers* buffers, void* stream);             /* both                              */
 int ltpl_tick_batch(const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims, const LtplBuffers* buf,
                     void* stream);
+/* number of scenario windows a tick is split into (1 .. LTPL_MAX_SUB; default 4, or the environment variable           */
+/* LTPL_SUBBATCHES at ltpl_lattice_create): window s runs its kernels on an internal stream forked from / joined into    */
+/* the caller's stream (events), so k_plan of one window overlaps k_path / k_vel of another.  Results do not depend on it */
+/* (only the order of the compact export rows, which is unspecified anyway).                                             */
+int ltpl_set_subbatches(LtplLattice* lat, int n);
 /* one kernel of the tick on its own (profiling / per-kernel roofline timing in bench.py):                               */
 /* stage 0 k_startpos, 1 k_plan, 2 k_path, 3 k_vel, 4 k_export                                                            */
 int ltpl_launch_stage(int stage, const LtplLattice* lat, const LtplParams* prm, const LtplDims* dims,

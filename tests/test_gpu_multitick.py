@@ -68,6 +68,7 @@ def test_next_tick_matches_reference_sequences(fixture, emerg, group, tag):
         pl_kw = dict(online=online, **veh)
         vel.update(vel_v)
     pl = BatchPlanner(H.lattice_for(tag), device="cuda:0", stateful=True, **pl_kw)
+    pl.set_subbatches(1 + n_seq % 4)                       # 1 .. 4 scenario windows inside the library
     pl.set_vel_params(ax_max_machines=g["ax_max_machines"], incl_emerg_traj=emerg, **vel)
     tc = np.array([_t_const(g["dt"][q, 1:]) for q in range(n_seq)])       # t_const of ticks 1 ..
     fails, compared = [], 0
@@ -163,6 +164,7 @@ def test_closed_loop_matches_session_oracle(tag, n_seq, omin, omax):
     prefer = (("right", "left", "straight", "follow"), ("follow", "straight", "left", "right"),
               ("left", "right", "follow", "straight"), ("straight", "follow", "right", "left"))
     pl = BatchPlanner(lat, device="cuda:0", stateful=True)
+    pl.set_subbatches(5)                                   # five scenario windows inside the library (uneven split)
     pl.set_vel_params(**vel)
 
     class Clk(object):

@@ -12,9 +12,14 @@ pytestmark = pytest.mark.gpu
 VEL = dict(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), safety_d=30.0)
 
 
+SUBBATCHES = {"default": 3, "l216": 4, "l430": 1, "open": 5, "layers14": 2}   # scenario windows inside the library
+
+
 def _planner(tag):
     from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
-    return BatchPlanner(H.lattice_for(tag), device="cuda:0")
+    pl = BatchPlanner(H.lattice_for(tag), device="cuda:0")
+    pl.set_subbatches(SUBBATCHES[tag])   # explicit: also for these small batches (uneven windows incl.)
+    return pl
 
 
 def _run_batch(pl, sc, axm):

@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 def _planner(g):
     from graphbasedlocaltrajectoryplanner_b200.planner import BatchPlanner
     pl = BatchPlanner(H.lattice_for("default"), device="cuda:0")
+    pl.set_subbatches(3)   # zones, emergency rows and prediction arrays across three scenario windows
     pl.set_vel_params(vel_max=100.0, gg_scale=1.0, local_gg=(5.0, 5.0), ax_max_machines=g["ax_max_machines"],
                       safety_d=30.0, incl_emerg_traj=True)
     return pl
