@@ -1,8 +1,9 @@
 """per-source-line hot spots of one kernel from an .ncu-rep (needs --import-source on, -lineinfo):
-python tools/ncu_hotlines.py rep.ncu-rep kernel_regex [top_n]"""
+python tools/ncu_hotlines.py rep.ncu-rep kernel_regex [top_n] [smp|inst]"""
 import csv, subprocess, sys, io, os
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+key = 1 if (len(sys.argv) > 4 and sys.argv[4] == "inst") else 0
 raw = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--kernel-name', 'regex:' + kern, '--print-source',
                       'cuda,sass'], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True).stdout
 fname, hdr, lines = "?", None, []
@@ -22,5 +23,5 @@ for r in csv.reader(io.StringIO(raw)):
 ts = sum(l[0] for l in lines) or 1.0
 ti = sum(l[1] for l in lines) or 1.0
 print("kernel %s: %.4g warp instructions, %.4g stall samples" % (kern, ti, ts))
-for smp, ins, loc, src in sorted(lines, key=lambda l: -l[0])[:top]:
+for smp, ins, loc, src in sorted(lines, key=lambda l: -l[key])[:top]:
     print("%5.1f%% smp %5.1f%% inst | %-22s | %s" % (100 * smp / ts, 100 * ins / ti, loc, src))
