@@ -40,16 +40,18 @@ class LatticeHeader(C.Structure):
     _fields_ = ([("abi_version", C.c_int32)]
                 + [(n, C.c_int32) for n in ("num_layers", "num_nodes", "num_edges", "num_samples", "n_glob_rl", "closed",
                                             "plan_horizon_mode", "max_nodes_per_layer", "max_window_edges",
-                                            "max_pair_edges", "tab_stride")]
+                                            "max_pair_edges", "tab_stride", "grid_nx", "grid_ny")]
                 + [(n, C.c_double) for n in ("lat_offset", "lat_resolution", "sampled_resolution", "vel_decrease_lat",
-                                             "veh_width", "veh_length", "virt_goal_node_cost", "min_plan_horizon")]
+                                             "veh_width", "veh_length", "virt_goal_node_cost", "min_plan_horizon",
+                                             "grid_x0", "grid_y0", "grid_inv_cell")]
                 + [(n, C.c_uint64) for n in (
                     "off_node_off", "off_raceline_index", "off_s_raceline", "off_vel_raceline", "off_refline",
                     "off_raceline", "off_bound1", "off_bound2", "off_centerline", "off_node_xy", "off_node_psi",
                     "off_node_layer", "off_in_off", "off_edge_layer_off", "off_edge_src", "off_edge_dst",
                     "off_edge_cost", "off_edge_len", "off_edge_psi1", "off_edge_psi0", "off_samp_off", "off_samp_xy", "off_samp_el",
                     "off_samp_edge", "off_glob_rl", "off_glob_xy", "off_edge_rec", "off_tab_reach", "off_tab_node",
-                    "off_tab_edge", "blob_bytes")])
+                    "off_tab_edge", "off_grid_center", "off_grid_refline", "off_grid_raceline", "off_grid_glob",
+                    "blob_bytes")])
 
 
 class Params(C.Structure):

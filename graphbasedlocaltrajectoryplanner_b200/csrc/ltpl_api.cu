@@ -131,6 +131,7 @@ int ltpl_lattice_create(const LtplLatticeHeader* h, void* dev_blob, LtplLattice*
         return fail("ltpl_lattice_create: max_nodes_per_layer must be in [1, 64]");
     if (h->tab_stride < 3 || h->tab_stride > 255) return fail("ltpl_lattice_create: tab_stride must be in [3, 255]");
     if (h->num_layers < 4) return fail("ltpl_lattice_create: lattice needs at least 4 layers");
+    if (h->grid_nx < 1 || h->grid_ny < 1 || !(h->grid_inv_cell > 0.0)) return fail("ltpl_lattice_create: nearest-vertex grid missing");
     LtplLattice* lat = new (std::nothrow) LtplLattice;
     if (!lat) return fail("ltpl_lattice_create: out of host memory");
     lat->h = *h;
@@ -184,7 +185,17 @@ int ltpl_lattice_create(const LtplLatticeHeader* h, void* dev_blob, LtplLattice*
     LTPL_PTR(tab_reach, int, off_tab_reach);
     LTPL_PTR(tab_node, unsigned char, off_tab_node);
     LTPL_PTR(tab_edge, int, off_tab_edge);
+    LTPL_PTR(grid_center, int, off_grid_center);
+    LTPL_PTR(grid_refline, int, off_grid_refline);
+    LTPL_PTR(grid_raceline, int, off_grid_raceline);
+    LTPL_PTR(grid_glob, int, off_grid_glob);
 #undef LTPL_PTR
+    d.grid_nx = h->grid_nx;
+    d.grid_ny = h->grid_ny;
+    d.grid_cyclic = h->closed;
+    d.grid_x0 = h->grid_x0;
+    d.grid_y0 = h->grid_y0;
+    d.grid_inv_cell = h->grid_inv_cell;
     d.tab_stride = h->tab_stride;
     {  // follow table: one warp per node (k_follow_table), once per lattice
         const int maxn = ((h->max_nodes_per_layer + 31) / 32) * 32;

@@ -66,6 +66,14 @@ struct LatDev {
     const unsigned char* tab_node; // [Nn][tab_stride] node index per step
     const int* tab_edge;           // [Nn][tab_stride] edge id per step
     int tab_stride;
+    // nearest-vertex grids (lattice_blob.nearest_grid): cell -> (first << 6 | count) candidates that contain the nearest
+    // vertex of every position inside the cell
+    const int* grid_center;
+    const int* grid_refline;
+    const int* grid_raceline;
+    const int* grid_glob;
+    int grid_nx, grid_ny, grid_cyclic;
+    double grid_x0, grid_y0, grid_inv_cell;
 };
 
 #ifndef LTPL_DEFAULT_SUB
@@ -216,11 +224,38 @@ __device__ __noinline__ ArgMinD warp_closest_point(const double2* __restrict__ p
     return warp_argmin(bv, bi);
 }
 
+// the same argmin for one of the lattice's own polylines: the grid cell of (px, py) bounds the nearest vertex (and every
+// vertex tied with it) to <= 32 consecutive indices -> one distance per lane instead of a scan of the polyline; cells
+// without a bound (far from the track) fall back to the scan.  Exact by construction (lattice_blob.nearest_grid).
+__device__ __noinline__ ArgMinD warp_closest_point_grid(const LatDev& lt, const int* __restrict__ grid,
+                                                           const double2* __restrict__ pts, int n, double px, double py,
+                                                           int lane) {
+    const double fx = floor((px - lt.grid_x0) * lt.grid_inv_cell), fy = floor((py - lt.grid_y0) * lt.grid_inv_cell);
+    if (fx >= 0.0 && fy >= 0.0 && fx < (double)lt.grid_nx && fy < (double)lt.grid_ny) {
+        const int ent = grid[(int)fy * lt.grid_nx + (int)fx];
+        const int cnt = ent & 63;
+        if (cnt) {
+            int i = (ent >> 6) + lane;
+            if (lt.grid_cyclic && i >= n) i -= n;
+            double dv = LTPL_INF;
+            if (lane < cnt) {
+                const double2 p = pts[i];
+                dv = dist2_rn(p.x, p.y, px, py);
+            } else {
+                i = 0x7fffffff;
+            }
+            return warp_argmin(dv, i);
+        }
+    }
+    return warp_closest_point(pts, n, px, py, lane);
+}
+
 // get_s_coord.py:8-99 on a CLOSED polyline with explicit s_array (s_array[0] <= 0.05, i.e. no leading-zero insertion).
 // Warp-collective; returns the s coordinate; idx_out = closest_indexes (pair)
-__device__ __noinline__ double s_coord_closed(const double2* __restrict__ pts, const double* __restrict__ s_arr, int n,
+__device__ __noinline__ double s_coord_closed(const LatDev& lt, const int* __restrict__ grid,
+                                                 const double2* __restrict__ pts, const double* __restrict__ s_arr, int n,
                                                  double px, double py, int lane, int* i0_out, int* i1_out) {
-    ArgMinD m = warp_closest_point(pts, n, px, py, lane);
+    ArgMinD m = warp_closest_point_grid(lt, grid, pts, n, px, py, lane);
     int nb = m.i;
     int idx1 = nb - 1;  // python negative index -> last element
     int idx2 = nb + 1;
@@ -256,12 +291,82 @@ __device__ __noinline__ double s_coord_closed(const double2* __restrict__ pts, c
     return __dadd_rn(sbase, ds);
 }
 
+// ---- one query PER LANE -------------------------------------------------------------------------------------------
+// The searches of a scenario (constant-segment ends, every object, every disc) are independent of each other; run one
+// per lane, their dependent load -> compare -> load chains overlap instead of following each other warp-wide.
+// Nearest vertex of this lane's position (active lanes): the candidates of its grid cell, serially; lanes whose cell has
+// no bound are served one after the other by the warp-wide scan.
+__device__ __forceinline__ int lanes_closest_point(const LatDev& lt, const int* __restrict__ grid,
+                                                   const double2* __restrict__ pts, int n, double px, double py,
+                                                   bool active, int lane) {
+    int res = 0;
+    bool fb = false;
+    if (active) {
+        const double fx = floor((px - lt.grid_x0) * lt.grid_inv_cell), fy = floor((py - lt.grid_y0) * lt.grid_inv_cell);
+        int cnt = 0, first = 0;
+        if (fx >= 0.0 && fy >= 0.0 && fx < (double)lt.grid_nx && fy < (double)lt.grid_ny) {
+            const int ent = grid[(int)fy * lt.grid_nx + (int)fx];
+            cnt = ent & 63;
+            first = ent >> 6;
+        }
+        fb = (cnt == 0);
+        double bv = LTPL_INF;
+        int bi = 0x7fffffff;
+        #pragma unroll 1
+        for (int c = 0; c < cnt; ++c) {
+            int i = first + c;
+            if (lt.grid_cyclic && i >= n) i -= n;
+            const double2 p = pts[i];
+            const double dv = dist2_rn(p.x, p.y, px, py);
+            if (dv < bv || (dv == bv && i < bi)) {   // first minimum in INDEX order (the candidates may wrap)
+                bv = dv;
+                bi = i;
+            }
+        }
+        res = bi;
+    }
+    unsigned m = __ballot_sync(LTPL_FULL, fb);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const double qx = __shfl_sync(LTPL_FULL, px, src), qy = __shfl_sync(LTPL_FULL, py, src);
+        const ArgMinD r = warp_closest_point(pts, n, qx, qy, lane);
+        if (lane == src) res = r.i;
+    }
+    return res;
+}
+
+// get_s_coord.py:48-99 behind the nearest vertex nb (closed polyline, explicit s_array): per lane
+__device__ __forceinline__ double s_coord_from_vertex(const double2* __restrict__ pts, const double* __restrict__ s_arr,
+                                                      int n, int nb, double px, double py) {
+    int idx2 = nb + 1;
+    if (idx2 > n - 1) idx2 = 0;
+    const int a1 = (nb - 1 < 0) ? nb - 1 + n : nb - 1;
+    const double2 pn = pts[nb], p1 = pts[a1], p2 = pts[idx2];
+    double2 a, b;
+    double sbase;
+    if (angle_cmp(pn, px, py, p1, p2).gt) {
+        a = p1;
+        b = pn;
+        sbase = s_arr[a1];
+    } else {
+        a = pn;
+        b = p2;
+        sbase = s_arr[nb];
+    }
+    const double bax = b.x - a.x, bay = b.y - a.y;
+    const double t = __ddiv_rn(__dadd_rn(__dmul_rn(px - a.x, bax), __dmul_rn(py - a.y, bay)), __dadd_rn(sq_rn(bax), sq_rn(bay)));
+    const double sx = __dadd_rn(a.x, __dmul_rn(t, bax));
+    const double sy = __dadd_rn(a.y, __dmul_rn(t, bay));
+    return __dadd_rn(sbase, sqrt(__dadd_rn(sq_rn(a.x - sx), sq_rn(a.y - sy))));
+}
+
 // check_inside_bounds.py:26-59 (warp-collective)
 __device__ __noinline__ bool inside_bounds(const LatDev& lt, double px, double py, int lane) {
     int i0, i1;
     {
         // get_s_coord(centerline, pos, only_index=True, closed=True)[1]
-        ArgMinD m = warp_closest_point(lt.center, lt.L, px, py, lane);
+        ArgMinD m = warp_closest_point_grid(lt, lt.grid_center, lt.center, lt.L, px, py, lane);
         int nb = m.i, n = lt.L;
         int idx1 = nb - 1, idx2 = nb + 1;
         if (idx2 > n - 1) idx2 = 0;
@@ -300,6 +405,61 @@ __device__ __noinline__ bool inside_bounds(const LatDev& lt, double px, double p
     double d_track_2 = dist2_rn(b1x, b1y, b2x, b2y);
     double d_b1_2 = dist2_rn(b1x, b1y, px, py);
     double d_b2_2 = dist2_rn(b2x, b2y, px, py);
+    return !(d_b1_2 > d_track_2 || d_b2_2 > d_track_2);
+}
+
+// check_inside_bounds.py:26-59 behind the nearest centre-line vertex nb: per lane.  The argmin over the 50 linspace points
+// between the two centre-line vertices is taken over the six points around the foot of the perpendicular: the squared
+// distance is a convex quadratic in the point index, every other point is further by >= 2 (|c1 - c0| / 49)^2 (orders of
+// magnitude above the rounding of either evaluation); degenerate (nearly coincident) vertices scan all 50.
+__device__ __forceinline__ bool inside_bounds_from_vertex(const LatDev& lt, int nb, double px, double py) {
+    const int n = lt.L;
+    int idx2 = nb + 1;
+    if (idx2 > n - 1) idx2 = 0;
+    const int a1 = (nb - 1 < 0) ? nb - 1 + n : nb - 1;
+    int i0, i1;
+    {
+        const double2 pn = lt.center[nb], p1 = lt.center[a1], p2 = lt.center[idx2];
+        if (angle_cmp(pn, px, py, p1, p2).ge) {
+            i0 = a1;
+            i1 = nb;
+        } else {
+            i0 = nb;
+            i1 = idx2;
+        }
+    }
+    const double2 c0 = lt.center[i0], c1 = lt.center[i1];
+    const double2 u0 = lt.bound1[i0], u1 = lt.bound1[i1], w0 = lt.bound2[i0], w1 = lt.bound2[i1];
+    const double stx = __ddiv_rn(c1.x - c0.x, 49.0), sty = __ddiv_rn(c1.y - c0.y, 49.0);
+    const double ex = c1.x - c0.x, ey = c1.y - c0.y;
+    const double den = ex * ex + ey * ey;
+    int lo = 0, hi = 49;
+    if (den > 1e-6) {
+        double kc = ((px - c0.x) * ex + (py - c0.y) * ey) * fast_rcp(den) * 49.0;
+        kc = fmin(fmax(kc, 0.0), 49.0);
+        const int kf = (int)kc;
+        lo = max(kf - 2, 0);
+        hi = min(kf + 3, 49);
+    }
+    double bv = LTPL_INF;
+    int k = 0;
+    #pragma unroll 1
+    for (int j = lo; j <= hi; ++j) {
+        const double cx = (j == 49) ? c1.x : __dadd_rn(__dmul_rn((double)j, stx), c0.x);
+        const double cy = (j == 49) ? c1.y : __dadd_rn(__dmul_rn((double)j, sty), c0.y);
+        const double dv = dist2_rn(cx, cy, px, py);
+        if (dv < bv) {   // first minimum
+            bv = dv;
+            k = j;
+        }
+    }
+    const double b1x = (k == 49) ? u1.x : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(u1.x - u0.x, 49.0)), u0.x);
+    const double b1y = (k == 49) ? u1.y : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(u1.y - u0.y, 49.0)), u0.y);
+    const double b2x = (k == 49) ? w1.x : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(w1.x - w0.x, 49.0)), w0.x);
+    const double b2y = (k == 49) ? w1.y : __dadd_rn(__dmul_rn((double)k, __ddiv_rn(w1.y - w0.y, 49.0)), w0.y);
+    const double d_track_2 = dist2_rn(b1x, b1y, b2x, b2y);
+    const double d_b1_2 = dist2_rn(b1x, b1y, px, py);
+    const double d_b2_2 = dist2_rn(b2x, b2y, px, py);
     return !(d_b1_2 > d_track_2 || d_b2_2 > d_track_2);
 }
 

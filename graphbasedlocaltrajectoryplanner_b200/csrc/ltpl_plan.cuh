@@ -398,12 +398,10 @@ __device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, un
 
 // get_intersec_edges (GIE:36-63) for one disc: layer of the disc's centre (or -1 when outside the planning range) and
 // the (up to) two layer pairs pa -> pa+1, pb -> pb+1 whose edges the disc can block (-1: none)
-__device__ __forceinline__ int disc_pairs(const LatDev& lt, int lane, double ox, double oy, int p_start, int p_end,
-                                          int* pa, int* pb) {
+// (o = nearest reference-line layer of the disc's centre; per lane)
+__device__ __forceinline__ int disc_pairs(const LatDev& lt, int o, int p_start, int p_end, int* pa, int* pb) {
     *pa = -1;
     *pb = -1;
-    const ArgMinD m = warp_closest_point(lt.refline, lt.L, ox, oy, lane);
-    const int o = m.i;
     const int lo = 1;
     const bool in_rng = (p_start - lo <= o && o <= p_end + lo) ||
                         (p_start > p_end && (p_start - lo <= o || o <= p_end + lo));
@@ -483,11 +481,20 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         int n_in = bf.n_obj[b];
         if (n_in > dm.k_obj) n_in = dm.k_obj;
         bool over = false;
+        // on-track test of all objects at once: lane k = object k (k_obj <= 16)
+        unsigned in_mask;
+        {
+            const bool act = lane < n_in;
+            const double* o = bf.obj + ((size_t)b * dm.k_obj + (act ? lane : 0)) * 5;
+            const double ox = o[0], oy = o[1];
+            const int nb = lanes_closest_point(lt, lt.grid_center, lt.center, lt.L, ox, oy, act, lane);
+            in_mask = __ballot_sync(LTPL_FULL, act && inside_bounds_from_vertex(lt, nb, ox, oy));
+        }
         #pragma unroll 1
         for (int k = 0; k < n_in; ++k) {
             const double* o = bf.obj + ((size_t)b * dm.k_obj + k) * 5;
             const double ox = o[0], oy = o[1];
-            if (inside_bounds(lt, ox, oy, lane)) {
+            if ((in_mask >> k) & 1u) {
                 int np_k = -1;   // -1: built-in prediction
                 if (dm.k_pred > 0 && bf.n_pred) np_k = min(bf.n_pred[(size_t)b * dm.k_obj + k], dm.k_pred);
                 const int n_pd = (np_k < 0) ? 1 : np_k;
@@ -550,19 +557,18 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     // ---- obstacles -> blocked edges, closest object (GLNT:165-213) ----
     int closest_dist = -1, closest_idx = -1, con_layer = -1, con_node = -1;
     int my_pa = -1, my_pb = -1;  // lane d: layer pairs disc d can block
+    int my_layer = -1;           // lane d: nearest reference-line layer of disc d, -1 outside the planning range
+    __syncwarp();
+    {
+        const bool act = lane < n_disc;
+        const double ox = act ? ps->dx[lane] : 0.0, oy = act ? ps->dy[lane] : 0.0;
+        const int o = lanes_closest_point(lt, lt.grid_refline, lt.refline, lt.L, ox, oy, act, lane);
+        if (act) my_layer = disc_pairs(lt, o, start_layer, end_layer, &my_pa, &my_pb);
+    }
     #pragma unroll 1
     for (int v = 0; v < n_veh; ++v) {
-        const int d0 = ps->vd0[v], d1 = d0 + ps->vdn[v];
-        int obj_layer = -1;
-        #pragma unroll 1
-        for (int d = d0; d <= d1; ++d) {   // current position, then the prediction points: the LAST one sets obj_layer (q14)
-            int pa, pb;
-            obj_layer = disc_pairs(lt, lane, ps->dx[d], ps->dy[d], start_layer, end_layer, &pa, &pb);
-            if (lane == d) {
-                my_pa = pa;
-                my_pb = pb;
-            }
-        }
+        // current position, then the prediction points: the LAST one sets obj_layer (q14)
+        const int obj_layer = __shfl_sync(LTPL_FULL, my_layer, ps->vd0[v] + ps->vdn[v]);
         if (obj_layer >= 0) {
             int ld = obj_layer - start_layer;
             if (ld < 0) ld = lt.L - start_layer + obj_layer;
@@ -600,13 +606,24 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         // MOPG:80-84: pos_est of the previous calc_vel_profile call; None on the first tick -> first point of the segment
         const double sx0 = STATE ? bf.pos_last[2 * b] : cs[0], sy0 = STATE ? bf.pos_last[2 * b + 1] : cs[cplane];
         const double sxe = cs[p0 - 1], sye = cs[cplane + p0 - 1];
-        const double s_start = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sx0, sy0, lane, nullptr, nullptr);
-        const double s_end = s_coord_closed(lt.raceline, lt.s_rl, lt.L, sxe, sye, lane, nullptr, nullptr);
+        // s coordinates on the race line: lane 0 the start, lane 1 the end of the segment, lane 2 + v object v (n_veh <= 16)
+        double qx = sx0, qy = sy0;
+        if (lane == 1) {
+            qx = sxe;
+            qy = sye;
+        } else if (lane >= 2 && lane - 2 < n_veh) {
+            qx = ps->vx[lane - 2];
+            qy = ps->vy[lane - 2];
+        }
+        const bool q_act = lane < 2 + n_veh;
+        const int q_nb = lanes_closest_point(lt, lt.grid_raceline, lt.raceline, lt.L, qx, qy, q_act, lane);
+        const double s_mine = q_act ? s_coord_from_vertex(lt.raceline, lt.s_rl, lt.L, q_nb, qx, qy) : 0.0;
+        const double s_start = __shfl_sync(LTPL_FULL, s_mine, 0), s_end = __shfl_sync(LTPL_FULL, s_mine, 1);
         double smallest = LTPL_INF;
         #pragma unroll 1
         for (int v = 0; v < n_veh; ++v) {
             const double ox = ps->vx[v], oy = ps->vy[v];
-            const double s_obj = s_coord_closed(lt.raceline, lt.s_rl, lt.L, ox, oy, lane, nullptr, nullptr);
+            const double s_obj = __shfl_sync(LTPL_FULL, s_mine, 2 + v);
             if ((s_start <= s_obj && s_obj <= s_end) || (s_start > s_end && (s_obj > s_start || s_obj < s_end))) {
                 obj_beside = true;
                 double od;
@@ -632,7 +649,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     if (closest_idx >= 0) {
         const int ng = lt.n_glob - 1;
         const double ox = ps->vx[closest_idx], oy = ps->vy[closest_idx];
-        const ArgMinD m = warp_closest_point(lt.glob_xy, ng, ox, oy, lane);
+        const ArgMinD m = warp_closest_point_grid(lt, lt.grid_glob, lt.glob_xy, ng, ox, oy, lane);
         const int nb = m.i;
         const int i1 = (nb - 1 < 0) ? ng - 1 : nb - 1;
         const int i2 = (nb + 1 > ng - 1) ? 0 : nb + 1;

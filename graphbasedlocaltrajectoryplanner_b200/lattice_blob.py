@@ -72,6 +72,40 @@ def capacities(lat: Lattice) -> dict:
                 max_plan_layers=max_dist)
 
 
+GRID_CELL = 4.0        # m
+GRID_REACH = 60.0      # m: cells whose centre is further from the polyline get no bound (whole-polyline scan)
+GRID_MAX_COUNT = 32    # one vertex per lane
+
+
+def nearest_grid(pts: np.ndarray, closed: bool, x0: float, y0: float, nx: int, ny: int, cell: float = GRID_CELL) -> np.ndarray:
+    """int32 [ny][nx]: entry = first << 6 | count.  For EVERY position q inside cell (ix, iy) the nearest vertex of
+    ``pts`` -- and every vertex at the same distance, so np.argmin's first-minimum rule survives -- lies among the
+    ``count`` vertices first, first + 1, ... (indices modulo len(pts) when ``closed``).  Proof: with m the cell centre and
+    h its half diagonal, |d(q, v) - d(m, v)| <= h for all v, hence d(m, v*) <= min_v d(m, v) + 2 h for the nearest vertex
+    v* of q.  count = 0: no bound (far from the polyline, or the candidates span more than 32 indices)."""
+    n = pts.shape[0]
+    h = cell * np.sqrt(0.5)
+    cx = x0 + (np.arange(nx) + 0.5) * cell
+    cy = y0 + (np.arange(ny) + 0.5) * cell
+    out = np.zeros((ny, nx), dtype=np.int32)
+    for iy in range(ny):
+        dx = cx[:, None] - pts[None, :, 0]
+        dy = cy[iy] - pts[None, :, 1]
+        dist = np.sqrt(dx * dx + dy * dy)                       # (nx, n)
+        dmin = dist.min(axis=1)
+        for ix in np.nonzero(dmin <= GRID_REACH)[0]:
+            idx = np.nonzero(dist[ix] <= dmin[ix] + 2.0 * h + 1e-3)[0]
+            if closed and idx.size > 1:
+                gaps = np.diff(np.append(idx, idx[0] + n))      # cyclic distance to the next candidate
+                k = int(np.argmax(gaps))
+                first, count = int(idx[(k + 1) % idx.size]), int(n - gaps[k] + 1)
+            else:
+                first, count = int(idx[0]), int(idx[-1] - idx[0] + 1)
+            if count <= GRID_MAX_COUNT:
+                out[iy, ix] = (first << 6) | count
+    return out
+
+
 def pack_lattice(lat: Lattice) -> tuple:
     """returns (LatticeHeader, blob uint8 ndarray, capacities dict)."""
     cap = capacities(lat)
@@ -91,6 +125,22 @@ def pack_lattice(lat: Lattice) -> tuple:
     edge_rec = np.zeros(lat.num_edges, dtype=np.dtype([("cost", "<f8"), ("src", "<i4"), ("dst", "<i4")]))
     edge_rec["cost"], edge_rec["src"], edge_rec["dst"] = lat.edge_cost, lat.edge_src, lat.edge_dst
     tab_stride = int(cap["h_max"])
+    # nearest-vertex grids of the four polylines the online path searches for every object (cached on the lattice)
+    grids = getattr(lat, "_nearest_grids", None)
+    if grids is None:
+        allp = np.vstack((center, lat.refline, lat.raceline, glob6[:, 1:3]))
+        gx0, gy0 = (allp.min(axis=0) - GRID_REACH)
+        gnx, gny = (int(v) for v in np.ceil((allp.max(axis=0) + GRID_REACH - (gx0, gy0)) / GRID_CELL))
+        closed = bool(lat.closed)
+        grids = dict(x0=float(gx0), y0=float(gy0), nx=gnx, ny=gny,
+                     center=nearest_grid(center, closed, gx0, gy0, gnx, gny),
+                     refline=nearest_grid(lat.refline, closed, gx0, gy0, gnx, gny),
+                     raceline=nearest_grid(lat.raceline, closed, gx0, gy0, gnx, gny),
+                     glob=nearest_grid(np.ascontiguousarray(glob6[:, 1:3]), closed, gx0, gy0, gnx, gny))
+        try:
+            lat._nearest_grids = grids
+        except AttributeError:
+            pass
 
     sections = [
         ("off_node_off", lat.node_off.astype(np.int32)),
@@ -124,6 +174,10 @@ def pack_lattice(lat: Lattice) -> tuple:
         ("off_tab_reach", np.zeros(nn, dtype=np.int32)),
         ("off_tab_node", np.zeros(nn * tab_stride, dtype=np.uint8)),
         ("off_tab_edge", np.zeros(nn * tab_stride, dtype=np.int32)),
+        ("off_grid_center", grids["center"]),
+        ("off_grid_refline", grids["refline"]),
+        ("off_grid_raceline", grids["raceline"]),
+        ("off_grid_glob", grids["glob"]),
     ]
     h = capi.LatticeHeader()
     h.abi_version = capi.ABI_VERSION
@@ -137,6 +191,7 @@ def pack_lattice(lat: Lattice) -> tuple:
     h.max_window_edges = cap["max_window_edges"]
     h.max_pair_edges = max(int(np.diff(lat.edge_layer_off).max()), 1)
     h.tab_stride = tab_stride
+    h.grid_nx, h.grid_ny, h.grid_x0, h.grid_y0, h.grid_inv_cell = grids["nx"], grids["ny"], grids["x0"], grids["y0"], 1.0 / GRID_CELL
     h.lat_offset, h.lat_resolution, h.sampled_resolution = lat.lat_offset, lat.lat_resolution, lat.sampled_resolution
     h.vel_decrease_lat, h.veh_width, h.veh_length = lat.vel_decrease_lat, lat.veh_width, lat.veh_length
     h.virt_goal_node_cost, h.min_plan_horizon = lat.virt_goal_node_cost, lat.min_plan_horizon

@@ -83,8 +83,10 @@ typedef struct LtplLatticeHeader {
     int32_t max_window_edges;    /* max #edges inside any planning window (+1 layer)  */
     int32_t max_pair_edges;      /* max #edges between two consecutive layers         */
     int32_t tab_stride;          /* row length of the follow table (>= max plan layers + 2) */
+    int32_t grid_nx, grid_ny;    /* cells of the nearest-vertex grids (off_grid_*)                  */
     double lat_offset, lat_resolution, sampled_resolution, vel_decrease_lat, veh_width, veh_length;
     double virt_goal_node_cost, min_plan_horizon;
+    double grid_x0, grid_y0, grid_inv_cell; /* cell of (x, y) = floor((x - grid_x0) * grid_inv_cell), same for y */
     /* per layer [L] */
     uint64_t off_node_off;       /* int32 [L+1]                                       */
     uint64_t off_raceline_index; /* int32 [L]                                         */
@@ -121,6 +123,10 @@ typedef struct LtplLatticeHeader {
     uint64_t off_tab_reach;      /* int32 [Nn]             -- zero on input, filled   */
     uint64_t off_tab_node;       /* uint8 [Nn][tab_stride] -- by ltpl_lattice_create  */
     uint64_t off_tab_edge;       /* int32 [Nn][tab_stride] -- (k_follow_table)        */
+    /* nearest-vertex grids, int32 [grid_ny][grid_nx] each: entry = first << 6 | count: for every position inside the  */
+    /* cell the nearest vertex of the polyline (first minimum) is one of the count <= 32 vertices first, first + 1, ...  */
+    /* (cyclic on closed tracks); count = 0: no such bound, scan the whole polyline (lattice_blob.nearest_grid)         */
+    uint64_t off_grid_center, off_grid_refline, off_grid_raceline, off_grid_glob;
     uint64_t blob_bytes;
 } LtplLatticeHeader;
 

@@ -146,3 +146,32 @@ def test_zone_ids_and_masks_of_a_scenario_batch():
         ScenarioBatch.from_object_lists(np.zeros((1, 2)), np.zeros(1), np.ones(1), [[]], blocked_zones=[{"a": z1, "b": z2}])
     plain = ScenarioBatch.from_object_lists(np.zeros((2, 2)), np.zeros(2), np.ones(2), [[], []])
     assert plain.zones is None and plain.zone_key is None
+
+
+def test_nearest_vertex_grid_bounds_the_argmin():
+    """lattice_blob.nearest_grid: for random positions around the track the candidates of the position's cell contain
+    np.argmin's answer (first minimum) of the scan over the whole polyline -- closed and open track."""
+    from graphbasedlocaltrajectoryplanner_b200 import lattice_blob as LB
+    rng = np.random.default_rng(7)
+    for tag in ("l216", "open"):
+        lat = H.lattice_for(tag)
+        LB.pack_lattice(lat)
+        g = lat._nearest_grids
+        polys = dict(refline=lat.refline, raceline=lat.raceline, glob=np.ascontiguousarray(lat.glob_rl[:-1, 1:3]))
+        for name, pts in polys.items():
+            n = pts.shape[0]
+            q = pts[rng.integers(0, n, 4000)] + rng.normal(0.0, 10.0, (4000, 2))
+            q[:200] = pts[rng.integers(0, n, 200)]                       # exactly on vertices
+            ix = np.floor((q[:, 0] - g["x0"]) / LB.GRID_CELL).astype(int)
+            iy = np.floor((q[:, 1] - g["y0"]) / LB.GRID_CELL).astype(int)
+            ent = g[name][iy, ix]
+            cnt, first = ent & 63, ent >> 6
+            d2 = ((q[:, None, :] - pts[None]) ** 2).sum(-1)
+            full = d2.argmin(axis=1)
+            assert (cnt > 0).mean() > 0.95 and cnt.max() <= LB.GRID_MAX_COUNT
+            for i in np.nonzero(cnt > 0)[0]:
+                idx = first[i] + np.arange(cnt[i])
+                idx = idx % n if lat.closed else idx
+                assert idx.max() < n
+                dd = d2[i, idx]
+                assert idx[dd == dd.min()].min() == full[i], (tag, name, i)
