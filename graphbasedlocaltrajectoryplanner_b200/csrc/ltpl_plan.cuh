@@ -148,7 +148,7 @@ k_startpos(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplB
 struct DpCtx {
     double* dist;        // [2][maxn]
     double* dsave;       // [maxn] dist after step snap_li: prefix shared by the overtake-left / -right searches
-    unsigned char* pred; // [hl][maxn]  k-th in-edge of the node, 255 = unreachable
+    unsigned char* pred; // [hl][maxn]  predecessor (node index in the layer before) of the node, 255 = unreachable
     const int4* meta;    // [hl] per layer step li: (first node of the next layer, #nodes, first edge of the pair, #edges)
     int maxn;
     int cur;             // which half of dist holds the last completed layer
@@ -243,7 +243,7 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
         #pragma unroll 1
         for (int j = lane; j < maxn; j += 32) {
             double best = LTPL_INF, best_ds = LTPL_INF;
-            int best_k = 255;
+            int best_k = 255;   // start-layer node index of the chosen in-edge (255: unreachable)
             bool present = j < nl && !(nxt == rem_layer && j >= rem_lo && j < rem_hi);
             if (ZONE && present && zs) present = !((zs[(nbase + j) >> 5] >> ((nbase + j) & 31)) & 1u);
             if (present) {
@@ -268,7 +268,7 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
                     if (alt < best || (alt == best && ds < best_ds)) {
                         best = alt;
                         best_ds = ds;
-                        best_k = k;
+                        best_k = r.src;
                     } else if (alt == best && ds == best_ds) {
                         tie = 1;
                     }
@@ -295,6 +295,17 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
     c.layer = layer;
     c.tie = __any_sync(LTPL_FULL, tie) ? 1 : 0;
     return reach;
+}
+
+// the lattice edge (src node js of the layer before) -> (node jd of the layer whose first node is nbase); the lattice
+// holds at most one edge per node pair
+__device__ __forceinline__ int dp_edge_id(const LatDev& lt, int nbase, int jd, int js) {
+    const int2 io = lt.in_off[nbase + jd];
+    int e = io.x;
+    #pragma unroll 1
+    for (int k = 0; k < io.y; ++k)
+        if (lt.edge_src[io.x + k] == js) e = io.x + k;
+    return e;
 }
 
 // virtual goal node: argmin_j dist[j] + |raceline_index - j| * lat_resolution * w_virt_goal (GB:188)
@@ -480,62 +491,57 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     {
         int n_in = bf.n_obj[b];
         if (n_in > dm.k_obj) n_in = dm.k_obj;
-        bool over = false;
-        // on-track test of all objects at once: lane k = object k (k_obj <= 16)
-        unsigned in_mask;
-        {
-            const bool act = lane < n_in;
-            const double* o = bf.obj + ((size_t)b * dm.k_obj + (act ? lane : 0)) * 5;
-            const double ox = o[0], oy = o[1];
-            const int nb = lanes_closest_point(lt, lt.grid_center, lt.center, lt.L, ox, oy, act, lane);
-            in_mask = __ballot_sync(LTPL_FULL, act && inside_bounds_from_vertex(lt, nb, ox, oy));
+        // lane k = object k (k_obj <= 16): on-track test, radius, discs -- all objects at once; the on-track objects keep
+        // their order (vehicle index = number of on-track objects in front, disc index = their discs in front)
+        const bool act = lane < n_in;
+        const double* o = bf.obj + ((size_t)b * dm.k_obj + (act ? lane : 0)) * 5;
+        const double ox = o[0], oy = o[1];
+        const int nb = lanes_closest_point(lt, lt.grid_center, lt.center, lt.L, ox, oy, act, lane);
+        const bool inside = act && inside_bounds_from_vertex(lt, nb, ox, oy);
+        const unsigned in_mask = __ballot_sync(LTPL_FULL, inside);
+        int np_k = -1;   // -1: built-in prediction
+        if (inside && dm.k_pred > 0 && bf.n_pred) np_k = min(bf.n_pred[(size_t)b * dm.k_obj + lane], dm.k_pred);
+        const int n_pd = (np_k < 0) ? 1 : np_k;
+        const int mine = inside ? 1 + n_pd : 0;
+        int incl = mine;   // inclusive prefix sum of the disc counts
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int up = __shfl_up_sync(LTPL_FULL, incl, off);
+            if (lane >= off) incl += up;
         }
-        #pragma unroll 1
-        for (int k = 0; k < n_in; ++k) {
-            const double* o = bf.obj + ((size_t)b * dm.k_obj + k) * 5;
-            const double ox = o[0], oy = o[1];
-            if ((in_mask >> k) & 1u) {
-                int np_k = -1;   // -1: built-in prediction
-                if (dm.k_pred > 0 && bf.n_pred) np_k = min(bf.n_pred[(size_t)b * dm.k_obj + k], dm.k_pred);
-                const int n_pd = (np_k < 0) ? 1 : np_k;
-                if (n_disc + 1 + n_pd > LTPL_DMAX) {
-                    over = true;
-                    break;
-                }
-                if (lane == 0) {
-                    const double th = o[2], v = o[3], r = o[4] / 2.0;
-                    ps->vx[n_veh] = ox;
-                    ps->vy[n_veh] = oy;
-                    ps->vr[n_veh] = r;
-                    ps->vv[n_veh] = v;
-                    ps->vd0[n_veh] = n_disc;
-                    ps->vdn[n_veh] = n_pd;
-                    // obstacle_ref = (r + veh_width / 2)^2 + stepsize^2 / 4  (GB:626-629)
-                    const double ref = __dadd_rn(sq_rn(__dadd_rn(r, __ddiv_rn(lt.veh_width, 2.0))),
-                                                 __ddiv_rn(sq_rn(lt.step), 4.0));
-                    ps->dx[n_disc] = ox;
-                    ps->dy[n_disc] = oy;
-                    ps->dref[n_disc] = ref;
-                    if (np_k < 0) {
-                        ps->dx[n_disc + 1] = __dsub_rn(ox, __dmul_rn(__dmul_rn(sin(th), v), 0.2));
-                        ps->dy[n_disc + 1] = __dadd_rn(oy, __dmul_rn(__dmul_rn(cos(th), v), 0.2));
-                        ps->dref[n_disc + 1] = ref;
-                    } else {
-                        const double* pp = bf.obj_pred + (((size_t)b * dm.k_obj + k) * dm.k_pred) * 2;
-                        for (int j = 0; j < np_k; ++j) {
-                            ps->dx[n_disc + 1 + j] = pp[2 * j];
-                            ps->dy[n_disc + 1 + j] = pp[2 * j + 1];
-                            ps->dref[n_disc + 1 + j] = ref;
-                        }
-                    }
-                }
-                n_disc += 1 + n_pd;
-                ++n_veh;
-            }
-        }
-        if (over) {
+        n_disc = __shfl_sync(LTPL_FULL, incl, 31);
+        n_veh = __popc(in_mask);
+        if (n_disc > LTPL_DMAX) {   // (the reference has no limit; one warp ballot holds 32 discs)
             if (lane == 0) bf.sc_flags[b] = LTPL_SC_CAPACITY;
             return;
+        }
+        if (inside) {
+            const int v_i = __popc(in_mask & ((1u << lane) - 1u)), d_i = incl - mine;
+            const double th = o[2], v = o[3], r = o[4] / 2.0;
+            ps->vx[v_i] = ox;
+            ps->vy[v_i] = oy;
+            ps->vr[v_i] = r;
+            ps->vv[v_i] = v;
+            ps->vd0[v_i] = d_i;
+            ps->vdn[v_i] = n_pd;
+            // obstacle_ref = (r + veh_width / 2)^2 + stepsize^2 / 4  (GB:626-629)
+            const double ref = __dadd_rn(sq_rn(__dadd_rn(r, __ddiv_rn(lt.veh_width, 2.0))),
+                                         __ddiv_rn(sq_rn(lt.step), 4.0));
+            ps->dx[d_i] = ox;
+            ps->dy[d_i] = oy;
+            ps->dref[d_i] = ref;
+            if (np_k < 0) {
+                ps->dx[d_i + 1] = __dsub_rn(ox, __dmul_rn(__dmul_rn(sin(th), v), 0.2));
+                ps->dy[d_i + 1] = __dadd_rn(oy, __dmul_rn(__dmul_rn(cos(th), v), 0.2));
+                ps->dref[d_i + 1] = ref;
+            } else {
+                const double* pp = bf.obj_pred + (((size_t)b * dm.k_obj + lane) * dm.k_pred) * 2;
+                for (int j = 0; j < np_k; ++j) {
+                    ps->dx[d_i + 1 + j] = pp[2 * j];
+                    ps->dy[d_i + 1 + j] = pp[2 * j + 1];
+                    ps->dref[d_i + 1 + j] = ref;
+                }
+            }
         }
     }
     #pragma unroll 1
@@ -845,21 +851,25 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
                 }
                 nd[2 * cnd] = start_layer;
                 nd[2 * cnd + 1] = start_node;
-                if (src == 1) {
+                if (src == 1) {   // node sequence: a chain through the predecessor table in shared memory
                     int j = gj, layer = c.layer;
                     #pragma unroll 1
                     for (int li = reach; li >= 1; --li) {
                         nd[2 * (li + cnd)] = layer;
                         nd[2 * (li + cnd) + 1] = j;
-                        const int e = lt.in_off[lt.node_off[layer] + j].x + (int)pred[li * maxn + j];
-                        es[li - 1] = e;
-                        j = lt.edge_src[e];
+                        j = pred[li * maxn + j];
                         layer = (layer == 0) ? lt.L - 1 : layer - 1;
                     }
                 }
                 bf.n_nodes[q] = reach + 1 + cnd;
                 bf.action_id[q] = name;
                 bf.status[q] = st;
+            }
+            if (src == 1) {   // edge ids of all steps at once (lane = step)
+                __syncwarp();
+                #pragma unroll 1
+                for (int li = 1 + lane; li <= reach; li += 32)
+                    es[li - 1] = dp_edge_id(lt, meta[li].x, __ldcg(&nd[2 * (li + cnd) + 1]), __ldcg(&nd[2 * (li - 1 + cnd) + 1]));
             }
         } else if (lane == 0 && bf.action_id[q] == LTPL_ACT_NONE) {
             bf.status[q] = st;
@@ -940,15 +950,18 @@ k_follow_table(const LatDev lt, const int maxn, int* tab_reach, unsigned char* t
     int gj = 0;
     if (reach >= 1) gj = dp_goal(lt, lane, c, &tie);
     if (lane == 0) {
-        int j = gj, layer = c.layer;
+        int j = gj;
         #pragma unroll 1
         for (int li = reach; li >= 1; --li) {
-            const int e = lt.in_off[lt.node_off[layer] + j].x + (int)pred[li * maxn + j];
             tab_node[(size_t)n * hl + li - 1] = (unsigned char)j;
-            tab_edge[(size_t)n * hl + li - 1] = e;
-            j = lt.edge_src[e];
-            layer = (layer == 0) ? lt.L - 1 : layer - 1;
+            j = pred[li * maxn + j];
         }
         tab_reach[n] = reach | (tie << 8);
+    }
+    __syncwarp();
+    #pragma unroll 1
+    for (int li = 1 + lane; li <= reach; li += 32) {
+        const int js = (li == 1) ? start_node : (int)__ldcg(&tab_node[(size_t)n * hl + li - 2]);
+        tab_edge[(size_t)n * hl + li - 1] = dp_edge_id(lt, meta[li].x, (int)__ldcg(&tab_node[(size_t)n * hl + li - 1]), js);
     }
 }

@@ -125,6 +125,11 @@ def pack_lattice(lat: Lattice) -> tuple:
     edge_rec = np.zeros(lat.num_edges, dtype=np.dtype([("cost", "<f8"), ("src", "<i4"), ("dst", "<i4")]))
     edge_rec["cost"], edge_rec["src"], edge_rec["dst"] = lat.edge_cost, lat.edge_src, lat.edge_dst
     tab_stride = int(cap["h_max"])
+    # the device back-track identifies an edge by its (source node, destination node): one edge per node pair
+    e_layer = np.repeat(np.arange(lat.num_layers, dtype=np.int64), np.diff(lat.edge_layer_off))
+    key = (e_layer * 64 + lat.edge_src.astype(np.int64)) * 64 + lat.edge_dst.astype(np.int64)
+    if np.unique(key).size != key.size:
+        raise ValueError("lattice holds parallel edges between one pair of nodes")
     # nearest-vertex grids of the four polylines the online path searches for every object (cached on the lattice)
     grids = getattr(lat, "_nearest_grids", None)
     if grids is None:
