@@ -6,8 +6,9 @@
 #include "ltpl_plan.cuh"
 
 __host__ __device__ inline size_t path_smem_bytes_per_warp(int h_max) {
-    // doubles: px, py, el, mx, my, cp, dx, dy  (h_max each) ; ints: nidx, eid, nsamp (h_max each)
-    size_t s = sizeof(double) * 8 * (size_t)h_max + sizeof(int) * 3 * (size_t)h_max;
+    // doubles: px, py, el, mx, my, cp, dx, dy + five more rows of the tridiagonal solve (h_max each) ;
+    // ints: nidx, eid, nsamp, soff (h_max each)
+    size_t s = sizeof(double) * 13 * (size_t)h_max + sizeof(int) * 4 * (size_t)h_max;
     return (s + 15) & ~(size_t)15;
 }
 
@@ -46,9 +47,11 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     double* cp = my + H;
     double* dxp = cp + H;
     double* dyp = dxp + H;
-    int* nidx = reinterpret_cast<int*>(dyp + H);
+    double* pcr = dyp + H;   // [5][H]
+    int* nidx = reinterpret_cast<int*>(pcr + 5 * H);
     int* eid = nidx + H;
     int* nsamp = eid + H;
+    int* soff = nsamp + H;   // first sample of every edge
 
     const int p0 = bf.const_len[b];
     const size_t pplane = (size_t)LTPL_NSLOT * B * dm.p_max;
@@ -97,26 +100,37 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     const int* es = bf.edge_seq + (size_t)q * H;
     for (int i = lane; i < nseg; i += 32) {
         const int e = es[i];
+        const int so0 = lt.samp_off[e], so1 = lt.samp_off[e + 1];
         eid[i] = e;
-        nsamp[i] = lt.samp_off[e + 1] - lt.samp_off[e];
+        soff[i] = so0;
+        nsamp[i] = so1 - so0;
         kel[i] = lt.edge_len[e];
-        const double2 p = lt.samp_xy[lt.samp_off[e]];
+        const double2 p = lt.samp_xy[so0];
         kx[i] = p.x;
         ky[i] = p.y;
         if (i == nseg - 1) {
-            const double2 pl = lt.samp_xy[lt.samp_off[e + 1] - 1];
+            const double2 pl = lt.samp_xy[so1 - 1];
             kx[nseg] = pl.x;
             ky[nseg] = pl.y;
         }
     }
     __syncwarp();
-    if (lane == 0) {  // exclusive prefix sum of (n_i - 1): index of every node in the fused sample array
-        int acc = 0;
-        for (int i = 0; i < nseg; ++i) {
-            nidx[i] = acc;
-            acc += nsamp[i] - 1;
+    {   // exclusive prefix sum of (n_i - 1): index of every node in the fused sample array (warp scan, 32 segments a round)
+        int carry = 0;
+        #pragma unroll 1
+        for (int i0 = 0; i0 < nseg; i0 += 32) {
+            const int i = i0 + lane;
+            const int v = (i < nseg) ? nsamp[i] - 1 : 0;
+            int inc = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int up = __shfl_up_sync(LTPL_FULL, inc, off);
+                if (lane >= off) inc += up;
+            }
+            if (i < nseg) nidx[i] = carry + inc - v;
+            carry += __shfl_sync(LTPL_FULL, inc, 31);
         }
-        nidx[nseg] = acc;  // last node sits on the last sample
+        if (lane == 0) nidx[nseg] = carry;  // last node sits on the last sample
     }
     __syncwarp();
     const int p_new = nidx[nseg] + 1;
@@ -138,13 +152,28 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     const double psi_s = (STATE && p0 == 0) ? lt.edge_psi0[eid[0]] : cs[2 * cplane + p0 - 1];
     const double psi_e = lt.edge_psi1[eid[nseg - 1]];       // MOPG:307: psi of the last sample
     // rows k = 1 .. nseg-1:  (2/el[k-1]) m[k-1] + 4 (1/el[k-1] + 1/el[k]) m[k] + (2/el[k]) m[k+1] = r[k]
-    // The rows themselves (lo, r_x, r_y; di and up follow from lo) do not depend on the elimination: all lanes build
-    // them in parallel, so that the serial Thomas sweep on lanes 0 / 1 is left with one reciprocal per row.
+    // solved by PARALLEL CYCLIC REDUCTION: every row eliminates its two neighbours at distance s = 1, 2, 4, ...; after
+    // ceil(log2(n)) rounds the rows are decoupled.  All lanes work in every round (a Thomas sweep is n dependent steps on
+    // one lane per right-hand side); the system is strictly diagonally dominant (4 : 1 : 1), so the reduction is as stable
+    // as the elimination (agreement with tph's dense LAPACK solve <= 1e-13, tests compare the coefficients at 1e-6).
     // tangents (cos, sin)(psi + pi / 2) = (-sin psi, cos psi): one sincos per heading
     double sn_s, cs_s, sn_e, cs_e;
     sincos(psi_s, &sn_s, &cs_s);
     sincos(psi_e, &sn_e, &cs_e);
     const double m0x = -sn_s, m0y = cs_s, mex = -sn_e, mey = cs_e;
+    const int n = nseg - 1;
+    // two sets of rows (a, b, c, x, y) used alternately (set 1 borrows mx / my for its right-hand sides); the tangents
+    // are written to mx / my at the end
+    double* A0 = cp;
+    double* B0 = dxp;
+    double* C0 = dyp;
+    double* X0 = pcr;
+    double* Y0 = pcr + H;
+    double* A1 = pcr + 2 * H;
+    double* B1 = pcr + 3 * H;
+    double* C1 = pcr + 4 * H;
+    double* X1 = mx;
+    double* Y1 = my;
     for (int k = 1 + lane; k < nseg; k += 32) {
         const double i0 = fast_rcp(kel[k - 1]), i1 = fast_rcp(kel[k]);
         const double lo = 2.0 * i0, up = 2.0 * i1;
@@ -158,40 +187,56 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             rx -= up * mex;
             ry -= up * mey;
         }
-        cp[k] = lo;   // lower diagonal of row k (== upper diagonal of row k - 1); replaced by c' in the sweep
-        dxp[k] = rx;
-        dyp[k] = ry;
+        A0[k] = (k == 1) ? 0.0 : lo;
+        B0[k] = 2.0 * (lo + up);
+        C0[k] = (k == nseg - 1) ? 0.0 : up;
+        X0[k] = rx;
+        Y0[k] = ry;
+    }
+    __syncwarp();
+    #pragma unroll 1
+    for (int sd = 1; sd < n; sd <<= 1) {
+        for (int k = 1 + lane; k <= n; k += 32) {
+            double a = 0.0, c = 0.0, bb = B0[k], x = X0[k], y = Y0[k];
+            if (k - sd >= 1) {
+                const double al = -A0[k] * fast_rcp(B0[k - sd]);
+                a = al * A0[k - sd];
+                bb += al * C0[k - sd];
+                x += al * X0[k - sd];
+                y += al * Y0[k - sd];
+            }
+            if (k + sd <= n) {
+                const double ga = -C0[k] * fast_rcp(B0[k + sd]);
+                c = ga * C0[k + sd];
+                bb += ga * A0[k + sd];
+                x += ga * X0[k + sd];
+                y += ga * Y0[k + sd];
+            }
+            A1[k] = a;
+            B1[k] = bb;
+            C1[k] = c;
+            X1[k] = x;
+            Y1[k] = y;
+        }
+        __syncwarp();
+        double* t;
+        t = A0; A0 = A1; A1 = t;
+        t = B0; B0 = B1; B1 = t;
+        t = C0; C0 = C1; C1 = t;
+        t = X0; X0 = X1; X1 = t;
+        t = Y0; Y0 = Y1; Y1 = t;
+    }
+    for (int k = 1 + lane; k <= n; k += 32) {
+        const double inv = fast_rcp(B0[k]);
+        const double vx = X0[k] * inv, vy = Y0[k] * inv;
+        mx[k] = vx;
+        my[k] = vy;
     }
     if (lane == 0) {
         mx[0] = m0x;
         my[0] = m0y;
         mx[nseg] = mex;
         my[nseg] = mey;
-    }
-    __syncwarp();
-    if (lane < 2 && nseg > 1) {
-        double* m = (lane == 0) ? mx : my;
-        double* dp = (lane == 0) ? dxp : dyp;
-        // forward sweep; lo[k] is read before lane 0 overwrites cp[k] with c'[k] (both lanes run in lock step and the
-        // value is taken into a register first), up[k] = lo[k + 1]
-        double cprev = 0.0, dprev = 0.0;
-        double lo = cp[1];
-        for (int k = 1; k < nseg; ++k) {
-            const double up = (k + 1 < nseg) ? cp[k + 1] : 2.0 * fast_rcp(kel[k]);
-            const double di = 2.0 * (lo + up);
-            const double inv = fast_rcp((k == 1) ? di : (di - lo * cprev));
-            const double cc = (k == nseg - 1) ? 0.0 : up * inv;
-            const double dd = ((k == 1) ? dp[k] : (dp[k] - lo * dprev)) * inv;
-            __syncwarp(0x3);
-            if (lane == 0) cp[k] = cc;
-            dp[k] = dd;
-            cprev = cc;
-            dprev = dd;
-            lo = up;
-        }
-        __syncwarp(0x3);
-        m[nseg - 1] = dp[nseg - 1];
-        for (int k = nseg - 2; k >= 1; --k) m[k] = dp[k] - cp[k] * m[k + 1];
     }
     __syncwarp();
 
@@ -201,11 +246,9 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         for (int i = lane; i < cnd; i += 32) node_idx[i] = mem_ni[i] - mem_m;
         for (int i = lane; i < cnd * 8; i += 32) coeff[i] = mem_cf[i];
     }
+    if (!STATE && lane < 8) coeff[lane] = bf.const_coeff[(size_t)b * 8 + lane];
     if (lane == 0) {
-        if (!STATE) {
-            node_idx[0] = 0;
-            for (int c = 0; c < 8; ++c) coeff[c] = bf.const_coeff[(size_t)b * 8 + c];
-        }
+        if (!STATE) node_idx[0] = 0;
         bf.path_len[q] = p_tot;
         enqueue_path(bf, dm, q);
     }
@@ -219,8 +262,14 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         c[4] = ky[i]; c[5] = a1y; c[6] = 3 * dy - 2 * a1y - e1y; c[7] = -2 * dy + a1y + e1y;
     }
     // constant part (OTH:442-444): everything but the last point of the constant segment
-    for (int k = lane; k < loc; k += 32)
-        for (int c = 0; c < 5; ++c) pp[c * pplane + k] = cs[c * cplane + k];
+    for (int k = lane; k < loc; k += 32) {   // (five loads in flight, then five stores)
+        const double v0 = cs[k], v1 = cs[cplane + k], v2 = cs[2 * cplane + k], v3 = cs[3 * cplane + k], v4 = cs[4 * cplane + k];
+        pp[k] = v0;
+        pp[pplane + k] = v1;
+        pp[2 * pplane + k] = v2;
+        pp[3 * pplane + k] = v3;
+        pp[4 * pplane + k] = v4;
+    }
     __syncwarp();
 
     // ---- re-evaluation at the per-edge sample counts (MOPG:312-322); el column keeps the offline chords (q2) ----
@@ -236,6 +285,7 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         const int i = lo_i;
         const int k = p - nidx[i];
         const int n_i = nsamp[i];
+        const double el_off = lt.samp_el[soff[i] + k];   // (issued before the arithmetic that hides its latency)
         const double e0 = kel[i];
         const double dx = kx[i + 1] - kx[i], dy = ky[i + 1] - ky[i];
         const double a0x = kx[i], a1x = e0 * mx[i], e1x = e0 * mx[i + 1];
@@ -259,6 +309,6 @@ k_path(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         pp[1 * pplane + o] = y;
         pp[2 * pplane + o] = psi;
         pp[3 * pplane + o] = kap;
-        pp[4 * pplane + o] = lt.samp_el[lt.samp_off[eid[i]] + k];
+        pp[4 * pplane + o] = el_off;
     }
 }
