@@ -130,20 +130,17 @@ __device__ __forceinline__ float vr_tire(const VRCfg& c, float w, float K, float
     return vr_tire_pow(w * K, ax, c.exp_, c.inv_exp);
 }
 
-// Forward sweep of one lane's profile on points [lo, hi] of its path (K, E2, W: the path's shared-memory rows).
-//   profile lanes: tph.__solver_fb_acc_profile(backwards=False): start value min(curvature limit, wcap), acceleration
-//                  phases from the rising edges of the curvature-limit profile, end clamp we (< 0: none);
-//   brake lanes:   tph.calc_vel_profile_brake: full braking from wcap, zeros after standstill.
-// ONE branch-free step (selects) serves both kinds, so a warp that holds both advances them together.  The machine
-// limit is a table segment cached in registers; v moves slowly, and when a lane leaves its segment the WHOLE warp takes
-// one step to the neighbouring segment (warp-uniform branch: a miss never serialises lanes).
-// BRAKE: the warp also carries brake lanes (follow, warp 0); without them the step has no brake selects at all.
+// Forward sweep of one lane's profile on points [lo, hi] of its path (K, E2, W: the path's shared-memory rows):
+// tph.__solver_fb_acc_profile(backwards=False): start value min(curvature limit, wcap), acceleration phases from the
+// rising edges of the curvature-limit profile, end clamp we (< 0: none).  The step is branch-free (selects).  The
+// machine limit is a table segment cached in registers; v moves slowly, and when a lane leaves its segment the WHOLE
+// warp takes one step to the neighbouring segment (warp-uniform branch: a miss never serialises lanes).
+// (pure brake profiles: vr_brake below)
 // GG: per-point longitudinal tyre limit AX[] (location dependent local_gg), else the constant c.ax_max
-template <bool EXP1, bool BRAKE, bool GG>
-__device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane, const float* __restrict__ K,
+template <bool EXP1, bool GG>
+__device__ __noinline__ void vr_forward(const VRCfg c, bool on, const float* __restrict__ K,
                                         const float* __restrict__ E2, const float* __restrict__ AX, float* __restrict__ W,
                                         int lo, int hi, float wcap, float we, float wmax, int nmax) {
-    const bool brake = BRAKE && brake_lane;
     const int len = (on && hi >= lo) ? hi - lo : -1;
     int lmax = len;
 #pragma unroll
@@ -151,15 +148,10 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
     if (lmax < 0) return;
     if (len < 0) lo = 0;
     float k_prev = K[lo], ax_prev = GG ? AX[lo] : c.ax_max;
-    float cur = brake ? wcap : fminf(fminf(vr_rcp(k_prev), wmax), wcap);
-    // A brake profile approaches w = 0 from large values: the absolute rounding of an fp32 accumulator (1e-3 after 100
-    // steps from 60 m/s) would be several mm/s in v just before standstill.  Brake lanes therefore ACCUMULATE in
-    // float64 (the acceleration itself stays fp32: its error enters scaled by the step).
-    double cur64 = (double)cur;
+    float cur = fminf(fminf(vr_rcp(k_prev), wmax), wcap);
     if (len >= 0) W[lo] = cur;
     float o_prev = cur;
-    bool prev_rise = false, active = brake;
-    if (brake) wmax = CUDART_INF_F;
+    bool prev_rise = false, active = false;
     int sg = 1;   // cached table segment
     float xlo = c.xl[1], xhi = c.xl[2], x0 = c.x0[1], f0 = c.f0[1], sl = c.sl[1];
     // lanes whose profile has ended keep stepping on clamped indices without storing: no select in the step needs `live`
@@ -169,11 +161,11 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
         const bool live = i <= len;
         const int p = min(lo + i, pcap);
         const float kq = K[p], e2 = E2[p - 1];
-        const float o_n = brake ? CUDART_INF_F : fminf(vr_rcp(kq), wmax);
+        const float o_n = fminf(vr_rcp(kq), wmax);
         const bool rise = o_n > o_prev;
         active = active || (rise && !prev_rise);
         const float v = vr_sqrt(fmaxf(cur, 0.0f));
-        const bool need = live && active && !brake;   // machine limit: only inside an acceleration phase
+        const bool need = live && active;   // machine limit: only inside an acceleration phase
         bool miss = need && !(v >= xlo && v < xhi);
         while (__any_sync(LTPL_FULL, miss)) {
             if (miss) sg += (v >= xhi) ? 1 : -1;
@@ -186,19 +178,48 @@ __device__ __noinline__ void vr_forward(const VRCfg c, bool on, bool brake_lane,
         }
         const float a_t = vr_tire<EXP1>(c, cur, k_prev, ax_prev);
         const float a_m = fmaf(sl, v - x0, f0);                              // mode 'accel_forw': min(tyre, machine(v))
-        const float a_sel = brake ? -a_t : fminf(a_t, a_m);
-        const float a = fmaf(-cur, c.dm, a_sel);                             // + drag
+        const float a = fmaf(-cur, c.dm, fminf(a_t, a_m));                   // + drag
         const float wn = fmaf(a, e2, cur);
-        float nxt = active ? fminf(wn, o_n) : o_n;
-        if (BRAKE && brake) {   // negative radicand: standstill, the rest of the profile stays 0
-            cur64 = fmax(cur64 + (double)a * (double)e2, 0.0);
-            nxt = (float)cur64;
-        }
+        const float nxt = active ? fminf(wn, o_n) : o_n;
         active = active && !(wn > wmax);
         if (live) W[p] = nxt;
         cur = nxt;
         prev_rise = rise;
         o_prev = o_n;
+        k_prev = kq;
+        if (GG) ax_prev = AX[p];
+    }
+    if (len >= 0 && we >= 0.0f && W[hi] > we) W[hi] = we;
+}
+// Forward sweep of a pure brake profile (tph.calc_vel_profile_brake, mode 'decel_forw': -tyre + drag from wcap on): the
+// step of vr_forward for a brake lane without everything a brake lane does not use (curvature cap, acceleration phases,
+// machine limit and its sqrt / vote) -- same arithmetic, shorter chain.
+template <bool EXP1, bool GG>
+__device__ __noinline__ void vr_brake(const VRCfg c, bool on, const float* __restrict__ K, const float* __restrict__ E2,
+                                      const float* __restrict__ AX, float* __restrict__ W, int lo, int hi, float wcap,
+                                      float we, int nmax) {
+    const int len = (on && hi >= lo) ? hi - lo : -1;
+    int lmax = len;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(LTPL_FULL, lmax, o));
+    if (lmax < 0) return;
+    if (len < 0) lo = 0;
+    float k_prev = K[lo], ax_prev = GG ? AX[lo] : c.ax_max;
+    float cur = wcap;
+    // A brake profile approaches w = 0 from large values: the absolute rounding of an fp32 accumulator (1e-3 after 100
+    // steps from 60 m/s) would be several mm/s in v just before standstill.  It therefore ACCUMULATES in float64 (the
+    // acceleration itself stays fp32: its error enters scaled by the step).
+    double cur64 = (double)cur;
+    if (len >= 0) W[lo] = cur;
+    const int pcap = nmax - 1;
+#pragma unroll 2
+    for (int i = 1; i <= lmax; ++i) {
+        const int p = min(lo + i, pcap);
+        const float kq = K[p], e2 = E2[p - 1];
+        const float a = fmaf(-cur, c.dm, -vr_tire<EXP1>(c, cur, k_prev, ax_prev));
+        cur64 = fmax(cur64 + (double)a * (double)e2, 0.0);   // negative radicand: standstill, the rest stays 0
+        cur = (float)cur64;
+        if (i <= len) W[p] = cur;
         k_prev = kq;
         if (GG) ax_prev = AX[p];
     }
@@ -771,9 +792,9 @@ k_vel_res(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBu
         }
 
         if (fw1 && round == 0) {
-            vr_forward<EXP1, true, GG>(c, on, true, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
+            vr_brake<EXP1, GG>(c, on, Kp, E2, AXp, W, lo, hi, wcap, we, nmax);
         } else {
-            vr_forward<EXP1, false, GG>(c, on, false, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
+            vr_forward<EXP1, GG>(c, on, Kp, E2, AXp, W, lo, hi, wcap, we, wmx, nmax);
             if (fw0 && round == 0) {
                 LTPL_PH(3)
             }
