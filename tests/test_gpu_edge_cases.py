@@ -158,3 +158,49 @@ def test_c_abi_error_convention():
     assert rc < 0 and b"null" in pl.lib.ltpl_last_error()
     pl.tick()                                             # still usable afterwards
     assert pl.launch_count() > n0
+
+
+def test_tick_under_cuda_graph_capture_replays_identically():
+    """a tick (three scenario windows = fork / join over the library's internal streams) captured into a CUDA graph
+    and replayed gives the bytes of the eager tick (rows of the compact export compared through traj_row)."""
+    import torch
+    from graphbasedlocaltrajectoryplanner_b200.scenarios import Track, make_scenarios
+    g = H.golden("ticks_default.npz")
+    sc = make_scenarios(Track(H.TRACK_CSV), 300, seed=77, n_obj_min=0, n_obj_max=3)
+    pl = _planner("default")
+    pl.set_subbatches(3)
+    pl.set_vel_params(ax_max_machines=g["ax_max_machines"], incl_emerg_traj=True, **VEL)
+    pl.stage_scenarios(sc)
+    pl.upload()
+    pl.set_startpos()
+    names = ("action_id", "status", "n_nodes", "nodes", "path_len", "traj_len", "traj_row", "traj", "em_info", "sc_flags")
+
+    def snapshot():
+        torch.cuda.synchronize()
+        f = pl.fetch(*names)
+        ok = f["traj_row"] >= 0
+        rows = np.zeros(f["traj_row"].shape + f["traj"].shape[1:], dtype=np.float32)
+        rows[ok] = f["traj"][f["traj_row"][ok]]
+        rows[np.arange(rows.shape[2])[None, None, :] >= f["traj_len"][..., None]] = 0.0
+        nodes = f["nodes"].copy()
+        nodes[np.arange(nodes.shape[2])[None, None, :] >= f["n_nodes"][..., None]] = -1
+        em = f["em_info"].copy()
+        em_rows = f["traj"][np.maximum(em[:, 0], 0)] * (em[:, 0] >= 0)[:, None, None]
+        return dict(action_id=f["action_id"], status=f["status"], nodes=nodes, path_len=f["path_len"],
+                    traj_len=f["traj_len"], rows=rows, em_len=em[:, 1], em_rows=em_rows, flags=f["sc_flags"])
+
+    pl.tick()                                   # eager (also the warm-up that sets the kernels' attributes)
+    want = snapshot()
+    assert (want["traj_len"] > 0).sum() > 300
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        pl.tick()                               # launches on the capturing stream (torch's current stream)
+    torch.cuda.current_stream().wait_stream(side)
+    for name in ("traj", "traj_row", "traj_len", "action_id", "status"):   # the replay has to produce everything again
+        pl.t[name].zero_()
+    graph.replay()
+    got = snapshot()
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
