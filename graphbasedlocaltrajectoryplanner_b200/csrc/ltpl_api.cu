@@ -83,25 +83,22 @@ static const char* launch_k_plan(const LtplLattice* lat, const LtplParams* prm, 
     const int mask_words = (lat->h.max_window_edges + 31) / 32 + 1;
     const size_t smem = plan_smem_bytes_per_warp(maxn, hl, mask_words) * LTPL_WARPS_PER_CTA;
     if (smem > 200 * 1024) return "lattice window too large for shared memory";
+    const bool zone = dm->n_zones > 0;
+    const bool dense = lat->h.num_edges >= 2 * lat->h.num_nodes;   // in-edges per node (dp_run<.., DENSE>)
+    typedef void (*PlanFn)(const LatDev, const LtplParams, const LtplDims, const LtplBuffers, const int, const int, const int);
+    static const PlanFn fns[8] = {k_plan<false, false, false>, k_plan<true, false, false>, k_plan<false, true, false>,
+                                  k_plan<true, true, false>,   k_plan<false, false, true>, k_plan<true, false, true>,
+                                  k_plan<false, true, true>,   k_plan<true, true, true>};
     static thread_local size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
-        if (cudaFuncSetAttribute(k_plan<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(k_plan<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(k_plan<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(k_plan<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return "cudaFuncSetAttribute(k_plan) failed";
+        for (PlanFn f : fns)
+            if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return "cudaFuncSetAttribute(k_plan) failed";
         attr = smem;
     }
     const int grid = (dm->sub_cnt + LTPL_WARPS_PER_CTA - 1) / LTPL_WARPS_PER_CTA, thr = LTPL_WARPS_PER_CTA * 32;
-    const bool zone = dm->n_zones > 0;
-    if (zone && stateful)
-        k_plan<true, true><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
-    else if (zone)
-        k_plan<true, false><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
-    else if (stateful)
-        k_plan<false, true><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
-    else
-        k_plan<false, false><<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl, mask_words);
+    fns[(zone ? 1 : 0) + (stateful ? 2 : 0) + (dense ? 4 : 0)]<<<grid, thr, smem, st>>>(lat->d, *prm, *dm, *bf, maxn, hl,
+                                                                                        mask_words);
     return nullptr;
 }
 

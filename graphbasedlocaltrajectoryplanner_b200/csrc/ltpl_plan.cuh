@@ -210,7 +210,9 @@ __device__ __forceinline__ bool zone_unblocked(int l, int s0, int L) {
 // li_begin are those of the run that took the snapshot).  After step snap_at the state is saved to c.dsave.
 // Each lane owns one node of the next layer and scans its in-edges IN CSC ORDER, which keeps igraph's relaxation order
 // and tie rule (strict <, then smaller dist[src]) bit for bit.
-template <bool ZONE, bool COSTF = false>
+// DENSE: lattices with several in-edges per node keep two edge records in flight (6 % on the shipped lattice); sparse ones
+// (mostly 0 or 1 in-edge: the "216 x 11" / "430 x 21" parameter sets) run the plain loop, which is faster there
+template <bool ZONE, bool COSTF = false, bool DENSE = false>
 __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int start_layer, int start_node, int n_steps,
                                       const unsigned* mask, int e_base, int rem_layer, int rem_lo, int rem_hi,
                                       int li_begin, int snap_at, const unsigned* zone, int zone_s0 = -1) {
@@ -248,15 +250,12 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
             if (ZONE && present && zs) present = !((zs[(nbase + j) >> 5] >> ((nbase + j) & 31)) & 1u);
             if (present) {
                 const int2 io = lt.in_off[nbase + j];
-                #pragma unroll 1
-                for (int k = 0; k < io.y; ++k) {
-                    const int e = io.x + k;
-                    const LtplEdgeRec r = lt.edge_rec[e];
+                auto relax = [&](const LtplEdgeRec& r, int e) {
                     const double ds = dcur[r.src];
-                    if (!(ds < LTPL_INF)) continue;
+                    if (!(ds < LTPL_INF)) return;
                     if (mask) {
                         const int idx = e + moff;
-                        if ((mask[idx >> 5] >> (idx & 31)) & 1u) continue;
+                        if ((mask[idx >> 5] >> (idx & 31)) & 1u) return;
                     }
                     double cost = r.cost;
                     if (COSTF) {   // offline_cost *= factor on this tick's copy of the planning range (GB:505-508)
@@ -272,7 +271,17 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
                     } else if (alt == best && ds == best_ds) {
                         tie = 1;
                     }
+                };
+                // in-edges in CSC order (igraph's relaxation order); nodes with many in-edges keep two records in flight
+                int k = 0;
+                #pragma unroll 1
+                for (; DENSE && k + 1 < io.y; k += 2) {
+                    const LtplEdgeRec ra = lt.edge_rec[io.x + k], rb = lt.edge_rec[io.x + k + 1];
+                    relax(ra, io.x + k);
+                    relax(rb, io.x + k + 1);
                 }
+                #pragma unroll 1
+                for (; k < io.y; ++k) relax(lt.edge_rec[io.x + k], io.x + k);
             }
             dnxt[j] = best;
             c.pred[li * maxn + j] = (unsigned char)best_k;
@@ -378,12 +387,15 @@ __device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, un
     const int s0 = lt.samp_off[e0], s1 = lt.samp_off[e1];
     const int moff = (e0 >= e_base) ? -e_base : lt.E - e_base;
     #pragma unroll 1
-    for (int s = s0 + lane; s < s1; s += 128) {
+    for (int sb = s0; sb < s1; sb += 128) {
+        const int s = sb + lane;
         double2 p[4];
+        int ed[4];   // owning edge of every sample, loaded together with it (a hit does not wait for a second round trip)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int si = s + 32 * u;
-            p[u] = lt.samp_xy[(si < s1) ? si : s];
+            p[u] = lt.samp_xy[(si < s1) ? si : sb];
+            ed[u] = lt.samp_edge[(si < s1) ? si : sb];
         }
         unsigned hit = 0;
         #pragma unroll 1
@@ -400,7 +412,7 @@ __device__ __forceinline__ void block_pair(const LatDev& lt, int lane, int a, un
         for (int u = 0; u < 4; ++u) {
             const int si = s + 32 * u;
             if (((hit >> u) & 1u) && si < s1) {
-                const int idx = lt.samp_edge[si] + moff;
+                const int idx = ed[u] + moff;
                 atomicOr(&mask[idx >> 5], 1u << (idx & 31));
             }
         }
@@ -438,7 +450,7 @@ __device__ __forceinline__ int disc_pairs(const LatDev& lt, int o, int p_start, 
 // STATE: stateful tick (ltpl_state.cuh): start node / constant segment come from k_state, the constant segment lives in
 // the previous tick's path planes, pos_est and the last action id enter the action-set logic, the first edges of the
 // last solution are cheaper
-template <bool ZONE, bool STATE = false>
+template <bool ZONE, bool STATE = false, bool DENSE = false>
 __global__ void __launch_bounds__(LTPL_WARPS_PER_CTA * 32, LTPL_PLAN_MINB)
 k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffers bf, const int maxn, const int hl,
        const int mask_words) {
@@ -782,7 +794,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             } else {
                 const int li_begin = (f == 3 && c.snap_li >= 1) ? c.snap_li + 1 : 1;
                 const int snap_at = (f == 2 && a + 1 < n_act && filt[a + 1] == 3) ? closest_dist - 1 : 0;
-                reach = dp_run<ZONE, STATE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
+                reach = dp_run<ZONE, STATE, DENSE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
                                rem_layer, rem_lo, rem_hi, li_begin, snap_at, zone, zone_s0);
                 tie = c.tie;
             }
