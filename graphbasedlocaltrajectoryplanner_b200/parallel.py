@@ -6,7 +6,8 @@ crosses GPUs is bookkeeping around it:
   * ``broadcast_lattice``  -- rank 0 packs the read-only lattice blob once, every other rank receives the bytes
     (NCCL broadcast on the device, over NVLink 5 / NVSwitch) and builds its own handle on them;
   * ``PeerGather``         -- the gather of the action sets into ONE consumer rank without a collective call: every rank's
-    export kernels (k_export, k_emergency) store their fp32 rows straight into the consumer's HBM through a peer pointer
+    exporting kernels (k_vel_res on first ticks, k_export on stateful ticks, k_emergency) store their fp32 rows straight
+    into the consumer's HBM through a peer pointer
     (symmetric memory over NVLink), so only LIVE rows cross the fabric, fused into the kernel that produces them; one
     small peer copy of the per-path arrays and one device-side barrier per tick complete it;
   * ``gather_rows``        -- the same gather with point-to-point sends of the live rows (row counts are exchanged
@@ -95,7 +96,7 @@ class PeerGather(object):
 
     Every rank owns one region of a symmetric-memory buffer on ``dst``: [rows_cap][n_export][7] fp32 rows followed by a
     copy of the packed per-path arrays (BatchPlanner.d_meta_raw: traj_len, traj_id, action_id, traj_row, queue_cnt, ...).
-    ``attach`` points the planner's export buffer (LtplBuffers.traj) at the peer region, so k_export / k_emergency store
+    ``attach`` points the planner's export buffer (LtplBuffers.traj) at the peer region, so the exporting kernels store
     their rows over NVLink while they compute them -- the compact row index comes from the rank-local counter, only
     live rows move.  ``finish`` (on the planner's stream, after the tick) copies the per-path arrays into the region and
     runs the device-side barrier of the symmetric-memory handle; behind it the consumer may read every region."""
