@@ -306,6 +306,84 @@ __device__ __forceinline__ int dp_run(const LatDev& lt, int lane, DpCtx& c, int 
     return reach;
 }
 
+// The 'overtake_left' / 'overtake_right' pair (MOPG:148-159) on lattices with <= 16 nodes per layer: the two searches only
+// differ in which nodes of the object's layer are removed, and a layer leaves half of the warp idle -- lanes 0-15 carry
+// the search without the nodes [split, n_l) (left), lanes 16-31 the one without [0, split) (right), in ONE loop over the
+// layers.  Halves of the dist rows / pred rows at offset 16 hold the second search.  Returns the steps of the first
+// search; *reach_b, *tie_b those of the second.
+template <bool ZONE, bool COSTF>
+__device__ __forceinline__ int dp_run_pair(const LatDev& lt, int lane, DpCtx& c, int start_layer, int start_node,
+                                           int n_steps, const unsigned* mask, int e_base, int rem_layer, int split,
+                                           const unsigned* zone, int zone_s0, int* reach_b, int* tie_b) {
+    const int maxn = c.maxn;   // 32
+    const int half = lane >> 4, j = lane & 15, hoff = half << 4;
+    int tie = 0;
+    c.dist[lane] = (j == start_node) ? 0.0 : LTPL_INF;
+    __syncwarp();
+    int cur = 0, reach_a = 0, reach_2 = 0;
+    int layer = start_layer;
+    #pragma unroll 1
+    for (int li = 1; li <= n_steps; ++li) {
+        int nxt = layer + 1;
+        if (nxt >= lt.L) nxt = 0;
+        const int4 mt = c.meta[li];
+        const int nbase = mt.x, nl = mt.y;
+        const int moff = (mt.z >= e_base) ? -e_base : lt.E - e_base;
+        const unsigned* zs = (ZONE && zone && !zone_unblocked(nxt, zone_s0, lt.L)) ? zone : nullptr;
+        const double* dcur = c.dist + cur * maxn + hoff;
+        double* dnxt = c.dist + (cur ^ 1) * maxn + hoff;
+        double best = LTPL_INF, best_ds = LTPL_INF;
+        int best_k = 255;
+        bool present = j < nl && !(nxt == rem_layer && (half ? (j < split) : (j >= split)));
+        if (ZONE && present && zs) present = !((zs[(nbase + j) >> 5] >> ((nbase + j) & 31)) & 1u);
+        if (present) {
+            const int2 io = lt.in_off[nbase + j];
+            #pragma unroll 1
+            for (int k = 0; k < io.y; ++k) {
+                const int e = io.x + k;
+                const LtplEdgeRec r = lt.edge_rec[e];
+                const double ds = dcur[r.src];
+                if (!(ds < LTPL_INF)) continue;
+                if (mask) {
+                    const int idx = e + moff;
+                    if ((mask[idx >> 5] >> (idx & 31)) & 1u) continue;
+                }
+                double cost = r.cost;
+                if (COSTF) {
+                    if (e == c.fe0) cost = __dmul_rn(cost, c.ff0);
+                    else if (e == c.fe1) cost = __dmul_rn(cost, c.ff1);
+                    else if (e == c.fe2) cost = __dmul_rn(cost, c.ff2);
+                }
+                const double alt = __dadd_rn(ds, cost);
+                if (alt < best || (alt == best && ds < best_ds)) {
+                    best = alt;
+                    best_ds = ds;
+                    best_k = r.src;
+                } else if (alt == best && ds == best_ds) {
+                    tie = 1;
+                }
+            }
+        }
+        dnxt[j] = best;
+        c.pred[li * maxn + lane] = (unsigned char)best_k;
+        const unsigned alive = __ballot_sync(LTPL_FULL, best_k != 255);
+        __syncwarp();
+        if (!alive) break;
+        // a search without a reachable node in this layer has none in any later layer either (all its distances are inf)
+        if ((alive & 0xffffu) && reach_a == li - 1) reach_a = li;
+        if ((alive >> 16) && reach_2 == li - 1) reach_2 = li;
+        cur ^= 1;
+        layer = nxt;
+    }
+    c.cur = cur;
+    c.layer = layer;
+    const unsigned tb = __ballot_sync(LTPL_FULL, tie != 0);
+    c.tie = (tb & 0xffffu) ? 1 : 0;
+    *tie_b = (tb >> 16) ? 1 : 0;
+    *reach_b = reach_2;
+    return reach_a;
+}
+
 // the lattice edge (src node js of the layer before) -> (node jd of the layer whose first node is nbase); the lattice
 // holds at most one edge per node pair
 __device__ __forceinline__ int dp_edge_id(const LatDev& lt, int nbase, int jd, int js) {
@@ -318,11 +396,11 @@ __device__ __forceinline__ int dp_edge_id(const LatDev& lt, int nbase, int jd, i
 }
 
 // virtual goal node: argmin_j dist[j] + |raceline_index - j| * lat_resolution * w_virt_goal (GB:188)
-__device__ __forceinline__ int dp_goal(const LatDev& lt, int lane, const DpCtx& c, int* tie_out) {
+__device__ __forceinline__ int dp_goal(const LatDev& lt, int lane, const DpCtx& c, int* tie_out, int off = 0) {
     const int layer = c.layer;
     const int nl = lt.node_off[layer + 1] - lt.node_off[layer];
     const int rl = lt.rl_idx[layer];
-    const double* d = c.dist + c.cur * c.maxn;
+    const double* d = c.dist + c.cur * c.maxn + off;   // off = 16: the second search of dp_run_pair
     double best = LTPL_INF, best_ds = LTPL_INF;
     int best_j = 0x7fffffff, tie = 0;
     #pragma unroll 1
@@ -761,6 +839,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
     const int tab_row = lt.node_off[start_layer] + start_node;
     int mod_steps = goal_steps;
     int prev_q = -1, prev_f = -1, prev_reach = 0;
+    int pair_reach = -1, pair_tie = 0;   // second search of an 'overtake_left' / 'overtake_right' pair (dp_run_pair)
     #pragma unroll 1
     for (int a = 0; a < n_act; ++a) {
         int name = names[a];
@@ -781,7 +860,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         if (src == 0 && (tr & 0xff) > mod_steps) src = 1;  // table rows end at their own goal layer (open track only)
         if (ZONE && src == 0 && zone) src = 1;              // the table holds searches on the zone-free lattice
         if (STATE && src == 0 && n_fe > 0) src = 1;         // ... with the offline costs
-        int st = 0, tie = 0, found = 0, reach = 0;
+        int st = 0, tie = 0, found = 0, reach = 0, goal_off = 0;
         if (mod_steps > 0) {
             const bool start_removed = (rem_layer == start_layer && start_node >= rem_lo && start_node < rem_hi);
             if (start_removed) {
@@ -792,11 +871,22 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
             } else if (src == 2) {
                 reach = prev_reach;
             } else {
-                const int li_begin = (f == 3 && c.snap_li >= 1) ? c.snap_li + 1 : 1;
-                const int snap_at = (f == 2 && a + 1 < n_act && filt[a + 1] == 3) ? closest_dist - 1 : 0;
-                reach = dp_run<ZONE, STATE, DENSE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask, e_base,
-                               rem_layer, rem_lo, rem_hi, li_begin, snap_at, zone, zone_s0);
-                tie = c.tie;
+                const bool with_next = (f == 2 && a + 1 < n_act && filt[a + 1] == 3);
+                if (f == 3 && pair_reach >= 0) {          // searched together with 'overtake_left' (dp_run_pair)
+                    reach = pair_reach;
+                    tie = pair_tie;
+                    goal_off = 16;
+                } else if (with_next && maxn == 32 && lt.max_nodes <= 16) {
+                    reach = dp_run_pair<ZONE, STATE>(lt, lane, c, start_layer, start_node, mod_steps, mask, e_base, con_layer,
+                                                     con_node, zone, zone_s0, &pair_reach, &pair_tie);
+                    tie = c.tie;
+                } else {
+                    const int li_begin = (f == 3 && c.snap_li >= 1) ? c.snap_li + 1 : 1;
+                    const int snap_at = with_next ? closest_dist - 1 : 0;
+                    reach = dp_run<ZONE, STATE, DENSE>(lt, lane, c, start_layer, start_node, mod_steps, (f == 0) ? nullptr : mask,
+                                                       e_base, rem_layer, rem_lo, rem_hi, li_begin, snap_at, zone, zone_s0);
+                    tie = c.tie;
+                }
             }
             LTPL_PH(21)
             if (name == LTPL_ACT_FOLLOW || name == LTPL_ACT_STRAIGHT) {
@@ -848,7 +938,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
         }
         if (found) {
             int gj = 0;
-            if (src == 1) gj = dp_goal(lt, lane, c, &tie);
+            if (src == 1) gj = dp_goal(lt, lane, c, &tie, goal_off);
             if (tie) st |= LTPL_ST_TIE_AMBIGUOUS;
             st |= LTPL_ST_FOUND;
             if (STATE && src != 2) {   // constant nodes in front of the start node: the memory of the last tick (OTH:462-466)
@@ -869,7 +959,7 @@ k_plan(const LatDev lt, const LtplParams prm, const LtplDims dm, const LtplBuffe
                     for (int li = reach; li >= 1; --li) {
                         nd[2 * (li + cnd)] = layer;
                         nd[2 * (li + cnd) + 1] = j;
-                        j = pred[li * maxn + j];
+                        j = pred[li * maxn + goal_off + j];
                         layer = (layer == 0) ? lt.L - 1 : layer - 1;
                     }
                 }
