@@ -250,47 +250,6 @@ __device__ __noinline__ ArgMinD warp_closest_point_grid(const LatDev& lt, const 
     return warp_closest_point(pts, n, px, py, lane);
 }
 
-// get_s_coord.py:8-99 on a CLOSED polyline with explicit s_array (s_array[0] <= 0.05, i.e. no leading-zero insertion).
-// Warp-collective; returns the s coordinate; idx_out = closest_indexes (pair)
-__device__ __noinline__ double s_coord_closed(const LatDev& lt, const int* __restrict__ grid,
-                                                 const double2* __restrict__ pts, const double* __restrict__ s_arr, int n,
-                                                 double px, double py, int lane, int* i0_out, int* i1_out) {
-    ArgMinD m = warp_closest_point_grid(lt, grid, pts, n, px, py, lane);
-    int nb = m.i;
-    int idx1 = nb - 1;  // python negative index -> last element
-    int idx2 = nb + 1;
-    if (idx2 > n - 1) idx2 = 0;
-    int a1 = (idx1 < 0) ? idx1 + n : idx1;
-    double2 pn = pts[nb], p1 = pts[a1], p2 = pts[idx2];
-    const AngCmp ac = angle_cmp(pn, px, py, p1, p2);
-    double2 a, b;
-    double sbase;
-    if (ac.gt) {
-        a = p1;
-        b = pn;
-        sbase = s_arr[a1];
-    } else {
-        a = pn;
-        b = p2;
-        sbase = s_arr[nb];
-    }
-    double bax = b.x - a.x, bay = b.y - a.y;
-    double t = __ddiv_rn(__dadd_rn(__dmul_rn(px - a.x, bax), __dmul_rn(py - a.y, bay)), __dadd_rn(sq_rn(bax), sq_rn(bay)));
-    double sx = __dadd_rn(a.x, __dmul_rn(t, bax));
-    double sy = __dadd_rn(a.y, __dmul_rn(t, bay));
-    double ds = sqrt(__dadd_rn(sq_rn(a.x - sx), sq_rn(a.y - sy)));
-    if (i0_out) {
-        if (ac.ge) {
-            *i0_out = idx1;
-            *i1_out = nb;
-        } else {
-            *i0_out = nb;
-            *i1_out = idx2;
-        }
-    }
-    return __dadd_rn(sbase, ds);
-}
-
 // ---- one query PER LANE -------------------------------------------------------------------------------------------
 // The searches of a scenario (constant-segment ends, every object, every disc) are independent of each other; run one
 // per lane, their dependent load -> compare -> load chains overlap instead of following each other warp-wide.
@@ -336,7 +295,8 @@ __device__ __forceinline__ int lanes_closest_point(const LatDev& lt, const int* 
     return res;
 }
 
-// get_s_coord.py:48-99 behind the nearest vertex nb (closed polyline, explicit s_array): per lane
+// get_s_coord.py:8-99 behind the nearest vertex nb, on a CLOSED polyline with explicit s_array (s_array[0] <= 0.05, i.e.
+// no leading-zero insertion): neighbour choice by the larger angle (:48-58), foot of the perpendicular, s; per lane
 __device__ __forceinline__ double s_coord_from_vertex(const double2* __restrict__ pts, const double* __restrict__ s_arr,
                                                       int n, int nb, double px, double py) {
     int idx2 = nb + 1;
